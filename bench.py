@@ -1,0 +1,334 @@
+#!/usr/bin/env python
+"""Benchmark of the pgm-vae hot path on B200 (see BASELINE.md / SURVEY.md 8d).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg3|cfg1]
+
+A "step" is one training step (forward, MSE + VQ loss, backward, Adam, EMA codebook update)
+over one batch of synthetic binary data.  Default workload = BASELINE.json configs[1]
+("cfg2": 69 variables, units 50/40/30/20, K=128, D=16, EMA, batch 4096 per GPU).
+Prints ONE JSON line on rank 0.
+
+  value      whole-job training samples/s, batches already resident in HBM (device pointers)
+  e2e        the same through the public API (core.model.VqVAE.train_on_batch) with PINNED HOST
+             batches: H2D copy of the batch and D2H read of the loss inside every step
+  roofline   the dominant kernel of the step, from a per-kernel CUDA-event pass over the same steps
+  cpu_baseline / --impl reference : the CPU restatement of the reference (oracle/, torch-CPU fp32;
+             TensorFlow itself is not installable in this image) timed on the host cores
+  pll_eval   stage 2 (encoder + VQ assignment + histogram) samples/s, device-resident and e2e
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "pgm-vae_b200"))
+
+WORKLOADS = {
+    # name: (V, units, D, K, per-GPU batch, description)
+    "cfg1": (16, [15, 14, 13, 12], 4, 32, 256, "cfg1: nltcs shape, 16 vars, units 15/14/13/12, K=32 D=4 EMA, batch 256"),
+    "cfg2": (69, [50, 40, 30, 20], 16, 128, 4096,
+             "cfg2: synthetic 69-var binary data (plants-scale), units 50/40/30/20, K=128 D=16 EMA, batch 4096"),
+    "cfg3": (1556, [400, 200, 100, 50], 64, 512, 4096,
+             "cfg3: synthetic 1556-var binary data, units 400/200/100/50, K=512 D=64 EMA, batch 4096 per GPU"),
+}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d["hbm_gbs"], d.get("bf16_tflops_sustained", d["bf16_tflops"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, 1590.0, "fallback (B200_PROFILING.md)"
+
+
+def flops_per_sample(V, units, D, K):
+    """dense fwd + bwd (no dgrad for layer 0) + VQ distance contraction."""
+    chain = [V - 1] + units + [D] + units[::-1] + [V - 1]
+    macs = [chain[i] * chain[i + 1] for i in range(10)]
+    fwd = 2 * V * sum(macs)
+    bwd = 2 * V * (2 * sum(macs) - macs[0])
+    return fwd + bwd + 2 * V * D * K, 2 * V * (sum(macs[:5]) + D * K)
+
+
+# --------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.proc, self.path = None, f"/tmp/pgmvae_clocks_{os.getpid()}.csv"
+        try:
+            self.f = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.f.close()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path):
+            parts = [t.strip() for t in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1])); power.append(float(parts[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        try:
+            os.remove(self.path)
+        except OSError:
+            pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "power_w_max": max(power),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------- reference arm (CPU)
+def cpu_train_samples_per_s(V, units, D, K, B, steps, warmup, seed=0):
+    """Times the oracle's training step (the CPU restatement of the reference) on the host."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import torch
+    import pgmvae_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    m = O.OracleVqVAE(units, V, D, K, cost=0.25, decay=0.99, ema=True, seed=seed)
+    y = O.synthetic_binary(B * 2, V, seed=seed)
+    xs = [O.make_xs(y[:B]), O.make_xs(y[B:])]
+    for i in range(warmup):
+        m.train_step(xs[i % 2], lr=1e-3)
+    t0 = time.perf_counter()
+    for i in range(steps):
+        m.train_step(xs[i % 2], lr=1e-3)
+    dt = time.perf_counter() - t0
+    return B * steps / dt, dt / steps, cores
+
+
+def run_reference(args, wl):
+    V, units, D, K, B, desc = wl
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    # bounded sample: largest per-step batch such that the whole run stays within ~2.5 minutes
+    sps, t_probe, cores = cpu_train_samples_per_s(V, units, D, K, min(B, 128), 1, 1)
+    per_sample = t_probe / min(B, 128)
+    Bref = B
+    while Bref > 64 and (args.steps + args.warmup) * per_sample * Bref > 150.0:
+        Bref //= 2
+    sps, t_step, cores = cpu_train_samples_per_s(V, units, D, K, Bref, args.steps, args.warmup)
+    sample = f"{args.steps} training steps of batch {Bref} (full workload batch {B})"
+    line = {
+        "impl": "reference", "metric": "train_samples_per_s", "value": sps, "unit": "samples/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_step * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": desc, "per_step_batch": Bref,
+                   "note": "CPU restatement of the reference (oracle/pgmvae_oracle.py, torch-CPU fp32); "
+                           "TensorFlow, which the reference needs, is not installable in this image"},
+        "cpu_baseline": {"value": sps, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": sps, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------- our arm
+def run_ours(args, wl):
+    V, units, D, K, B, desc = wl
+    from pgmvae import _ffi, data, dist
+    from core.model import VqVAE, Adam
+    import ctypes as C
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    ctx = _ffi.get_context(local)
+    comm, rank, world = dist.init_from_env(ctx)
+    if world != args.gpus and rank == 0:
+        print(f"warning: --gpus {args.gpus} but WORLD_SIZE={world}", file=sys.stderr)
+    L = _ffi.lib()
+
+    def barrier():
+        ctx.sync()
+        if world > 1:
+            import torch.distributed as tdist
+            tdist.barrier()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        import torch
+        import torch.distributed as tdist
+        t = torch.tensor([x], dtype=torch.float64)
+        tdist.all_reduce(t, op=tdist.ReduceOp.MAX)
+        return float(t[0])
+
+    model = VqVAE(units, V, D, K, cost=0.25, decay=0.99, ema=True, seed=0, max_batch=B, device=local, comm=comm)
+    model.compile(optimizer=Adam(lr=1e-3), loss="mse", metrics=["mae"])
+    gB = B * world
+    nb = 8                                              # distinct batches, rotated
+    y = data.synthetic_binary(nb * B, V, seed=1000 + rank)
+    y_dev = _ffi.DeviceArray.from_numpy(ctx, y)
+    comm_h = comm.h if comm is not None else None
+    lr = C.c_float(1e-3)
+
+    def step_dev(i, met=None):
+        off = (i % nb) * B * V
+        _ffi.check(L.pgmvae_model_train_step(model._h, y_dev.ptr + off, 1, B, gB, lr, comm_h, 0, met))
+
+    # ---- device-resident timing ("value")
+    for i in range(args.warmup):
+        step_dev(i)
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    l0 = ctx.launches
+    ctx.timer_start()
+    for i in range(args.steps):
+        step_dev(i)
+    ms = ctx.timer_stop_ms()
+    launches = ctx.launches - l0
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    ms = max_over_ranks(ms)
+    value = gB * args.steps / (ms * 1e-3)
+    met = (C.c_double * 4)()
+    step_dev(0, met)
+    assert all(np.isfinite(v) for v in met), "non-finite loss"
+
+    # ---- end-to-end through the public API, pinned host batches
+    hp = C.c_void_p()
+    _ffi.check(L.pgmvae_malloc_host(ctx.h, nb * B * V, C.byref(hp)))
+    pinned = np.ctypeslib.as_array(C.cast(hp, C.POINTER(C.c_uint8)), shape=(nb * B, V))
+    pinned[:] = y
+    for i in range(max(3, args.warmup)):
+        model.train_on_batch(pinned[(i % nb) * B:(i % nb + 1) * B], global_batch=gB, sync=True)
+    barrier()
+    ctx.timer_start()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        model.train_on_batch(pinned[(i % nb) * B:(i % nb + 1) * B], global_batch=gB, sync=True)
+    e2e_ms = ctx.timer_stop_ms()
+    e2e_wall = (time.perf_counter() - t0) * 1e3
+    barrier()
+    e2e_ms = max_over_ranks(max(e2e_ms, e2e_wall))
+    e2e_value = gB * args.steps / (e2e_ms * 1e-3)
+
+    # ---- per-kernel pass (CUDA events around every launch of the same steps) -> roofline of the top kernel
+    ctx.profile_begin()
+    psteps = min(args.steps, 10)
+    for i in range(psteps):
+        step_dev(i)
+    prof = ctx.profile_end()
+    hbm_peak, tc_peak, peak_src = peaks()
+    tot_ms = sum(k["ms"] for k in prof) or 1.0
+    prof.sort(key=lambda k: -k["ms"])
+    top = prof[0]
+    avg_ms = top["ms"] / top["launches"]
+    gbs = top["bytes"] / top["launches"] / (avg_ms * 1e-3) / 1e9
+    tfs = top["flops"] / top["launches"] / (avg_ms * 1e-3) / 1e12
+    intensity = top["flops"] / max(top["bytes"], 1.0)
+    tensor_bound = intensity > (tc_peak * 1e12) / (hbm_peak * 1e9) and top["name"].endswith("_tc")
+    roofline = {
+        "kernel": top["name"], "bound": "tensor" if tensor_bound else "hbm",
+        "achieved": tfs if tensor_bound else gbs, "peak": tc_peak if tensor_bound else hbm_peak,
+        "unit": "TFLOP/s" if tensor_bound else "GB/s",
+        "frac": (tfs / tc_peak) if tensor_bound else (gbs / hbm_peak), "traffic": None,
+        "peak_source": peak_src, "avg_launch_ms": avg_ms, "launches_per_step": top["launches"] / psteps,
+        "share_of_step": top["ms"] / tot_ms, "algorithmic_bytes_per_launch": top["bytes"] / top["launches"],
+        "algorithmic_flops_per_launch": top["flops"] / top["launches"],
+        "method": "CUDA events around every library launch over %d of the timed steps (separate pass)" % psteps,
+        "kernels": [{"name": k["name"], "ms_per_step": k["ms"] / psteps, "share": k["ms"] / tot_ms,
+                     "GBps": k["bytes"] / max(k["ms"], 1e-9) / 1e6, "TFLOPs": k["flops"] / max(k["ms"], 1e-9) / 1e9}
+                    for k in prof],
+    }
+
+    # ---- stage 2: PLL evaluation (encoder + assignment + histogram)
+    n_eval = nb * B
+    n1 = np.zeros((V, K), np.uint64)
+    n0 = np.zeros((V, K), np.uint64)
+    reps = max(2, min(10, args.steps))
+    _ffi.check(L.pgmvae_model_count(model._h, y_dev.ptr, 1, n_eval, n1.ctypes.data, n0.ctypes.data))
+    barrier()
+    ctx.timer_start()
+    for _ in range(reps):
+        _ffi.check(L.pgmvae_model_count(model._h, y_dev.ptr, 1, n_eval, n1.ctypes.data, n0.ctypes.data))
+    pll_ms = max_over_ranks(ctx.timer_stop_ms())
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        model.dist = model.cpt(pinned)
+        pll = model.pseudo_log_likelihood(pinned, total=n_eval * world)
+    pll_e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / 2.0)      # two passes over the data per rep
+    assert (n1 + n0).sum() == n_eval * V
+    pll_eval = {"metric": "pll_eval_samples_per_s", "value": world * n_eval * reps / (pll_ms * 1e-3),
+                "e2e_value": world * n_eval * reps / (pll_e2e_ms * 1e-3), "unit": "samples/s",
+                "samples_per_pass": world * n_eval, "pll": pll}
+    _ffi.check(L.pgmvae_free_host(ctx.h, hp))
+
+    if rank != 0:
+        return
+    # ---- CPU baseline beside it (rank 0, N == 1 only): bounded sample of the same workload
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        Bc = B
+        sps, t_probe, cores = cpu_train_samples_per_s(V, units, D, K, min(B, 128), 1, 1)
+        while Bc > 64 and 4 * (t_probe / min(B, 128)) * Bc > 25.0:
+            Bc //= 2
+        sps, t_step, cores = cpu_train_samples_per_s(V, units, D, K, Bc, 3, 1)
+        cpu = {"value": sps, "unit": "samples/s", "cores": cores, "kind": "port",
+               "sample": f"3 training steps of batch {Bc} after 1 warm-up (torch-CPU fp32 oracle, {cores} threads)"}
+    train_fl, pll_fl = flops_per_sample(V, units, D, K)
+    line = {
+        "metric": "train_samples_per_s", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": desc, "per_gpu_batch": B, "global_batch": gB, "parallelism": f"dp{world}",
+                   "l2": "per-step working set (activations + gradients, >400 MB at cfg2) exceeds the 126 MB L2; "
+                         "8 distinct input batches rotated",
+                   "flop_per_sample_train": train_fl, "flop_per_sample_pll": pll_fl,
+                   "achieved_tflops": value * train_fl / 1e12, "device_bytes": model.device_bytes()},
+        "roofline": roofline, "cpu_baseline": cpu,
+        "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": B * V, "d2h_bytes_per_step": 32,
+                "ms_per_step": e2e_ms / args.steps},
+        "gpu_launches": launches, "clocks": clocks, "pll_eval": pll_eval,
+        "loss_after": {"loss": met[0], "mse": met[1], "mae": met[2], "vq_loss": met[3]},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, wl)
+    else:
+        run_ours(args, wl)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,356 @@
+"""VqVAE on B200 -- host mirror of the reference ``core/model.py`` (VqVAE, :14-148).
+
+Same constructor ``VqVAE(units, nvar, dim, k, cost=0.5, decay=0.99, ema=True)``, same
+attributes (``fd0..fd9``, ``vq_layer``, ``dist``) and methods (``__call__``, ``compile``,
+``fit``, ``count``, ``cpt``, ``pseudo_log_likelihood``, ``get_probability``).  All state
+lives in HBM inside a ``pgmvae_model`` handle of libpgmvae.so; one Keras fit step
+(run.py:62) is one ``pgmvae_model_train_step`` call and ``count`` (core/model.py:58-82) is
+one ``pgmvae_model_count`` call.  No TensorFlow, no CPU fallback.
+
+Inputs: the reference feeds the materialised leave-one-out tensor ``x [N, V, V-1]``
+(run.py:48-50).  Every method here accepts that tensor *or* the raw data matrix
+``y [N, V]`` (0/1) from which it is built; the kernels only ever read ``y``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import json
+import os
+import time
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+
+from pgmvae import _ffi
+from core.dense import FatDense
+from core.quantizer import VectorQuantizer, VectorQuantizerEMA
+
+
+class Adam:
+    """Stand-in for ``tf.keras.optimizers.Adam(lr=...)`` (run.py:60): carries the learning
+    rate; the update itself is the fused Adam kernel (Keras form, eps=1e-7 added to sqrt(v))."""
+
+    def __init__(self, lr=0.001, learning_rate=None, **kwargs):
+        self.learning_rate = float(learning_rate if learning_rate is not None else lr)
+        self.lr = self.learning_rate
+
+
+class History:
+    def __init__(self):
+        self.history: Dict[str, List[float]] = {"loss": [], "mae": []}
+        self.epoch: List[int] = []
+
+
+def to_y(x) -> np.ndarray:
+    """uint8 data matrix [N,V] from either y [N,V] or the reference's x [N,V,V-1]
+    (row v of a sample = y without element v, run.py:46-50)."""
+    a = x.numpy() if isinstance(x, _ffi.DeviceArray) else x
+    if hasattr(a, "detach") and hasattr(a, "cpu"):
+        a = a.detach().cpu().numpy()
+    a = np.asarray(a)
+    if a.ndim == 3:
+        n, v, vm1 = a.shape
+        if vm1 != v - 1:
+            raise ValueError(f"expected leave-one-out inputs [N,V,V-1], got {a.shape}")
+        y = np.empty((n, v), dtype=a.dtype)
+        y[:, 0] = a[:, 1, 0]           # row 1 drops element 1, so it starts with y0
+        y[:, 1:] = a[:, 0, :]          # row 0 drops element 0
+        a = y
+    if a.ndim != 2:
+        raise ValueError(f"expected y [N,V] or x [N,V,V-1], got shape {a.shape}")
+    if a.dtype != np.uint8:
+        a = (a != 0).astype(np.uint8)
+    return np.ascontiguousarray(a)
+
+
+class VqVAE:
+    """Many independent per-variable auto-encoders packed in one network around a
+    per-variable VQ codebook (reference core/model.py:14-55)."""
+
+    def __init__(self, units, nvar, dim, k, cost=0.5, decay=0.99, ema=True, *, seed=0, max_batch=1024,
+                 device: Optional[int] = None, comm=None):
+        if len(units) != 4:
+            raise ValueError("units must list the 4 hidden widths (core/model.py:21-24 indexes units[0..3])")
+        self.name = "vq_vae"
+        self.units, self.nvar, self.dim, self.k = [int(u) for u in units], int(nvar), int(dim), int(k)
+        self.cost, self.decay, self.ema, self.seed = float(cost), float(decay), bool(ema), int(seed)
+        self.epsilon = 1e-5
+        self.ctx = _ffi.get_context(device)
+        self.comm = comm
+        self._h = C.c_void_p()
+        self.max_batch = 0
+        self._create(int(max_batch))
+        _ffi.check(_ffi.lib().pgmvae_model_init(self._h, C.c_uint64(self.seed)))
+        act, init = "selu", "he_uniform"
+        widths = self.units + [self.dim] + self.units[::-1]
+        self._layers = []
+        for i in range(9):
+            self._layers.append(FatDense(widths[i], activation=act, kernel_initializer=init))
+        self._layers.append(FatDense(self.nvar - 1, activation="sigmoid", kernel_initializer="glorot_uniform"))
+        for i, l in enumerate(self._layers):
+            l._bind(self, i)
+            setattr(self, f"fd{i}", l)
+        if self.ema:
+            self.vq_layer = VectorQuantizerEMA(embedding_dim=dim, num_embeddings=k, commitment_cost=cost, decay=decay,
+                                               num_var=nvar)
+        else:
+            self.vq_layer = VectorQuantizer(embedding_dim=dim, num_embeddings=k, commitment_cost=cost, num_var=nvar)
+        self.vq_layer._bind(self)
+        self.dist = np.zeros((self.nvar, self.k), dtype=np.float64)        # core/model.py:37
+        self.losses: List[float] = []
+        self.optimizer: Optional[Adam] = None
+        self._adam_t = 0
+        self._ema_steps = 0
+
+    # ---- handle management -------------------------------------------------------
+    def _create(self, max_batch: int):
+        units = (C.c_int * 4)(*self.units)
+        h = C.c_void_p()
+        _ffi.check(_ffi.lib().pgmvae_model_create(self.ctx.h, units, self.nvar, self.dim, self.k, self.cost, self.decay,
+                                                  self.epsilon, int(self.ema), max_batch, C.byref(h)))
+        self._h, self.max_batch = h, max_batch
+
+    def _ensure_capacity(self, batch: int):
+        """The workspace is sized for max_batch samples; grow it (state is carried over)."""
+        if batch <= self.max_batch:
+            return
+        state = self.state_dict()
+        old = self._h
+        self._create(int(batch))
+        _ffi.lib().pgmvae_model_destroy(old)
+        self.load_state_dict(state)
+
+    def tensor_names(self) -> List[str]:
+        names = [f"fd{i}.{s}" for i in range(10) for s in ("kernel", "bias")] + ["vq.embeddings"]
+        if self.ema:
+            names += ["vq.ema_w", "vq.ema_cluster_size", "vq.biased_w", "vq.biased_c"]
+        return names
+
+    def _tensor_shape(self, name: str):
+        V, D, K = self.nvar, self.dim, self.k
+        base = name.split(".", 1)[1] if name.split(".", 1)[0] in ("grad", "adam_m", "adam_v") else name
+        if base.startswith("fd"):
+            i = int(base[2])
+            chain = [V - 1] + self.units + [D] + self.units[::-1] + [V - 1]
+            return (V, chain[i], chain[i + 1]) if base.endswith("kernel") else (V, 1, chain[i + 1])
+        if base in ("vq.embeddings", "vq.ema_w", "vq.biased_w", "vq.stat_w"):
+            return (V, D, K)
+        return (V, K)
+
+    def _get_tensor(self, name: str) -> np.ndarray:
+        out = np.empty(self._tensor_shape(name), dtype=np.float32)
+        _ffi.check(_ffi.lib().pgmvae_model_get_tensor(self._h, name.encode(), out.ctypes.data, out.size))
+        return out
+
+    def _set_tensor(self, name: str, value):
+        v = np.ascontiguousarray(value, dtype=np.float32)
+        if v.shape != self._tensor_shape(name):
+            raise ValueError(f"{name}: expected shape {self._tensor_shape(name)}, got {v.shape}")
+        _ffi.check(_ffi.lib().pgmvae_model_set_tensor(self._h, name.encode(), v.ctypes.data, v.size))
+
+    def state_dict(self) -> Dict[str, np.ndarray]:
+        sd = {n: self._get_tensor(n) for n in self.tensor_names()}
+        train = [f"fd{i}.{s}" for i in range(10) for s in ("kernel", "bias")] + ([] if self.ema else ["vq.embeddings"])
+        for n in train:
+            sd["adam_m." + n] = self._get_tensor("adam_m." + n)
+            sd["adam_v." + n] = self._get_tensor("adam_v." + n)
+        sd["_adam_t"] = np.int64(self._adam_t)
+        sd["_ema_steps"] = np.int64(self._ema_steps)
+        return sd
+
+    def load_state_dict(self, sd: Dict[str, np.ndarray]):
+        for n, v in sd.items():
+            if not n.startswith("_"):
+                self._set_tensor(n, v)
+        if "_adam_t" in sd:
+            self._adam_t = int(sd["_adam_t"])
+            _ffi.check(_ffi.lib().pgmvae_model_set_adam_step(self._h, self._adam_t))
+        if "_ema_steps" in sd:
+            self._ema_steps = int(sd["_ema_steps"])
+            _ffi.check(_ffi.lib().pgmvae_model_set_ema_steps(self._h, self._ema_steps, self._ema_steps))
+
+    def set_weights_from(self, params: Dict[str, np.ndarray]):
+        """Inject reference-layout weights ({'fd0.kernel':..., 'vq.embeddings':...}); the EMA
+        shadow ``ema_w`` is re-initialised from the codebook (core/quantizer.py:117)."""
+        for n, v in params.items():
+            self._set_tensor(n, np.asarray(v, dtype=np.float32))
+        if self.ema and "vq.embeddings" in params and "vq.ema_w" not in params:
+            self._set_tensor("vq.ema_w", np.asarray(params["vq.embeddings"], dtype=np.float32))
+
+    # ---- forward -----------------------------------------------------------------
+    def __call__(self, inputs, training=None, code_only=False, fts=None):
+        """reference core/model.py:39-55."""
+        if fts is not None:
+            return self._call_fts(inputs, code_only, fts)
+        y = to_y(inputs)
+        B = y.shape[0]
+        self._ensure_capacity(B)
+        L = _ffi.lib()
+        if code_only:
+            idx = _ffi.DeviceArray(self.ctx, (self.nvar, B), np.int32, zero=False)
+            _ffi.check(L.pgmvae_model_encode(self._h, y.ctypes.data, 0, B, idx.ptr))
+            self.losses = [0.0]
+            return np.eye(self.k, dtype=np.float32)[idx.numpy()]           # one-hot [V,B,K]
+        Vp = (self.nvar + 7) // 8 * 8
+        out = _ffi.DeviceArray(self.ctx, (self.nvar, self.max_batch, Vp), np.float32, zero=False)
+        met = (C.c_double * 4)()
+        _ffi.check(L.pgmvae_model_forward(self._h, y.ctypes.data, 0, B, 1 if training else 0, out.ptr, met))
+        if training and self.ema:
+            self._ema_steps += 1
+        self.losses = [met[3]]
+        o = out.numpy()[:, :B, :self.nvar]                                   # [V,B,V] expanded
+        V = self.nvar
+        keep = ~np.eye(V, dtype=bool)
+        rec = o.transpose(1, 0, 2)[:, keep].reshape(B, V, V - 1)            # drop column v of net v
+        return np.ascontiguousarray(rec)
+
+    def _call_fts(self, inputs, code_only, fts):
+        """Sub-net path (core/model.py:41, ``fts`` branches of every layer): inputs [F,B,V-1]."""
+        x = inputs
+        for i in range(5):
+            x = self._layers[i](x, fts=fts)
+        x = self.vq_layer(x, training=None, code_only=code_only, fts=fts)
+        if not code_only:
+            for i in range(5, 10):
+                x = self._layers[i](x, fts=fts)
+            x = x.numpy()
+        return x
+
+    # ---- training ------------------------------------------------------------------
+    def compile(self, optimizer=None, loss="mse", metrics=None):
+        """run.py:61.  Only the reference configuration is implemented."""
+        if loss not in ("mse", "mean_squared_error"):
+            raise NotImplementedError("only loss='mse' (the reference configuration) is implemented")
+        for m in (metrics or []):
+            if m not in ("mae", "mean_absolute_error"):
+                raise NotImplementedError("only metrics=['mae'] is implemented")
+        if optimizer is None:
+            optimizer = Adam()
+        lr = getattr(optimizer, "learning_rate", getattr(optimizer, "lr", None))
+        self.optimizer = optimizer if isinstance(optimizer, Adam) else Adam(lr=float(lr))
+
+    def train_on_batch(self, y_batch: np.ndarray, global_batch: Optional[int] = None, sync: bool = True):
+        """One Keras fit step on a uint8 batch [B,V]; returns {loss, mse, mae, vq_loss} if sync."""
+        if self.optimizer is None:
+            self.compile()
+        B = y_batch.shape[0]
+        self._ensure_capacity(B)
+        met = (C.c_double * 4)() if sync else None
+        comm_h = self.comm.h if self.comm is not None else None
+        _ffi.check(_ffi.lib().pgmvae_model_train_step(self._h, y_batch.ctypes.data, 0, B, int(global_batch or B),
+                                                      self.optimizer.learning_rate, comm_h, 0, met))
+        self._adam_t += 1
+        if self.ema:
+            self._ema_steps += 1
+        if sync:
+            return {"loss": met[0], "mse": met[1], "mae": met[2], "vq_loss": met[3]}
+        return None
+
+    def fit(self, x, y=None, batch_size=32, epochs=1, callbacks=None, verbose=0, shuffle=True, order=None):
+        """``model.fit(train_x, train_x, batch_size, epochs)`` (run.py:62): per-epoch reshuffle,
+        last partial batch kept, loss/mae reported as sample-weighted epoch means.
+
+        ``order`` (list of per-epoch permutations) pins the batch order for parity runs; by
+        default ``np.random.permutation`` is used, which run.py seeds (run.py:36).  With a
+        data-parallel ``comm`` every rank must pass the same order; each rank then takes its
+        contiguous share of every global batch."""
+        if self.optimizer is None:
+            self.compile()
+        data = to_y(x)
+        n = data.shape[0]
+        rank, world = (self.comm.rank, self.comm.nranks) if self.comm is not None else (0, 1)
+        hist = History()
+        for ep in range(int(epochs)):
+            if order is not None:
+                perm = np.asarray(order[ep])
+            elif shuffle:
+                perm = np.random.permutation(n)
+            else:
+                perm = np.arange(n)
+            t0 = time.time()
+            sums = np.zeros(2)
+            seen = 0
+            for s in range(0, n, batch_size):
+                gidx = perm[s:s + batch_size]
+                gb = len(gidx)
+                lo, hi = gb * rank // world, gb * (rank + 1) // world
+                if hi <= lo:
+                    raise ValueError("a data-parallel rank received an empty share of a batch")
+                batch = np.ascontiguousarray(data[gidx[lo:hi]])
+                m = self.train_on_batch(batch, global_batch=gb, sync=True)
+                sums += np.array([m["loss"], m["mae"]]) * gb
+                seen += gb
+            hist.epoch.append(ep)
+            hist.history["loss"].append(sums[0] / seen)
+            hist.history["mae"].append(sums[1] / seen)
+            if verbose and rank == 0:
+                print(f"Epoch {ep + 1}/{epochs} - {time.time() - t0:.2f}s - loss: {sums[0] / seen:.6f} "
+                      f"- mae: {sums[1] / seen:.6f}", flush=True)
+            for cb in (callbacks or []):
+                if hasattr(cb, "on_epoch_end"):
+                    cb.on_epoch_end(ep, {"loss": sums[0] / seen, "mae": sums[1] / seen})
+        return hist
+
+    # ---- stage 2 ---------------------------------------------------------------------
+    def count(self, x, y=None):
+        """n1[v,k] = #(y_v = 1, code_v = k), n0 likewise (reference core/model.py:58-82),
+        as float64 [V,K].  With a communicator the samples are this rank's shard and the
+        counts are summed over ranks."""
+        data = to_y(y if y is not None else x)
+        n = data.shape[0]
+        if n > self.max_batch:
+            self._ensure_capacity(min(n, 8192))
+        n1 = np.zeros((self.nvar, self.k), dtype=np.uint64)
+        n0 = np.zeros((self.nvar, self.k), dtype=np.uint64)
+        _ffi.check(_ffi.lib().pgmvae_model_count(self._h, data.ctypes.data, 0, n, n1.ctypes.data, n0.ctypes.data))
+        if self.comm is not None and self.comm.nranks > 1:
+            n1, n0 = self.comm.allreduce_u64(n1), self.comm.allreduce_u64(n0)
+        return n1.astype(np.float64), n0.astype(np.float64)
+
+    def cpt(self, x, y=None):
+        """p(y=1 | code=k) with additive smoothing (reference core/model.py:85-88)."""
+        n1, n0 = self.count(x, y)
+        return (n1 + 0.8) / (n1 + n0 + 1.6)
+
+    def pseudo_log_likelihood(self, x, y=None, total: Optional[int] = None):
+        """Average pseudo log-likelihood (reference core/model.py:91-96); the float64
+        reduction runs on the device (pgmvae_pll_reduce)."""
+        data = to_y(y if y is not None else x)
+        n1, n0 = self.count(data)
+        n = int(total if total is not None else data.shape[0])
+        ctx, L = self.ctx, _ffi.lib()
+        d1 = _ffi.DeviceArray.from_numpy(ctx, n1.astype(np.uint64))
+        d0 = _ffi.DeviceArray.from_numpy(ctx, n0.astype(np.uint64))
+        dd = _ffi.DeviceArray.from_numpy(ctx, np.ascontiguousarray(self.dist, dtype=np.float64))
+        out = _ffi.DeviceArray(ctx, (1,), np.float64)
+        _ffi.check(L.pgmvae_pll_reduce(ctx.h, None, d1.ptr, d0.ptr, dd.ptr, n1.size, out.ptr))
+        return float(out.numpy()[0]) / n
+
+    def get_probability(self, x, fts=None):
+        """p(y_i = 1 | code) of the selected nets (reference core/model.py:99-108);
+        x [F, B, V-1], returns [F, B] float32."""
+        fts = np.asarray(fts, dtype=np.int64).reshape(-1)
+        enc_idx = self(x, code_only=True, fts=fts)                          # [F,B]
+        prb = self.dist[fts].astype(np.float32)
+        return np.take_along_axis(prb, enc_idx, axis=1)
+
+    def conditional_marginal_log_likelihood(self, x, p1, num_smp, burn_in, verbose=True):
+        raise NotImplementedError("Gibbs-sampling CMLL (reference core/model.py:110-148) is outside the hot path "
+                                  "(its call is commented out at run.py:74); see SURVEY.md 8(f)")
+
+    def device_bytes(self) -> int:
+        return int(_ffi.lib().pgmvae_model_device_bytes(self._h))
+
+    def save_weights(self, path: str):
+        np.savez(path, **self.state_dict())
+
+    def load_weights(self, path: str):
+        with np.load(path) as z:
+            self.load_state_dict({k: z[k] for k in z.files})
+
+    def __del__(self):
+        try:
+            if self._h:
+                _ffi.lib().pgmvae_model_destroy(self._h)
+        except Exception:
+            pass

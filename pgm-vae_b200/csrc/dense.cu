@@ -1,0 +1,62 @@
+// Public operator entry points of kernels (a) and (b): argument checks and the choice of
+// arithmetic (ctx precision): exact fp32 on CUDA cores, or tcgen05 tensor cores.
+#include "common.cuh"
+#include "ops.cuh"
+
+extern "C" {
+
+int pgmvae_dense_fwd(pgmvae_ctx* ctx, void* stream, const float* x, int64_t x_gs, int ldx, const float* w,
+                     int64_t w_gs, int ldw, const float* bias, int64_t bias_gs, float* out, int64_t out_gs, int ldo,
+                     int G, int B, int in, int out_dim, int act) {
+    PG_CHECK_ARG(ctx && x && w && out);
+    PG_CHECK_ARG(G >= 0 && B >= 0 && in > 0 && out_dim > 0);
+    PG_CHECK_ARG(ldx >= in && ldw >= out_dim && ldo >= out_dim);
+    PG_CHECK_ARG(act >= PGMVAE_ACT_NONE && act <= PGMVAE_ACT_SIGMOID);
+    return pg_dense_fwd_fp32(ctx, pg_stream(ctx, stream), x, x_gs, ldx, w, w_gs, ldw, bias, bias_gs, out, out_gs, ldo,
+                             G, B, in, out_dim, act);
+}
+
+int pgmvae_dense_fwd_sigmoid_mse(pgmvae_ctx* ctx, void* stream, const float* x, int64_t x_gs, int ldx, const float* w,
+                                 int64_t w_gs, int ldw, const float* bias, int64_t bias_gs, const float* y, int ldy,
+                                 float* dpre, int64_t dpre_gs, int ldd, float* out_opt, double* acc2, int G, int g0,
+                                 int B, int in, int V, float grad_scale) {
+    PG_CHECK_ARG(ctx && x && w && y && dpre && acc2);
+    PG_CHECK_ARG(G >= 0 && B >= 0 && in > 0 && V > 0 && g0 >= 0 && g0 + G <= V);
+    PG_CHECK_ARG(ldx >= in && ldw >= V && ldd >= V && ldy >= V);
+    return pg_dense_fwd_sigmoid_mse_fp32(ctx, pg_stream(ctx, stream), x, x_gs, ldx, w, w_gs, ldw, bias, bias_gs, y,
+                                         ldy, dpre, dpre_gs, ldd, out_opt, acc2, G, g0, B, in, V, grad_scale);
+}
+
+int pgmvae_dense_dgrad(pgmvae_ctx* ctx, void* stream, const float* dy, int64_t dy_gs, int lddy, const float* w,
+                       int64_t w_gs, int ldw, const float* h_in, int64_t h_gs, int ldh, const float* z,
+                       const float* q, int64_t zq_gs, int ldzq, float cscale, float* dx, int64_t dx_gs, int lddx,
+                       int G, int B, int in, int out_dim, int act_below) {
+    PG_CHECK_ARG(ctx && dy && w && dx);
+    PG_CHECK_ARG(G >= 0 && B >= 0 && in > 0 && out_dim > 0);
+    PG_CHECK_ARG(lddy >= out_dim && ldw >= out_dim && lddx >= in);
+    PG_CHECK_ARG((z == nullptr) == (q == nullptr));
+    PG_CHECK_ARG(!h_in || ldh >= in);
+    return pg_dense_dgrad_fp32(ctx, pg_stream(ctx, stream), dy, dy_gs, lddy, w, w_gs, ldw, h_in, h_gs, ldh, z, q,
+                               zq_gs, ldzq, cscale, dx, dx_gs, lddx, G, B, in, out_dim, act_below);
+}
+
+int pgmvae_dense_wgrad(pgmvae_ctx* ctx, void* stream, const float* x, int64_t x_gs, int ldx, const float* dy,
+                       int64_t dy_gs, int lddy, float* dw, int64_t dw_gs, int lddw, float* db, int64_t db_gs, int G,
+                       int B, int in, int out_dim, int zero_row_base) {
+    PG_CHECK_ARG(ctx && x && dy && dw);
+    PG_CHECK_ARG(G >= 0 && B >= 0 && in > 0 && out_dim > 0);
+    PG_CHECK_ARG(ldx >= in && lddy >= out_dim && lddw >= out_dim);
+    return pg_dense_wgrad_fp32(ctx, pg_stream(ctx, stream), x, x_gs, ldx, dy, dy_gs, lddy, dw, dw_gs, lddw, db, db_gs,
+                               G, B, in, out_dim, zero_row_base);
+}
+
+int pgmvae_vq_assign(pgmvae_ctx* ctx, void* stream, const float* z, int64_t z_gs, int ldz, const float* e,
+                     int64_t e_gs, int lde, int32_t* idx, int64_t idx_gs, float* best_opt, float* gap_opt, int G,
+                     int B, int D, int K) {
+    PG_CHECK_ARG(ctx && z && e && idx);
+    PG_CHECK_ARG(G >= 0 && B >= 0 && D > 0 && K > 0 && ldz >= D && lde >= D);
+    return pg_vq_assign_fp32(ctx, pg_stream(ctx, stream), z, z_gs, ldz, e, e_gs, lde, idx, idx_gs, best_opt, gap_opt,
+                             G, B, D, K);
+}
+
+}  // extern "C"

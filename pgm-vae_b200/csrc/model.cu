@@ -1,0 +1,620 @@
+// Model handle: device-resident state of one VqVAE (reference core/model.py:17-37) and the
+// fused loops that drive the kernels:
+//   train_step  = one Keras fit step (run.py:62): forward (core/model.py:39-55), MSE + VQ loss,
+//                 backward, Adam, EMA codebook update (core/quantizer.py:144-152)
+//   count       = VqVAE.count (core/model.py:58-82): encoder + assignment + histogram
+//
+// HBM layout (P(n) = n rounded up to 8 floats):
+//   layer l weights   W_l [V][P(in_l)][P(out_l)], bias b_l [V][P(out_l)]; zero padding.
+//     Layer 0 and 9 are stored EXPANDED over all V data columns: net v reads the raw data
+//     matrix y[B,V] with weight row v fixed at zero (fd0) / reconstructs all V columns with
+//     column v masked out of the loss (fd9).  This is the reference's leave-one-out input
+//     (run.py:46-50) without ever materialising [N,V,V-1].
+//   codebook          E [V][K][P(D)] code-major (reference variable is [V,D,K]).
+//   activations       H_l [Vg][B][P(out_l)] for one group of Vg variables at a time; networks
+//     of different variables are independent, so a step walks the variables group by group
+//     and the workspace is sized for one group.
+#include <math.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "ops.cuh"
+
+struct pgmvae_comm;
+int pg_comm_allreduce(pgmvae_comm* c, void* buf, int64_t n, int dtype, cudaStream_t st);  // comm.cu
+
+namespace {
+
+struct Layer {
+    int in, out;        // logical (expanded for layer 0 / 9)
+    int pin, pout;      // padded
+    int ref_in, ref_out;  // reference shapes (V-1 for the leave-one-out dims)
+    size_t w_off, b_off;  // float offsets into the parameter buffer
+    int act;
+};
+
+__global__ void init_uniform_kernel(float* __restrict__ dst, long long n, int rows, int cols, int prow, int pcol,
+                                    int zero_row_is_v, int zero_col_is_v, float limit, unsigned long long seed) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int c = (int)(i % pcol);
+    const long long t = i / pcol;
+    const int r = (int)(t % prow);
+    const int v = (int)(t / prow);
+    float val = 0.f;
+    if (r < rows && c < cols && !(zero_row_is_v && r == v) && !(zero_col_is_v && c == v)) {
+        // splitmix64 on (seed, element index) -> uniform in [-limit, limit)
+        unsigned long long x = seed + 0x9E3779B97F4A7C15ull * (unsigned long long)(i + 1);
+        x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+        x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+        x = x ^ (x >> 31);
+        const float u = (float)(x >> 40) * (1.0f / 16777216.0f);   // [0,1)
+        val = (2.0f * u - 1.0f) * limit;
+    }
+    dst[i] = val;
+}
+
+}  // namespace
+
+struct pgmvae_model {
+    pgmvae_ctx* ctx = nullptr;
+    int V = 0, D = 0, K = 0, Vp = 0, Dp = 0;
+    int units[4] = {0, 0, 0, 0};
+    double cost = 0.25, decay = 0.99, epsilon = 1e-5;
+    int ema = 1, max_batch = 0, Vg = 0;
+    Layer L[10];
+    size_t n_dense = 0, e_off = 0, n_params = 0;   // floats
+    float *params = nullptr, *grads = nullptr, *adam_m = nullptr, *adam_v = nullptr;
+    float *ema_w = nullptr, *biased_w = nullptr, *stat_w = nullptr;    // [V][K][Dp]
+    float *ema_c = nullptr, *biased_c = nullptr, *stat_c = nullptr;    // [V][K]
+    int step_c = 0, step_w = 0;
+    int64_t adam_t = 0;
+    // workspace
+    uint8_t* y_u8 = nullptr;
+    float* yf = nullptr;
+    float* H[10] = {};
+    float* Gd[10] = {};
+    float *q = nullptr, *st = nullptr;
+    int32_t* idx = nullptr;
+    double* acc = nullptr;          // device [4]
+    double* acc_host = nullptr;     // pinned [4]
+    unsigned long long *n1 = nullptr, *n0 = nullptr;
+    int64_t device_bytes = 0;
+    std::vector<void*> allocs;
+
+    float* E() const { return params + e_off; }
+    float* dE() const { return grads + e_off; }
+};
+
+namespace {
+
+int dev_alloc(pgmvae_model* m, void** p, size_t bytes) {
+    PG_TRY(pgmvae_malloc(m->ctx, bytes, p));
+    m->allocs.push_back(*p);
+    m->device_bytes += (int64_t)bytes;
+    cudaError_t e = cudaMemsetAsync(*p, 0, bytes, m->ctx->stream);
+    if (e != cudaSuccess) {
+        pgmvae_set_error("memset: %s", cudaGetErrorString(e));
+        return PGMVAE_ECUDA;
+    }
+    return PGMVAE_OK;
+}
+
+// ---- reference-layout <-> internal-layout conversion (host side) -------------------
+struct TensorRef {
+    enum Kind { KERNEL, BIAS, CODEBOOK, CODESIZE } kind;
+    int layer = -1;
+    float* base = nullptr;   // device pointer of the internal tensor
+    int64_t ref_count = 0, int_count = 0;
+};
+
+int resolve(pgmvae_model* m, const char* name, TensorRef* t) {
+    std::string s(name);
+    float* pbase = m->params;
+    if (s.rfind("grad.", 0) == 0) { pbase = m->grads; s = s.substr(5); }
+    else if (s.rfind("adam_m.", 0) == 0) { pbase = m->adam_m; s = s.substr(7); }
+    else if (s.rfind("adam_v.", 0) == 0) { pbase = m->adam_v; s = s.substr(7); }
+    const int64_t V = m->V;
+    if (s.size() >= 5 && s[0] == 'f' && s[1] == 'd' && s[2] >= '0' && s[2] <= '9' && s[3] == '.') {
+        const int l = s[2] - '0';
+        const Layer& L = m->L[l];
+        const std::string f = s.substr(4);
+        t->layer = l;
+        if (f == "kernel") {
+            t->kind = TensorRef::KERNEL;
+            t->base = pbase + L.w_off;
+            t->ref_count = V * L.ref_in * L.ref_out;
+            t->int_count = V * (int64_t)L.pin * L.pout;
+            return PGMVAE_OK;
+        }
+        if (f == "bias") {
+            t->kind = TensorRef::BIAS;
+            t->base = pbase + L.b_off;
+            t->ref_count = V * L.ref_out;
+            t->int_count = V * (int64_t)L.pout;
+            return PGMVAE_OK;
+        }
+    }
+    const int64_t cb = V * (int64_t)m->K * m->Dp;
+    auto codebook = [&](float* base) {
+        t->kind = TensorRef::CODEBOOK; t->base = base;
+        t->ref_count = V * (int64_t)m->D * m->K; t->int_count = cb;
+        return PGMVAE_OK;
+    };
+    auto codesize = [&](float* base) {
+        t->kind = TensorRef::CODESIZE; t->base = base;
+        t->ref_count = V * (int64_t)m->K; t->int_count = t->ref_count;
+        return PGMVAE_OK;
+    };
+    if (s == "vq.embeddings") {
+        if (pbase != m->params && m->ema) {
+            pgmvae_set_error("tensor '%s': the EMA codebook has no gradient / Adam slots", name);
+            return PGMVAE_EINVAL;
+        }
+        return codebook(pbase + m->e_off);
+    }
+    if (m->ema && pbase == m->params) {
+        if (s == "vq.ema_w") return codebook(m->ema_w);
+        if (s == "vq.biased_w") return codebook(m->biased_w);
+        if (s == "vq.stat_w") return codebook(m->stat_w);
+        if (s == "vq.ema_cluster_size") return codesize(m->ema_c);
+        if (s == "vq.biased_c") return codesize(m->biased_c);
+        if (s == "vq.stat_c") return codesize(m->stat_c);
+    }
+    pgmvae_set_error("unknown tensor name '%s'", name);
+    return PGMVAE_EINVAL;
+}
+
+// maps a reference index j in [0, V-1) of net v to its expanded position in [0, V)
+inline int expand_idx(int j, int v) { return j + (j >= v ? 1 : 0); }
+
+void to_internal(const pgmvae_model* m, const TensorRef& t, const float* ref, float* in) {
+    const int V = m->V;
+    memset(in, 0, sizeof(float) * (size_t)t.int_count);
+    if (t.kind == TensorRef::KERNEL) {
+        const Layer& L = m->L[t.layer];
+        for (int v = 0; v < V; ++v)
+            for (int r = 0; r < L.ref_in; ++r) {
+                const int ir = t.layer == 0 ? expand_idx(r, v) : r;
+                const float* src = ref + ((size_t)v * L.ref_in + r) * L.ref_out;
+                float* dst = in + ((size_t)v * L.pin + ir) * L.pout;
+                if (t.layer == 9) for (int c = 0; c < L.ref_out; ++c) dst[expand_idx(c, v)] = src[c];
+                else memcpy(dst, src, sizeof(float) * L.ref_out);
+            }
+    } else if (t.kind == TensorRef::BIAS) {
+        const Layer& L = m->L[t.layer];
+        for (int v = 0; v < V; ++v)
+            for (int c = 0; c < L.ref_out; ++c)
+                in[(size_t)v * L.pout + (t.layer == 9 ? expand_idx(c, v) : c)] = ref[(size_t)v * L.ref_out + c];
+    } else if (t.kind == TensorRef::CODEBOOK) {
+        for (int v = 0; v < V; ++v)
+            for (int d = 0; d < m->D; ++d)
+                for (int k = 0; k < m->K; ++k)
+                    in[((size_t)v * m->K + k) * m->Dp + d] = ref[((size_t)v * m->D + d) * m->K + k];
+    } else {
+        memcpy(in, ref, sizeof(float) * (size_t)t.ref_count);
+    }
+}
+
+void to_reference(const pgmvae_model* m, const TensorRef& t, const float* in, float* ref) {
+    const int V = m->V;
+    if (t.kind == TensorRef::KERNEL) {
+        const Layer& L = m->L[t.layer];
+        for (int v = 0; v < V; ++v)
+            for (int r = 0; r < L.ref_in; ++r) {
+                const int ir = t.layer == 0 ? expand_idx(r, v) : r;
+                float* dst = ref + ((size_t)v * L.ref_in + r) * L.ref_out;
+                const float* src = in + ((size_t)v * L.pin + ir) * L.pout;
+                if (t.layer == 9) for (int c = 0; c < L.ref_out; ++c) dst[c] = src[expand_idx(c, v)];
+                else memcpy(dst, src, sizeof(float) * L.ref_out);
+            }
+    } else if (t.kind == TensorRef::BIAS) {
+        const Layer& L = m->L[t.layer];
+        for (int v = 0; v < V; ++v)
+            for (int c = 0; c < L.ref_out; ++c)
+                ref[(size_t)v * L.ref_out + c] = in[(size_t)v * L.pout + (t.layer == 9 ? expand_idx(c, v) : c)];
+    } else if (t.kind == TensorRef::CODEBOOK) {
+        for (int v = 0; v < V; ++v)
+            for (int d = 0; d < m->D; ++d)
+                for (int k = 0; k < m->K; ++k)
+                    ref[((size_t)v * m->D + d) * m->K + k] = in[((size_t)v * m->K + k) * m->Dp + d];
+    } else {
+        memcpy(ref, in, sizeof(float) * (size_t)t.ref_count);
+    }
+}
+
+int upload_batch(pgmvae_model* m, const uint8_t* y, int on_device, int B, const uint8_t** y_dev) {
+    cudaStream_t st = m->ctx->stream;
+    if (on_device) {
+        *y_dev = y;
+    } else {
+        PG_CUDA(cudaMemcpyAsync(m->y_u8, y, (size_t)B * m->V, cudaMemcpyHostToDevice, st));
+        *y_dev = m->y_u8;
+    }
+    return pgmvae_y_to_f32(m->ctx, st, *y_dev, m->V, m->yf, m->Vp, B, m->V);
+}
+
+// encoder fd0..fd4 + assignment for variables [g0, g0+Gn) of the current batch (in m->yf)
+int encode_group(pgmvae_model* m, int g0, int Gn, int B) {
+    pgmvae_ctx* ctx = m->ctx;
+    cudaStream_t st = ctx->stream;
+    for (int l = 0; l < 5; ++l) {
+        const Layer& L = m->L[l];
+        const float* x = l == 0 ? m->yf : m->H[l - 1];
+        const int64_t x_gs = l == 0 ? 0 : (int64_t)m->max_batch * m->L[l - 1].pout;
+        const int ldx = l == 0 ? m->Vp : m->L[l - 1].pout;
+        PG_TRY(pgmvae_dense_fwd(ctx, st, x, x_gs, ldx, m->params + L.w_off + (size_t)g0 * L.pin * L.pout,
+                                (int64_t)L.pin * L.pout, L.pout, m->params + L.b_off + (size_t)g0 * L.pout, L.pout,
+                                m->H[l], (int64_t)m->max_batch * L.pout, L.pout, Gn, B, L.in, L.out, L.act));
+    }
+    PG_TRY(pgmvae_vq_assign(ctx, st, m->H[4], (int64_t)m->max_batch * m->Dp, m->Dp, m->E() + (size_t)g0 * m->K * m->Dp,
+                            (int64_t)m->K * m->Dp, m->Dp, m->idx, B, nullptr, nullptr, Gn, B, m->D, m->K));
+    return PGMVAE_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int pgmvae_model_create(pgmvae_ctx* ctx, const int* units4, int nvar, int dim, int k, double cost, double decay,
+                        double epsilon, int ema, int max_batch, pgmvae_model** out) {
+    PG_CHECK_ARG(ctx && units4 && out);
+    PG_CHECK_ARG(nvar >= 2 && dim >= 1 && k >= 1 && max_batch >= 1);
+    for (int i = 0; i < 4; ++i) PG_CHECK_ARG(units4[i] >= 1);
+    PG_CUDA(cudaSetDevice(ctx->device));
+    pgmvae_model* m = new pgmvae_model();
+    m->ctx = ctx; m->V = nvar; m->D = dim; m->K = k;
+    m->Vp = pg_round_up(nvar, 8); m->Dp = pg_round_up(dim, 8);
+    memcpy(m->units, units4, sizeof(int) * 4);
+    m->cost = cost; m->decay = decay; m->epsilon = epsilon; m->ema = ema ? 1 : 0; m->max_batch = max_batch;
+    // core/model.py:21-36: V-1 -> u0 -> u1 -> u2 -> u3 -> D | D -> u3 -> u2 -> u1 -> u0 -> V-1
+    const int chain[11] = {nvar - 1, units4[0], units4[1], units4[2], units4[3], dim,
+                           units4[3], units4[2], units4[1], units4[0], nvar - 1};
+    size_t off = 0;
+    for (int l = 0; l < 10; ++l) {
+        Layer& L = m->L[l];
+        L.ref_in = chain[l]; L.ref_out = chain[l + 1];
+        L.in = l == 0 ? nvar : chain[l];
+        L.out = l == 9 ? nvar : chain[l + 1];
+        L.pin = pg_round_up(L.in, 8); L.pout = pg_round_up(L.out, 8);
+        L.act = l == 9 ? PGMVAE_ACT_SIGMOID : PGMVAE_ACT_SELU;
+        L.w_off = off; off += (size_t)nvar * L.pin * L.pout;
+        L.b_off = off; off += (size_t)nvar * L.pout;
+    }
+    m->n_dense = off;
+    m->e_off = off;
+    off += (size_t)nvar * k * m->Dp;
+    m->n_params = off;
+
+    int rc = PGMVAE_OK;
+    auto A = [&](void** p, size_t bytes) { if (rc == PGMVAE_OK) rc = dev_alloc(m, p, bytes); };
+    const size_t trainable = m->ema ? m->n_dense : m->n_params;
+    A((void**)&m->params, m->n_params * 4);
+    A((void**)&m->grads, trainable * 4);
+    A((void**)&m->adam_m, trainable * 4);
+    A((void**)&m->adam_v, trainable * 4);
+    const size_t cb = (size_t)nvar * k * m->Dp, cs = (size_t)nvar * k;
+    if (m->ema) {
+        A((void**)&m->ema_w, cb * 4); A((void**)&m->biased_w, cb * 4); A((void**)&m->stat_w, cb * 4);
+        A((void**)&m->ema_c, cs * 4); A((void**)&m->biased_c, cs * 4); A((void**)&m->stat_c, cs * 4);
+    }
+    // group size: keep the per-group activation workspace under ~12 GB
+    size_t per_vb = 0;   // floats per (variable, sample)
+    for (int l = 0; l < 9; ++l) per_vb += (size_t)m->L[l].pout;       // H_0..H_8
+    for (int l = 0; l < 10; ++l) per_vb += (size_t)m->L[l].pout;      // Gd_0..Gd_9
+    per_vb += 2 * (size_t)m->Dp + 1;                                  // q, st, idx
+    const size_t budget = (size_t)12 << 30;
+    size_t vg = budget / (per_vb * 4 * (size_t)max_batch);
+    if (vg < 1) vg = 1;
+    if (vg > (size_t)nvar) vg = nvar;
+    m->Vg = (int)vg;
+    A((void**)&m->y_u8, (size_t)max_batch * nvar);
+    A((void**)&m->yf, (size_t)max_batch * m->Vp * 4);
+    for (int l = 0; l < 10; ++l) {
+        if (l < 9) A((void**)&m->H[l], vg * max_batch * m->L[l].pout * 4);
+        A((void**)&m->Gd[l], vg * max_batch * m->L[l].pout * 4);
+    }
+    A((void**)&m->q, vg * max_batch * m->Dp * 4);
+    A((void**)&m->st, vg * max_batch * m->Dp * 4);
+    // idx holds all V variables of a batch (encode / count expose [V,B])
+    A((void**)&m->idx, (size_t)nvar * max_batch * 4);
+    A((void**)&m->acc, 4 * sizeof(double));
+    A((void**)&m->n1, cs * 8);
+    A((void**)&m->n0, cs * 8);
+    if (rc == PGMVAE_OK && cudaMallocHost((void**)&m->acc_host, 4 * sizeof(double)) != cudaSuccess) {
+        pgmvae_set_error("cudaMallocHost failed");
+        rc = PGMVAE_ECUDA;
+    }
+    if (rc != PGMVAE_OK) {
+        pgmvae_model_destroy(m);
+        return rc;
+    }
+    PG_CUDA(cudaStreamSynchronize(ctx->stream));
+    *out = m;
+    return PGMVAE_OK;
+}
+
+int pgmvae_model_destroy(pgmvae_model* m) {
+    if (!m) return PGMVAE_OK;
+    cudaStreamSynchronize(m->ctx->stream);
+    for (void* p : m->allocs) cudaFree(p);
+    if (m->acc_host) cudaFreeHost(m->acc_host);
+    delete m;
+    return PGMVAE_OK;
+}
+
+int64_t pgmvae_model_device_bytes(pgmvae_model* m) { return m ? m->device_bytes : 0; }
+int pgmvae_model_group_size(pgmvae_model* m) { return m ? m->Vg : 0; }
+
+int pgmvae_model_init(pgmvae_model* m, uint64_t seed) {
+    PG_CHECK_ARG(m != nullptr);
+    pgmvae_ctx* ctx = m->ctx;
+    cudaStream_t st = ctx->stream;
+    const double V = m->V;
+    for (int l = 0; l < 10; ++l) {
+        const Layer& L = m->L[l];
+        // Keras fans on the reference shape [V, in, out]: fan_in = V*in, fan_out = V*out
+        const double fan_in = V * L.ref_in, fan_out = V * L.ref_out;
+        const float limit = (float)(l < 9 ? sqrt(6.0 / fan_in) : sqrt(6.0 / (fan_in + fan_out)));
+        const long long n = (long long)m->V * L.pin * L.pout;
+        init_uniform_kernel<<<(unsigned)pg_cdiv(n, 256), 256, 0, st>>>(m->params + L.w_off, n, L.in, L.out, L.pin,
+                                                                      L.pout, l == 0, l == 9, limit,
+                                                                      seed * 1000003ull + (unsigned long long)l);
+        PG_LAUNCHED(ctx);
+        PG_CUDA(cudaMemsetAsync(m->params + L.b_off, 0, (size_t)m->V * L.pout * 4, st));
+    }
+    {
+        const float limit = (float)sqrt(3.0 / (V * m->D));
+        const long long n = (long long)m->V * m->K * m->Dp;
+        init_uniform_kernel<<<(unsigned)pg_cdiv(n, 256), 256, 0, st>>>(m->E(), n, m->K, m->D, m->K, m->Dp, 0, 0, limit,
+                                                                      seed * 1000003ull + 100ull);
+        PG_LAUNCHED(ctx);
+    }
+    const size_t trainable = m->ema ? m->n_dense : m->n_params;
+    PG_CUDA(cudaMemsetAsync(m->adam_m, 0, trainable * 4, st));
+    PG_CUDA(cudaMemsetAsync(m->adam_v, 0, trainable * 4, st));
+    m->adam_t = 0;
+    if (m->ema) {
+        const size_t cb = (size_t)m->V * m->K * m->Dp, cs = (size_t)m->V * m->K;
+        PG_CUDA(cudaMemcpyAsync(m->ema_w, m->E(), cb * 4, cudaMemcpyDeviceToDevice, st));   // core/quantizer.py:117
+        PG_CUDA(cudaMemsetAsync(m->biased_w, 0, cb * 4, st));
+        PG_CUDA(cudaMemsetAsync(m->ema_c, 0, cs * 4, st));
+        PG_CUDA(cudaMemsetAsync(m->biased_c, 0, cs * 4, st));
+        m->step_c = m->step_w = 0;
+    }
+    PG_CUDA(cudaStreamSynchronize(st));
+    return PGMVAE_OK;
+}
+
+int pgmvae_model_tensor_size(pgmvae_model* m, const char* name, int64_t* count) {
+    PG_CHECK_ARG(m && name && count);
+    TensorRef t;
+    PG_TRY(resolve(m, name, &t));
+    *count = t.ref_count;
+    return PGMVAE_OK;
+}
+
+int pgmvae_model_set_tensor(pgmvae_model* m, const char* name, const float* host, int64_t count) {
+    PG_CHECK_ARG(m && name && host);
+    TensorRef t;
+    PG_TRY(resolve(m, name, &t));
+    if (count != t.ref_count) {
+        pgmvae_set_error("set_tensor '%s': expected %lld elements, got %lld", name, (long long)t.ref_count,
+                         (long long)count);
+        return PGMVAE_EINVAL;
+    }
+    std::vector<float> in((size_t)t.int_count);
+    to_internal(m, t, host, in.data());
+    PG_CUDA(cudaStreamSynchronize(m->ctx->stream));
+    PG_CUDA(cudaMemcpy(t.base, in.data(), sizeof(float) * (size_t)t.int_count, cudaMemcpyHostToDevice));
+    return PGMVAE_OK;
+}
+
+int pgmvae_model_get_tensor(pgmvae_model* m, const char* name, float* host, int64_t count) {
+    PG_CHECK_ARG(m && name && host);
+    TensorRef t;
+    PG_TRY(resolve(m, name, &t));
+    if (count != t.ref_count) {
+        pgmvae_set_error("get_tensor '%s': expected %lld elements, got %lld", name, (long long)t.ref_count,
+                         (long long)count);
+        return PGMVAE_EINVAL;
+    }
+    std::vector<float> in((size_t)t.int_count);
+    PG_CUDA(cudaStreamSynchronize(m->ctx->stream));
+    PG_CUDA(cudaMemcpy(in.data(), t.base, sizeof(float) * (size_t)t.int_count, cudaMemcpyDeviceToHost));
+    to_reference(m, t, in.data(), host);
+    return PGMVAE_OK;
+}
+
+int pgmvae_model_set_ema_steps(pgmvae_model* m, int step_c, int step_w) {
+    PG_CHECK_ARG(m && step_c >= 0 && step_w >= 0);
+    m->step_c = step_c; m->step_w = step_w;
+    return PGMVAE_OK;
+}
+int pgmvae_model_set_adam_step(pgmvae_model* m, int64_t t) {
+    PG_CHECK_ARG(m && t >= 0);
+    m->adam_t = t;
+    return PGMVAE_OK;
+}
+
+}  // extern "C"
+
+namespace {
+enum { STEP_NO_UPDATE = 1, STEP_FWD_ONLY = 2, STEP_NO_EMA = 4 };
+
+int run_step(pgmvae_model* m, const uint8_t* y, int y_on_device, int B, int global_B, float lr, pgmvae_comm* comm,
+             int flags, float* out_dev, double* metrics4) {
+    PG_CHECK_ARG(m && y);
+    PG_CHECK_ARG(B >= 1 && B <= m->max_batch);
+    if (global_B <= 0) global_B = B;
+    PG_CHECK_ARG(global_B >= B);
+    pgmvae_ctx* ctx = m->ctx;
+    cudaStream_t st = ctx->stream;
+    PG_CUDA(cudaSetDevice(ctx->device));
+    const int V = m->V, D = m->D, K = m->K, Dp = m->Dp;
+    const uint8_t* y_dev = nullptr;
+    PG_TRY(upload_batch(m, y, y_on_device, B, &y_dev));
+
+    const size_t trainable = m->ema ? m->n_dense : m->n_params;
+    PG_CUDA(cudaMemsetAsync(m->grads, 0, trainable * 4, st));
+    PG_CUDA(cudaMemsetAsync(m->acc, 0, 4 * sizeof(double), st));
+    if (m->ema) {
+        PG_CUDA(cudaMemsetAsync(m->stat_w, 0, (size_t)V * K * Dp * 4, st));
+        PG_CUDA(cudaMemsetAsync(m->stat_c, 0, (size_t)V * K * 4, st));
+    }
+    // global means: Keras mse over B*V*(V-1) outputs (run.py:61); VQ means over V*B*D
+    const double n_out = (double)global_B * V * (V - 1);
+    const double n_lat = (double)global_B * V * D;
+    const float gscale = (float)(2.0 / n_out);
+    const float cscale = (float)(m->cost * 2.0 / n_lat);
+
+    for (int g0 = 0; g0 < V; g0 += m->Vg) {
+        const int Gn = std::min(m->Vg, V - g0);
+        PG_TRY(encode_group(m, g0, Gn, B));
+        // m->idx rows [0, Gn) now hold this group's codes
+        const float* Eg = m->E() + (size_t)g0 * K * Dp;
+        const int64_t MB = m->max_batch;   // activation strides are fixed so that pad columns stay zero
+        const int64_t zgs = MB * Dp;
+        PG_TRY(pgmvae_vq_quantize(ctx, st, m->H[4], zgs, Dp, Eg, (int64_t)K * Dp, Dp, m->idx, B, m->q, m->st, zgs, Dp,
+                                  m->acc + 2, Gn, B, D, K));
+        if (m->ema) {
+            if (!(flags & STEP_NO_EMA))
+            PG_TRY(pgmvae_ema_stats(ctx, st, m->H[4], zgs, Dp, m->idx, B, m->stat_c + (size_t)g0 * K, K,
+                                    m->stat_w + (size_t)g0 * K * Dp, (int64_t)K * Dp, Dp, Gn, B, D, K));
+        } else if (!(flags & STEP_FWD_ONLY)) {
+            // q_latent_loss gradient wrt the codebook: 2 (q - z) / (V B D)   (core/quantizer.py:51)
+            PG_TRY(pgmvae_vq_codebook_grad(ctx, st, m->H[4], m->q, zgs, Dp, m->idx, B, m->dE() + (size_t)g0 * K * Dp,
+                                           (int64_t)K * Dp, Dp, (float)(2.0 / n_lat), Gn, B, D, K));
+        }
+        // decoder fd5..fd8
+        for (int l = 5; l < 9; ++l) {
+            const Layer& L = m->L[l];
+            const float* x = l == 5 ? m->st : m->H[l - 1];
+            const int ldx = l == 5 ? Dp : m->L[l - 1].pout;
+            PG_TRY(pgmvae_dense_fwd(ctx, st, x, MB * ldx, ldx, m->params + L.w_off + (size_t)g0 * L.pin * L.pout,
+                                    (int64_t)L.pin * L.pout, L.pout, m->params + L.b_off + (size_t)g0 * L.pout, L.pout,
+                                    m->H[l], MB * L.pout, L.pout, Gn, B, L.in, L.out, L.act));
+        }
+        {   // fd9 + loss + d(loss)/d(pre-activation)
+            const Layer& L = m->L[9];
+            PG_TRY(pgmvae_dense_fwd_sigmoid_mse(
+                ctx, st, m->H[8], MB * m->L[8].pout, m->L[8].pout,
+                m->params + L.w_off + (size_t)g0 * L.pin * L.pout, (int64_t)L.pin * L.pout, L.pout,
+                m->params + L.b_off + (size_t)g0 * L.pout, L.pout, m->yf, m->Vp, m->Gd[9], MB * L.pout, L.pout,
+                out_dev ? out_dev + (size_t)g0 * MB * L.pout : nullptr, m->acc, Gn, g0, B, L.in, V, gscale));
+        }
+        // backward
+        for (int l = (flags & STEP_FWD_ONLY) ? -1 : 9; l >= 0; --l) {
+            const Layer& L = m->L[l];
+            const float* x = l == 0 ? m->yf : (l == 5 ? m->st : m->H[l - 1]);
+            const int ldx = l == 0 ? m->Vp : (l == 5 ? Dp : m->L[l - 1].pout);
+            const int64_t x_gs = l == 0 ? 0 : MB * ldx;
+            PG_TRY(pgmvae_dense_wgrad(ctx, st, x, x_gs, ldx, m->Gd[l], MB * L.pout, L.pout,
+                                      m->grads + L.w_off + (size_t)g0 * L.pin * L.pout, (int64_t)L.pin * L.pout, L.pout,
+                                      m->grads + L.b_off + (size_t)g0 * L.pout, L.pout, Gn, B, L.in, L.out,
+                                      l == 0 ? g0 : -1));
+            if (l > 0) {
+                const Layer& P = m->L[l - 1];
+                const bool vqb = (l == 5);
+                PG_TRY(pgmvae_dense_dgrad(ctx, st, m->Gd[l], MB * L.pout, L.pout,
+                                          m->params + L.w_off + (size_t)g0 * L.pin * L.pout, (int64_t)L.pin * L.pout,
+                                          L.pout, m->H[l - 1], MB * P.pout, P.pout, vqb ? m->H[4] : nullptr,
+                                          vqb ? m->q : nullptr, zgs, Dp, cscale, m->Gd[l - 1], MB * P.pout,
+                                          P.pout, Gn, B, L.in, L.out, PGMVAE_ACT_SELU));
+            }
+        }
+    }
+
+    if (comm) {
+        if (!(flags & STEP_FWD_ONLY)) PG_TRY(pg_comm_allreduce(comm, m->grads, (int64_t)trainable, 0, st));
+        if (m->ema && !(flags & STEP_NO_EMA)) {
+            PG_TRY(pg_comm_allreduce(comm, m->stat_w, (int64_t)V * K * Dp, 0, st));
+            PG_TRY(pg_comm_allreduce(comm, m->stat_c, (int64_t)V * K, 0, st));
+        }
+        PG_TRY(pg_comm_allreduce(comm, m->acc, 4, 1, st));
+    }
+
+    if (!(flags & (STEP_NO_UPDATE | STEP_FWD_ONLY))) {
+        m->adam_t += 1;
+        const double b1 = 0.9, b2 = 0.999;
+        const float alpha = (float)((double)lr * sqrt(1.0 - pow(b2, (double)m->adam_t)) / (1.0 - pow(b1, (double)m->adam_t)));
+        PG_TRY(pgmvae_adam_step(ctx, st, m->params, m->grads, m->adam_m, m->adam_v, (int64_t)trainable, alpha, b1, b2,
+                                1e-7));
+    }
+    if (!(flags & STEP_NO_UPDATE)) {
+        if (m->ema && !(flags & STEP_NO_EMA)) {
+            m->step_c += 1; m->step_w += 1;
+            PG_TRY(pgmvae_ema_apply(ctx, st, m->stat_c, m->stat_w, m->biased_c, m->biased_w, m->ema_c, m->ema_w, m->E(),
+                                    V, K, Dp, Dp, m->decay, m->epsilon, m->step_c, 1));
+        }
+    }
+    if (metrics4) {
+        PG_CUDA(cudaMemcpyAsync(m->acc_host, m->acc, 4 * sizeof(double), cudaMemcpyDeviceToHost, st));
+        PG_CUDA(cudaStreamSynchronize(st));
+        const double mse = m->acc_host[0] / n_out, mae = m->acc_host[1] / n_out;
+        const double e_latent = m->acc_host[2] / n_lat;
+        const double vq = m->ema ? m->cost * e_latent : (1.0 + m->cost) * e_latent;
+        metrics4[0] = mse + vq; metrics4[1] = mse; metrics4[2] = mae; metrics4[3] = vq;
+    }
+    return PGMVAE_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int pgmvae_model_train_step(pgmvae_model* m, const uint8_t* y, int y_on_device, int B, int global_B, float lr,
+                            pgmvae_comm* comm, int flags, double* metrics4) {
+    return run_step(m, y, y_on_device, B, global_B, lr, comm, (flags & 1) ? STEP_NO_UPDATE : 0, nullptr, metrics4);
+}
+
+int pgmvae_model_forward(pgmvae_model* m, const uint8_t* y, int y_on_device, int B, int training, float* out_dev,
+                         double* metrics4) {
+    return run_step(m, y, y_on_device, B, B, 0.f, nullptr, STEP_FWD_ONLY | (training ? 0 : STEP_NO_EMA), out_dev,
+                    metrics4);
+}
+
+int pgmvae_model_encode(pgmvae_model* m, const uint8_t* y, int y_on_device, int B, int32_t* idx_dev) {
+    PG_CHECK_ARG(m && y && idx_dev);
+    PG_CHECK_ARG(B >= 1 && B <= m->max_batch);
+    PG_CUDA(cudaSetDevice(m->ctx->device));
+    const uint8_t* y_dev = nullptr;
+    PG_TRY(upload_batch(m, y, y_on_device, B, &y_dev));
+    for (int g0 = 0; g0 < m->V; g0 += m->Vg) {
+        const int Gn = std::min(m->Vg, m->V - g0);
+        PG_TRY(encode_group(m, g0, Gn, B));
+        PG_CUDA(cudaMemcpyAsync(idx_dev + (size_t)g0 * B, m->idx, (size_t)Gn * B * 4, cudaMemcpyDeviceToDevice,
+                                m->ctx->stream));
+    }
+    return PGMVAE_OK;
+}
+
+int pgmvae_model_count(pgmvae_model* m, const uint8_t* y, int y_on_device, int64_t N, unsigned long long* n1_host,
+                       unsigned long long* n0_host) {
+    PG_CHECK_ARG(m && y && n1_host && n0_host && N >= 0);
+    pgmvae_ctx* ctx = m->ctx;
+    cudaStream_t st = ctx->stream;
+    PG_CUDA(cudaSetDevice(ctx->device));
+    const size_t cs = (size_t)m->V * m->K;
+    PG_CUDA(cudaMemsetAsync(m->n1, 0, cs * 8, st));
+    PG_CUDA(cudaMemsetAsync(m->n0, 0, cs * 8, st));
+    for (int64_t s = 0; s < N; s += m->max_batch) {
+        const int B = (int)std::min<int64_t>(m->max_batch, N - s);
+        const uint8_t* y_dev = nullptr;
+        PG_TRY(upload_batch(m, y + (size_t)s * m->V, y_on_device, B, &y_dev));
+        for (int g0 = 0; g0 < m->V; g0 += m->Vg) {
+            const int Gn = std::min(m->Vg, m->V - g0);
+            PG_TRY(encode_group(m, g0, Gn, B));
+            PG_TRY(pgmvae_pll_count(ctx, st, m->idx, B, y_dev, m->V, g0, m->n1 + (size_t)g0 * m->K,
+                                    m->n0 + (size_t)g0 * m->K, Gn, B, m->K));
+        }
+    }
+    PG_CUDA(cudaMemcpyAsync(n1_host, m->n1, cs * 8, cudaMemcpyDeviceToHost, st));
+    PG_CUDA(cudaMemcpyAsync(n0_host, m->n0, cs * 8, cudaMemcpyDeviceToHost, st));
+    PG_CUDA(cudaStreamSynchronize(st));
+    return PGMVAE_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,210 @@
+// Kernel (d): pseudo-log-likelihood stage, plus the optimiser / input-conversion kernels.
+//   pll_count   histogram over (variable, code, y)   reference core/model.py:58-82
+//   cpt         Laplace-smoothed table, float64       reference core/model.py:88
+//   pll_reduce  float64 log-likelihood reduction      reference core/model.py:93-96
+//   adam_step   Keras Adam (ResourceApplyAdam form)   reference run.py:60
+//   y_to_f32    uint8 data matrix -> fp32 operand     replaces make_xs, reference run.py:46-50
+#include "common.cuh"
+
+namespace {
+
+constexpr int PLL_ROWS = 256;   // rows per tile == threads per CTA
+
+// One CTA owns a tile of VT variables and a contiguous range of rows; its histogram
+// [VT][K][2] lives in shared memory and is flushed once.  y is read through a
+// coalesced [PLL_ROWS][VT] byte tile, idx along its contiguous sample axis.
+__global__ void __launch_bounds__(PLL_ROWS) pll_count_kernel(
+    const int32_t* __restrict__ idx, long long idx_gs, const uint8_t* __restrict__ y, int ldy, int g0,
+    unsigned long long* __restrict__ n1, unsigned long long* __restrict__ n0, int G, int B, int K, int VT,
+    int rows_per_cta) {
+    extern __shared__ __align__(16) unsigned int hist[];              // [VT][K][2]
+    unsigned char* ytile = reinterpret_cast<unsigned char*>(hist + (size_t)VT * K * 2);  // [PLL_ROWS][VT]
+    const int t = threadIdx.x;
+    const int gv0 = blockIdx.y * VT;
+    const int nv = min(VT, G - gv0);
+    const int r0 = blockIdx.x * rows_per_cta, r1 = min(B, r0 + rows_per_cta);
+    for (int i = t; i < VT * K * 2; i += PLL_ROWS) hist[i] = 0u;
+    __syncthreads();
+    for (int rb = r0; rb < r1; rb += PLL_ROWS) {
+        const int nr = min(PLL_ROWS, r1 - rb);
+        for (int i = t; i < nr * nv; i += PLL_ROWS) {
+            const int row = i / nv, c = i - row * nv;
+            ytile[row * VT + c] = y[(long long)(rb + row) * ldy + g0 + gv0 + c];
+        }
+        __syncthreads();
+        if (t < nr) {
+            for (int c = 0; c < nv; ++c) {
+                const int k = idx[(long long)(gv0 + c) * idx_gs + rb + t];
+                const unsigned int one = ytile[t * VT + c] != 0 ? 1u : 0u;
+                atomicAdd(&hist[((size_t)c * K + k) * 2 + one], 1u);
+            }
+        }
+        __syncthreads();
+    }
+    for (int i = t; i < nv * K * 2; i += PLL_ROWS) {
+        const unsigned int h = hist[i];
+        if (h) {
+            const int c = i / (2 * K), r = i - c * 2 * K;
+            const int k = r >> 1;
+            unsigned long long* dst = (r & 1) ? n1 : n0;
+            atomicAdd(&dst[(long long)(gv0 + c) * K + k], (unsigned long long)h);
+        }
+    }
+}
+
+__global__ void cpt_kernel(const unsigned long long* __restrict__ n1, const unsigned long long* __restrict__ n0,
+                           double* __restrict__ dist, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const double a = (double)n1[i], b = (double)n0[i];
+        dist[i] = (a + 0.8) / (a + b + 1.6);
+    }
+}
+
+__global__ void __launch_bounds__(256) pll_reduce_kernel(const unsigned long long* __restrict__ n1,
+                                                         const unsigned long long* __restrict__ n0,
+                                                         const double* __restrict__ dist, long long n,
+                                                         double* out) {
+    __shared__ double red[8];
+    double part = 0.0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const double p = dist[i];
+        part += (double)n1[i] * log(p + 1e-5) + (double)n0[i] * log(1.0 - p + 1e-5);
+    }
+    part = pg_warp_sum_d(part);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = part;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0;
+        for (int i = 0; i < 8; ++i) a += red[i];
+        atomicAdd(out, a);
+    }
+}
+
+__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g,
+                                                   float* __restrict__ m, float* __restrict__ v, long long n,
+                                                   float alpha, float omb1, float omb2, float eps) {
+    const long long n4 = n >> 2;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        float4 pp = reinterpret_cast<float4*>(p)[i];
+        const float4 gg = reinterpret_cast<const float4*>(g)[i];
+        float4 mm = reinterpret_cast<float4*>(m)[i];
+        float4 vv = reinterpret_cast<float4*>(v)[i];
+#define PG_ADAM1(c)                                        \
+        mm.c += (gg.c - mm.c) * omb1;                      \
+        vv.c += (gg.c * gg.c - vv.c) * omb2;               \
+        pp.c -= (mm.c * alpha) / (sqrtf(vv.c) + eps);
+        PG_ADAM1(x) PG_ADAM1(y) PG_ADAM1(z) PG_ADAM1(w)
+#undef PG_ADAM1
+        reinterpret_cast<float4*>(p)[i] = pp;
+        reinterpret_cast<float4*>(m)[i] = mm;
+        reinterpret_cast<float4*>(v)[i] = vv;
+    }
+    for (long long i = (n4 << 2) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        float mm = m[i], vv = v[i];
+        const float gg = g[i];
+        mm += (gg - mm) * omb1;
+        vv += (gg * gg - vv) * omb2;
+        p[i] -= (mm * alpha) / (sqrtf(vv) + eps);
+        m[i] = mm;
+        v[i] = vv;
+    }
+}
+
+__global__ void y_to_f32_kernel(const uint8_t* __restrict__ y, int ldy, float* __restrict__ out, int ld, int B, int V) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)B * ld) return;
+    const int b = (int)(i / ld), c = (int)(i - (long long)b * ld);
+    out[i] = c < V ? (y[(long long)b * ldy + c] != 0 ? 1.0f : 0.0f) : 0.0f;
+}
+
+}  // namespace
+
+extern "C" {
+
+int pgmvae_pll_count(pgmvae_ctx* ctx, void* stream, const int32_t* idx, int64_t idx_gs, const uint8_t* y, int ldy,
+                     int g0, unsigned long long* n1, unsigned long long* n0, int G, int B, int K) {
+    PG_CHECK_ARG(ctx && idx && y && n1 && n0);
+    PG_CHECK_ARG(K > 0 && G >= 0 && B >= 0);
+    if (G == 0 || B == 0) return PGMVAE_OK;
+    const size_t budget = 128 * 1024;
+    int VT = (int)(budget / ((size_t)K * 8 + PLL_ROWS));
+    if (VT > 32) VT = 32;
+    if (VT > G) VT = G;
+    if (VT < 1) {
+        pgmvae_set_error("pll_count: K=%d too large for the shared-memory histogram", K);
+        return PGMVAE_EINVAL;
+    }
+    const size_t smem = (size_t)VT * K * 8 + (size_t)PLL_ROWS * VT;
+    const int vtiles = (int)pg_cdiv(G, VT);
+    // enough row splits to give every SM ~2 CTAs, but keep >= 8 row tiles per CTA to amortise the flush
+    int splits = (int)pg_cdiv(2 * ctx->sm_count, vtiles);
+    const int max_splits = (int)pg_cdiv(B, 8 * PLL_ROWS);
+    if (splits > max_splits) splits = max_splits;
+    if (splits < 1) splits = 1;
+    const int rows_per_cta = pg_round_up((int)pg_cdiv(B, splits), PLL_ROWS);
+    splits = (int)pg_cdiv(B, rows_per_cta);
+    static size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+        PG_CUDA(cudaFuncSetAttribute(pll_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    dim3 grid((unsigned)splits, (unsigned)vtiles);
+    PG_KERNEL(ctx, pg_stream(ctx, stream), "pll_count", (double)G * B * 5.0 + 2.0 * G * K * 8.0, (double)G * B);
+    pll_count_kernel<<<grid, PLL_ROWS, smem, pg_stream(ctx, stream)>>>(idx, idx_gs, y, ldy, g0, n1, n0, G, B, K, VT,
+                                                                      rows_per_cta);
+    PG_LAUNCHED(ctx);
+    return PGMVAE_OK;
+}
+
+int pgmvae_cpt(pgmvae_ctx* ctx, void* stream, const unsigned long long* n1, const unsigned long long* n0, double* dist,
+               int64_t count) {
+    PG_CHECK_ARG(ctx && n1 && n0 && dist && count >= 0);
+    if (count == 0) return PGMVAE_OK;
+    PG_KERNEL(ctx, pg_stream(ctx, stream), "cpt", 24.0 * count, 3.0 * count);
+    cpt_kernel<<<(unsigned)pg_cdiv(count, 256), 256, 0, pg_stream(ctx, stream)>>>(n1, n0, dist, count);
+    PG_LAUNCHED(ctx);
+    return PGMVAE_OK;
+}
+
+int pgmvae_pll_reduce(pgmvae_ctx* ctx, void* stream, const unsigned long long* n1, const unsigned long long* n0,
+                      const double* dist, int64_t count, double* out_sum) {
+    PG_CHECK_ARG(ctx && n1 && n0 && dist && out_sum && count >= 0);
+    cudaStream_t st = pg_stream(ctx, stream);
+    PG_CUDA(cudaMemsetAsync(out_sum, 0, sizeof(double), st));
+    if (count == 0) return PGMVAE_OK;
+    int blocks = (int)std::min<int64_t>(pg_cdiv(count, 256 * 4), ctx->sm_count);
+    if (blocks < 1) blocks = 1;
+    PG_KERNEL(ctx, st, "pll_reduce", 24.0 * count, 6.0 * count);
+    pll_reduce_kernel<<<blocks, 256, 0, st>>>(n1, n0, dist, count, out_sum);
+    PG_LAUNCHED(ctx);
+    return PGMVAE_OK;
+}
+
+int pgmvae_adam_step(pgmvae_ctx* ctx, void* stream, float* p, const float* g, float* m, float* v, int64_t n,
+                     float alpha, double b1, double b2, double eps) {
+    PG_CHECK_ARG(ctx && p && g && m && v && n >= 0);
+    PG_CHECK_ARG(((uintptr_t)p & 15) == 0 && ((uintptr_t)g & 15) == 0 && ((uintptr_t)m & 15) == 0 &&
+                 ((uintptr_t)v & 15) == 0);
+    if (n == 0) return PGMVAE_OK;
+    int blocks = (int)std::min<int64_t>(pg_cdiv(n, 256 * 4 * 4), (int64_t)ctx->sm_count * 8);
+    if (blocks < 1) blocks = 1;
+    PG_KERNEL(ctx, pg_stream(ctx, stream), "adam", 28.0 * n, 10.0 * n);
+    adam_kernel<<<blocks, 256, 0, pg_stream(ctx, stream)>>>(p, g, m, v, n, alpha, (float)(1.0 - b1), (float)(1.0 - b2),
+                                                            (float)eps);
+    PG_LAUNCHED(ctx);
+    return PGMVAE_OK;
+}
+
+int pgmvae_y_to_f32(pgmvae_ctx* ctx, void* stream, const uint8_t* y, int ldy, float* out, int ld, int B, int V) {
+    PG_CHECK_ARG(ctx && y && out && ld >= V && ldy >= V && B >= 0);
+    if (B == 0) return PGMVAE_OK;
+    const long long n = (long long)B * ld;
+    PG_KERNEL(ctx, pg_stream(ctx, stream), "y_to_f32", (double)B * V + 4.0 * n, 0.0);
+    y_to_f32_kernel<<<(unsigned)pg_cdiv(n, 256), 256, 0, pg_stream(ctx, stream)>>>(y, ldy, out, ld, B, V);
+    PG_LAUNCHED(ctx);
+    return PGMVAE_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,97 @@
+"""CLI driver -- same flags, defaults, identifier and result line as the reference run.py,
+on the B200 CUDA library instead of TensorFlow.
+
+Stage 1 trains the packed per-variable auto-encoders with the VQ codebook (reference
+run.py:59-62); stage 2 builds the conditional probability table from the training split and
+evaluates the pseudo log-likelihood of train / valid / test (run.py:66-72).  The
+leave-one-out tensor make_xs builds (run.py:46-50) is never materialised: the kernels read
+the raw 0/1 matrix.  Under torchrun (WORLD_SIZE > 1) training is data-parallel over the
+batch and the PLL splits are sharded over samples.
+"""
+import argparse
+import os
+import random as rdn
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+
+from baseline import baseline as bl  # noqa: E402
+
+
+def build_parser():
+    parser = argparse.ArgumentParser()
+    parser.add_argument('--name', '-n', required=True, help='target dataset name')
+    parser.add_argument('--embedding', '-k', type=int, required=True, help='embedding dictionary size')
+    parser.add_argument('--dim', '-d', type=int, required=True, help='embedding dimension')
+    parser.add_argument('--batch', '-b', type=int, default=128, help='training batch size')
+    parser.add_argument('--epoch', '-e', type=int, default=200, help='number of epochs for training')
+    parser.add_argument('--rate', '-r', type=float, default=0.001, help='learning rate')
+    parser.add_argument('--cost', '-c', type=float, default=0.25, help='commitment cost')
+    parser.add_argument('--ema', '-m', action='store_true', help='using exponential moving average')
+    parser.add_argument('--decay', '-g', type=float, default=0.99, help='EMA decay rate')
+    parser.add_argument('--seed', '-s', type=int, default=0, help='integer for random seed')
+    parser.add_argument('--device', '-u', type=int, default=0, help='which GPU to use (-1, the reference CPU path, is refused)')
+    parser.add_argument('--verbose', '-v', action='store_true', help='verbose mode when do model fitting and sampling')
+    parser.add_argument('--note', '-t', type=str, default='', help='note for other conditions')
+    return parser
+
+
+def main(argv=None):
+    args = build_parser().parse_args(argv)
+    name, K, D, bs, epochs, learn_rate, beta, ema, gamma, seed, device, vb, note = (
+        args.name, args.embedding, args.dim, args.batch, args.epoch, args.rate, args.cost, args.ema, args.decay,
+        args.seed, args.device, args.verbose, args.note)
+    if device == -1:
+        sys.exit("run.py: --device -1 selects the reference's TensorFlow CPU path, which this B200 build does not "
+                 "have (no CPU fallback); pass a GPU index")
+    from pgmvae import _ffi, data, dist
+    from core.model import VqVAE, Adam
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1:
+        device = int(os.environ.get("LOCAL_RANK", device))
+    ctx = _ffi.get_context(device)
+    comm, rank, world = dist.init_from_env(ctx)
+
+    os.environ['PYTHONHASHSEED'] = '0'
+    rdn.seed(seed)
+    np.random.seed(seed)
+    identifier = f"{name}_K-{K}_D-{D}_bs-{bs}_epk-{epochs}_lr-{learn_rate}_bta-{beta}_ema-{ema}_gma-{gamma}_sd-{seed}-{note}"
+    n_var = bl[name]['vars']
+
+    def get_data(tvt):
+        ys = data.load_split(name, tvt, n_var)
+        return ys, ys          # the path consumes y directly; x == y stands for make_xs(ys)
+
+    train_x, train_y = get_data('train')
+    model = VqVAE(units=bl[name]['units'], nvar=n_var, dim=D, k=K, cost=beta, decay=gamma, ema=ema, seed=seed,
+                  max_batch=max(bs, 4096), device=device, comm=comm)
+    optimizer = Adam(lr=learn_rate)
+    model.compile(optimizer=optimizer, loss='mse', metrics=['mae'])
+    model.fit(train_x, train_x, batch_size=bs, epochs=epochs, verbose=vb)
+
+    def shard(a):
+        lo, hi = dist.shard_bounds(a.shape[0], rank, world)
+        return a[lo:hi]
+
+    # conditional distribution from the training data (counts are summed over ranks)
+    model.dist = model.cpt(shard(train_x), shard(train_y))
+
+    test_x, test_y = get_data('test')
+    valid_x, valid_y = get_data('valid')
+    pll_train = model.pseudo_log_likelihood(shard(train_x), shard(train_y), total=train_y.shape[0])
+    pll_valid = model.pseudo_log_likelihood(shard(valid_x), shard(valid_y), total=valid_y.shape[0])
+    pll_test = model.pseudo_log_likelihood(shard(test_x), shard(test_y), total=test_y.shape[0])
+
+    out = f' pll-train:{pll_train} pll-valid:{pll_valid} pll-test:{pll_test} cmll-test:{1}'
+    if rank == 0:
+        with open('result.txt', 'a') as f:
+            f.write(identifier + out + '\n')
+        print(identifier + out)
+    return pll_train, pll_valid, pll_test
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,187 @@
+"""GPU parity tests, model level: the fused training step, VqVAE.count / cpt / PLL and the
+run.py flow through the reference-facing API, against the committed oracle fixtures and the
+live oracle.  Floating point within 1e-3 relative (north_star); counts and codes exact."""
+import glob
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+import pgmvae_oracle as O
+from test_oracle import load_case, make_oracle
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CASES = ["v4_ema", "v9_grad", "v16_ema"]
+
+
+def rel_err(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-12)
+
+
+def build(cfg, params, max_batch=None):
+    from core.model import VqVAE, Adam
+    m = VqVAE(cfg["units"], cfg["V"], cfg["D"], cfg["K"], cost=cfg["cost"], decay=cfg["decay"], ema=cfg["ema"],
+              max_batch=max_batch or max(cfg["B"], 256))
+    m.set_weights_from(params)
+    m.compile(optimizer=Adam(lr=cfg["lr"]), loss="mse", metrics=["mae"])
+    return m
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_forward_activations_and_codes(ctx, name):
+    z, cfg, params = load_case(name)
+    m = build(cfg, params)
+    y = z["y_train"][0]
+    onehot = m(y, code_only=True)
+    idx = onehot.argmax(-1)
+    safe = z["act.gap"] > 1e-5
+    np.testing.assert_array_equal(idx[safe], z["act.idx"][safe])
+    rec = m(O.make_xs(y).numpy(), training=False)           # materialised reference input accepted
+    assert rec.shape == (cfg["B"], cfg["V"], cfg["V"] - 1)
+    assert rel_err(rec, z["act.out"]) < 1e-4
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_gradients_first_step(ctx, name):
+    import ctypes as C
+    from pgmvae import _ffi
+    z, cfg, params = load_case(name)
+    m = build(cfg, params)
+    y = np.ascontiguousarray(z["y_train"][0])
+    met = (C.c_double * 4)()
+    _ffi.check(_ffi.lib().pgmvae_model_train_step(m._h, y.ctypes.data, 0, y.shape[0], y.shape[0], cfg["lr"], None, 1, met))
+    np.testing.assert_allclose(list(met), z["metrics"][0], rtol=1e-5)
+    for k in z.files:
+        if k.startswith("grad1."):
+            got = m._get_tensor("grad." + k[6:])
+            assert rel_err(got, z[k]) < 1e-4, k
+    if cfg["ema"]:
+        np.testing.assert_array_equal(m._get_tensor("vq.stat_c"), z["stat1.counts"])
+        assert rel_err(m._get_tensor("vq.stat_w"), z["stat1.dw"]) < 1e-5
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_three_training_steps_match_golden(ctx, name):
+    z, cfg, params = load_case(name)
+    m = build(cfg, params)
+    for s in range(cfg["steps"]):
+        met = m.train_on_batch(np.ascontiguousarray(z["y_train"][s]))
+        exp = z["metrics"][s]
+        np.testing.assert_allclose([met["loss"], met["mse"], met["mae"], met["vq_loss"]], exp, rtol=1e-3)
+        if s in (0, cfg["steps"] - 1):
+            tag = f"state{s + 1}."
+            for k in z.files:
+                if k.startswith(tag):
+                    n = k[len(tag):]
+                    assert rel_err(m._get_tensor(n), z[k]) < 1e-3, (s, n)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_count_cpt_pll_match_golden(ctx, name):
+    z, cfg, params = load_case(name)
+    m = build(cfg, params)
+    last = f"state{cfg['steps']}."
+    m.load_state_dict({k[len(last):]: z[k] for k in z.files if k.startswith(last) and "adam" not in k})
+    y = z["y_eval"]
+    # oracle codes and gaps for the evaluation split, to exclude numerically tied rows
+    om = make_oracle(cfg, {k[len(last):]: z[k] for k in z.files if k.startswith(last) and ".adam_" not in k
+                           and not k.endswith(("ema_w", "ema_cluster_size", "biased_w", "biased_c"))})
+    keep = {}
+    om(O.make_xs(y), code_only=True, keep=keep)
+    _, gap = O.vq_assign(keep["h5"], om.p["vq.embeddings"])
+    n1, n0 = m.count(y)
+    if bool((gap > 1e-5).all()):
+        np.testing.assert_array_equal(n1, z["n1"])
+        np.testing.assert_array_equal(n0, z["n0"])
+    assert np.abs(n1 - z["n1"]).sum() <= 2 * int((gap <= 1e-5).sum())
+    assert (n1 + n0).sum() == y.shape[0] * cfg["V"]
+    m.dist = m.cpt(O.make_xs(y).numpy(), y)                  # reference call shape cpt(x, y)
+    assert rel_err(m.dist, z["dist"]) < 1e-3
+    pll = m.pseudo_log_likelihood(y)
+    assert abs(pll - float(z["pll"])) <= 1e-3 * abs(float(z["pll"]))
+
+
+@pytest.mark.parametrize("ema,B", [(True, 256), (False, 53), (True, 1)])
+def test_live_oracle_parity_plants_scale(ctx, ema, B):
+    """cfg2 shapes (V=69, units 50/40/30/20, D=16, K=128) at a batch the oracle finishes quickly."""
+    units, V, D, K = [50, 40, 30, 20], 69, 16, 128
+    params = O.init_params(units, V, D, K, seed=9)
+    cfg = dict(units=units, V=V, D=D, K=K, cost=0.25, decay=0.99, ema=ema, B=B, lr=1e-3)
+    m = build(cfg, {k: v.numpy() for k, v in params.items()}, max_batch=256)
+    om = make_oracle(cfg, {k: v.numpy() for k, v in params.items()})
+    ys = O.synthetic_binary(2 * B, V, seed=2).reshape(2, B, V)
+    for s in range(2):
+        met = m.train_on_batch(np.ascontiguousarray(ys[s]))
+        exp = om.train_step(O.make_xs(ys[s]), lr=1e-3)
+        for k in ("loss", "mse", "mae", "vq_loss"):
+            assert abs(met[k] - exp[k]) <= 1e-3 * abs(exp[k]) + 1e-9, (s, k, met[k], exp[k])
+    st = om.state_numpy()
+    for n in ["fd0.kernel", "fd4.bias", "fd5.kernel", "fd9.kernel", "fd9.bias", "vq.embeddings"]:
+        assert rel_err(m._get_tensor(n), st[n]) < 1e-3, n
+
+
+def test_fit_with_pinned_order_and_partial_batch(ctx):
+    z, cfg, params = load_case("v4_ema")
+    m = build(cfg, params)
+    om = make_oracle(cfg, params)
+    y = z["y_eval"][:50]
+    order = [np.random.default_rng(e).permutation(50) for e in range(2)]
+    h = m.fit(y, y, batch_size=16, epochs=2, order=order)          # 3 full batches + one of 2
+    ho = om.fit(O.make_xs(y), 16, 2, lr=cfg["lr"], order=order)
+    w = np.array([16, 16, 16, 2] * 2, dtype=np.float64)
+    lo = np.array([d["loss"] for d in ho])
+    for e in range(2):
+        exp = (lo[4 * e:4 * e + 4] * w[:4]).sum() / 50
+        assert abs(h.history["loss"][e] - exp) <= 1e-3 * abs(exp)
+    assert rel_err(m.fd3.kernel, om.p["fd3.kernel"].detach().numpy()) < 1e-3
+
+
+def test_full_size_properties_cfg2(ctx):
+    """BASELINE cfg2 at full size (B=4096): size-independent invariants."""
+    from core.model import VqVAE
+    from pgmvae import data
+    V, D, K, B = 69, 16, 128, 4096
+    m = VqVAE([50, 40, 30, 20], V, D, K, cost=0.25, decay=0.99, ema=True, seed=0, max_batch=B)
+    y = data.synthetic_binary(3 * B, V, seed=0)
+    losses = []
+    for s in range(3):
+        met = m.train_on_batch(np.ascontiguousarray(y[s * B:(s + 1) * B]))
+        assert all(np.isfinite(v) for v in met.values())
+        losses.append(met["loss"])
+        # step-1 identity of the zero-debiased EMA: the visible counts are the raw histogram
+        if s == 0:
+            np.testing.assert_allclose(m.vq_layer.ema_cluster_size.sum(1), B, rtol=1e-5)
+    assert 0.15 < losses[0] < 0.35                                   # sigmoid(0)=0.5 against 0/1 data
+    n1, n0 = m.count(y)
+    assert (n1 + n0).sum() == y.shape[0] * V
+    np.testing.assert_array_equal((n1 + n0).sum(1), y.shape[0])
+    np.testing.assert_array_equal(n1.sum(1), y.sum(0))               # ones per variable
+    n1b, n0b = m.count(y)                                            # idempotent
+    np.testing.assert_array_equal(n1, n1b)
+    # counting in two halves adds up (linearity over samples)
+    a1, a0 = m.count(y[:5000])
+    b1, b0 = m.count(y[5000:])
+    np.testing.assert_array_equal(a1 + b1, n1)
+    m.dist = m.cpt(y)
+    pll = m.pseudo_log_likelihood(y)
+    assert -V * np.log(2) * 1.2 < pll < 0
+
+
+def test_run_py_nltcs_end_to_end(ctx, tmp_path):
+    """cfg1 flow: run.py on nltcs (few epochs), identifier and result line as the reference."""
+    env = dict(os.environ, PGMVAE_DATA="")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "pgm-vae_b200", "run.py"), "-n", "nltcs", "-k", "32", "-d", "4",
+                        "-b", "256", "-e", "3", "--ema", "-u", "0"], capture_output=True, text=True, cwd=tmp_path, env=env)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = open(tmp_path / "result.txt").read().strip()
+    assert line.startswith("nltcs_K-32_D-4_bs-256_epk-3_lr-0.001_bta-0.25_ema-True_gma-0.99_sd-0- pll-train:")
+    assert line.endswith("cmll-test:1")
+    vals = {k: float(v) for k, v in (t.split(":") for t in line.split(" ")[1:])}
+    for k in ("pll-train", "pll-valid", "pll-test"):
+        assert -16 * np.log(2) < vals[k] < -3.0
