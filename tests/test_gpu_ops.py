@@ -128,7 +128,8 @@ def test_vq_layer_outputs_and_losses(ctx, ema):
                        params={**O.init_params([3, 3, 3, 3], V, D, K), "vq.embeddings": torch.from_numpy(emb)})
     exp = om.vq_layer(torch.from_numpy(z), training=False).numpy()
     np.testing.assert_allclose(out, exp, rtol=1e-6, atol=1e-7)
-    assert abs(layer.losses[0] - float(om.losses[0])) <= 1e-5 * abs(float(om.losses[0]))
+    ref_loss = float(om.losses[0].detach())
+    assert abs(layer.losses[0] - ref_loss) <= 1e-5 * abs(ref_loss)
 
 
 def test_ema_update_three_steps(ctx):
