@@ -154,6 +154,11 @@ int pgmvae_vq_assign(pgmvae_ctx* ctx, void* stream,
                      float* best_opt, float* gap_opt,
                      int G, int B, int D, int K);
 
+/* Rows of the last tensor-core pgmvae_vq_assign on this context (precision TF32/BF16) whose
+ * top-2 gap fell inside the low-precision error bound and were re-scored in exact fp32.
+ * Synchronises the context stream.                                                       */
+int pgmvae_vq_assign_rescored(pgmvae_ctx* ctx, int G, int K, int* out);
+
 /* gather + losses + straight-through (core/quantizer.py:49-53, :141-142,156):
  *     q = e[idx];  st = z + (q - z);  loss_acc[0] += sum (q - z)^2                       */
 int pgmvae_vq_quantize(pgmvae_ctx* ctx, void* stream,

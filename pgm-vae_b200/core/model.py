@@ -297,9 +297,7 @@ class VqVAE:
         as float64 [V,K].  With a communicator the samples are this rank's shard and the
         counts are summed over ranks."""
         data = to_y(y if y is not None else x)
-        n = data.shape[0]
-        if n > self.max_batch:
-            self._ensure_capacity(min(n, 8192))
+        n = data.shape[0]          # pgmvae_model_count walks the samples in chunks of max_batch
         n1 = np.zeros((self.nvar, self.k), dtype=np.uint64)
         n0 = np.zeros((self.nvar, self.k), dtype=np.uint64)
         _ffi.check(_ffi.lib().pgmvae_model_count(self._h, data.ctypes.data, 0, n, n1.ctypes.data, n0.ctypes.data))

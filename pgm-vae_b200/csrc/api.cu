@@ -123,6 +123,7 @@ int pgmvae_ctx_destroy(pgmvae_ctx* ctx) {
     if (!ctx) return PGMVAE_OK;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    if (ctx->scratch) cudaFree(ctx->scratch);
     cudaEventDestroy(ctx->ev0);
     cudaEventDestroy(ctx->ev1);
     cudaStreamDestroy(ctx->stream);

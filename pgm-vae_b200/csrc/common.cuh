@@ -27,6 +27,8 @@ struct pgmvae_ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int64_t launches = 0;
     size_t smem_optin = 0;
+    void* scratch = nullptr;      // grown on demand by the tensor-core kernels
+    size_t scratch_bytes = 0;
 };
 
 void pgmvae_set_error(const char* fmt, ...);
