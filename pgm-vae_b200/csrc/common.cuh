@@ -29,6 +29,7 @@ struct pgmvae_ctx {
     size_t smem_optin = 0;
     void* scratch = nullptr;      // grown on demand by the tensor-core kernels
     size_t scratch_bytes = 0;
+    size_t vq_cnt_off = 0;
 };
 
 void pgmvae_set_error(const char* fmt, ...);

@@ -55,9 +55,10 @@ int pgmvae_vq_assign(pgmvae_ctx* ctx, void* stream, const float* z, int64_t z_gs
                      int B, int D, int K) {
     PG_CHECK_ARG(ctx && z && e && idx);
     PG_CHECK_ARG(G >= 0 && B >= 0 && D > 0 && K > 0 && ldz >= D && lde >= D);
-    if (ctx->precision != PGMVAE_PREC_FP32 && pg_vq_assign_tc_supported(D, K, ldz, lde, z, e, z_gs, e_gs))
-        return pg_vq_assign_tc(ctx, pg_stream(ctx, stream), z, z_gs, ldz, e, e_gs, lde, idx, idx_gs, best_opt, gap_opt,
-                               G, B, D, K);
+    if (ctx->precision != PGMVAE_PREC_FP32 &&
+        pg_vq_assign_tc_supported(ctx->precision, D, K, ldz, lde, z, e, z_gs, e_gs))
+        return pg_vq_assign_tc(ctx, pg_stream(ctx, stream), ctx->precision, z, z_gs, ldz, e, e_gs, lde, idx, idx_gs,
+                               best_opt, gap_opt, G, B, D, K);
     return pg_vq_assign_fp32(ctx, pg_stream(ctx, stream), z, z_gs, ldz, e, e_gs, lde, idx, idx_gs, best_opt, gap_opt,
                              G, B, D, K);
 }

@@ -22,9 +22,9 @@ int pg_vq_assign_fp32(pgmvae_ctx* ctx, cudaStream_t st, const float* z, int64_t 
                       int B, int D, int K);
 
 // tcgen05 tensor-core kernels (vq_tc.cu, dense_tc.cu)
-bool pg_vq_assign_tc_supported(int D, int K, int ldz, int lde, const float* z, const float* e, int64_t z_gs,
+bool pg_vq_assign_tc_supported(int prec, int D, int K, int ldz, int lde, const float* z, const float* e, int64_t z_gs,
                                int64_t e_gs);
-int pg_vq_assign_tc(pgmvae_ctx* ctx, cudaStream_t st, const float* z, int64_t z_gs, int ldz, const float* e,
+int pg_vq_assign_tc(pgmvae_ctx* ctx, cudaStream_t st, int prec, const float* z, int64_t z_gs, int ldz, const float* e,
                     int64_t e_gs, int lde, int32_t* idx, int64_t idx_gs, float* best_opt, float* gap_opt, int G, int B,
                     int D, int K);
 int pg_vq_assign_tc_last_flagged(pgmvae_ctx* ctx, int G, int K, int* out);

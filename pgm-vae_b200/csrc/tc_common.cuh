@@ -26,29 +26,29 @@ inline EncodeTiledFn encode_fn() {
     return fn;
 }
 
-// fp32 tensor [groups][rows][cols] (cols contiguous, row stride ld, group stride gs; gs == 0 is
-// expressed as a single group), box = [1][box_rows][32 floats = 128 B], 128-byte swizzle,
-// out-of-bounds elements read as zero.
-inline int make_map_f32(CUtensorMap* map, const float* base, uint64_t cols, uint64_t rows, uint64_t groups,
-                        uint64_t ld, uint64_t gs, uint32_t box_cols, uint32_t box_rows) {
+// tensor [groups][rows][cols] of fp32 (esize 4) or fp16 (esize 2): cols contiguous, row stride ld
+// and group stride gs in ELEMENTS (gs == 0 = one shared matrix); box = [1][box_rows][box_cols]
+// with box_cols * esize = 128 bytes, 128-byte swizzle, out-of-bounds elements read as zero.
+inline int make_map(CUtensorMap* map, const void* base, int esize, uint64_t cols, uint64_t rows, uint64_t groups,
+                    uint64_t ld, uint64_t gs, uint32_t box_cols, uint32_t box_rows) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) {
         pgmvae_set_error("cuTensorMapEncodeTiled unavailable");
         return PGMVAE_ECUDA;
     }
-    if (((uintptr_t)base & 15) || (ld * 4) % 16 || (gs * 4) % 16) {
-        pgmvae_set_error("TMA operand must be 16-byte aligned (base %p, ld %llu, gs %llu)", (const void*)base,
+    if (((uintptr_t)base & 15) || (ld * esize) % 16 || (gs * esize) % 16) {
+        pgmvae_set_error("TMA operand must be 16-byte aligned (base %p, ld %llu, gs %llu)", base,
                          (unsigned long long)ld, (unsigned long long)gs);
         return PGMVAE_EINVAL;
     }
     if (gs == 0) { groups = 1; gs = rows * ld; }
     cuuint64_t dims[3] = {cols, rows, groups};
-    cuuint64_t strides[2] = {ld * 4, gs * 4};
+    cuuint64_t strides[2] = {ld * esize, gs * esize};
     cuuint32_t box[3] = {box_cols, box_rows, 1};
     cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)base, dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r = fn(map, esize == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, (void*)base,
+                    dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         pgmvae_set_error("cuTensorMapEncodeTiled failed (%d): cols %llu rows %llu groups %llu ld %llu gs %llu", (int)r,
                          (unsigned long long)cols, (unsigned long long)rows, (unsigned long long)groups,
@@ -100,6 +100,14 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m
             smem_u32(smem_dst)),
         "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
+}
+
+// plain (non-tensor) bulk copy global -> shared, completing on an mbarrier; 16-byte granularity
+__device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"((uint64_t)gsrc), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
 }
 
 // ------------------------------------------------------------------ device: tcgen05 / TMEM
@@ -164,6 +172,21 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, float (&r)[32]) {
         : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// wait::ld plus a register dependency: nothing that reads r[] may be scheduled above the wait
+__device__ __forceinline__ void tmem_ld_wait(float (&r)[32]) {
+    uint32_t* u = reinterpret_cast<uint32_t*>(r);
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(u[0]), "+r"(u[1]), "+r"(u[2]), "+r"(u[3]), "+r"(u[4]), "+r"(u[5]), "+r"(u[6]), "+r"(u[7]),
+                   "+r"(u[8]), "+r"(u[9]), "+r"(u[10]), "+r"(u[11]), "+r"(u[12]), "+r"(u[13]), "+r"(u[14]), "+r"(u[15])
+                 :
+                 : "memory");
+    asm volatile(""
+                 : "+r"(u[16]), "+r"(u[17]), "+r"(u[18]), "+r"(u[19]), "+r"(u[20]), "+r"(u[21]), "+r"(u[22]),
+                   "+r"(u[23]), "+r"(u[24]), "+r"(u[25]), "+r"(u[26]), "+r"(u[27]), "+r"(u[28]), "+r"(u[29]),
+                   "+r"(u[30]), "+r"(u[31])
+                 :
+                 : "memory");
+}
 
 // ------------------------------------------------------------------ UMMA descriptors
 // Shared-memory matrix descriptor, 128-byte swizzle.  The tile is stored as rows of 128 bytes

@@ -18,7 +18,7 @@ def main():
     ap.add_argument("--n", type=int, default=1 << 20)
     ap.add_argument("--d", type=int, default=64)
     ap.add_argument("--k", type=int, default=8192)
-    ap.add_argument("--prec", default="tf32", choices=["fp32", "tf32"])
+    ap.add_argument("--prec", default="tf32", choices=["fp32", "tf32", "f16"])
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--clustered", action="store_true")
     ap.add_argument("--scatter", action="store_true")
@@ -35,7 +35,7 @@ def main():
     dz, de = _ffi.DeviceArray.from_numpy(ctx, z), _ffi.DeviceArray.from_numpy(ctx, e)
     idx = _ffi.DeviceArray(ctx, (1, a.n), np.int32)
     cnt, dw = _ffi.DeviceArray(ctx, (1, a.k)), _ffi.DeviceArray(ctx, (1, a.k, a.d))
-    ctx.set_precision(_ffi.PREC_TF32 if a.prec == "tf32" else _ffi.PREC_FP32)
+    ctx.set_precision({"fp32": _ffi.PREC_FP32, "tf32": _ffi.PREC_TF32, "f16": _ffi.PREC_BF16}[a.prec])
 
     def run():
         _ffi.check(L.pgmvae_vq_assign(ctx.h, None, dz.ptr, a.n * a.d, a.d, de.ptr, a.k * a.d, a.d, idx.ptr, a.n,
@@ -54,7 +54,7 @@ def main():
     run()
     prof = ctx.profile_end()
     n = C.c_int(0)
-    if a.prec == "tf32":
+    if a.prec != "fp32":
         _ffi.check(L.pgmvae_vq_assign_rescored(ctx.h, 1, a.k, C.byref(n)))
     flops = 2.0 * a.n * a.d * a.k
     print(json.dumps({"n": a.n, "d": a.d, "k": a.k, "prec": a.prec, "clustered": a.clustered, "scatter": a.scatter,

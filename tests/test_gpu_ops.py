@@ -83,14 +83,14 @@ def _assign_case(V, B, D, K, seed, clustered=False):
     (16, 256, 4, 32, False), (16, 53, 4, 32, True), (69, 512, 16, 128, False), (3, 1000, 64, 512, True),
     (1, 4096, 64, 1024, False), (2, 130, 10, 7, False), (5, 77, 30, 1, False),
 ])
-@pytest.mark.parametrize("prec", ["fp32", "tf32"])
+@pytest.mark.parametrize("prec", ["fp32", "tf32", "f16"])
 def test_vq_assign_indices(ctx, V, B, D, K, clustered, prec):
     from core.quantizer import VectorQuantizer
     from pgmvae import _ffi
     z, emb = _assign_case(V, B, D, K, seed=V + B + D + K, clustered=clustered)
     layer = VectorQuantizer(D, K, 0.25, V)
     layer.embeddings = emb
-    ctx.set_precision(_ffi.PREC_TF32 if prec == "tf32" else _ffi.PREC_FP32)
+    ctx.set_precision({"fp32": _ffi.PREC_FP32, "tf32": _ffi.PREC_TF32, "f16": _ffi.PREC_BF16}[prec])
     try:
         onehot = layer(z, code_only=True)
     finally:
@@ -221,7 +221,7 @@ def test_adam_step(ctx):
 
 
 @pytest.mark.parametrize("G,B,D,K", [(1, 8192, 64, 8192), (3, 1000, 64, 512), (69, 4096, 16, 128), (2, 300, 128, 600),
-                                     (16, 256, 4, 32)])
+                                     (16, 256, 4, 32), (2, 513, 40, 100)])
 def test_vq_assign_tensor_core_equals_fp32_path(ctx, G, B, D, K):
     """tcgen05 (tf32) assignment + fp32 re-scoring of the ambiguous rows must reproduce the exact-fp32
     CUDA-core kernel index for index (and therefore the oracle outside the 1e-5 band)."""
@@ -233,7 +233,8 @@ def test_vq_assign_tensor_core_equals_fp32_path(ctx, G, B, D, K):
     dz, de = _ffi.DeviceArray.from_numpy(ctx, z), _ffi.DeviceArray.from_numpy(ctx, e)
     L = _ffi.lib()
     out = {}
-    for prec in (_ffi.PREC_FP32, _ffi.PREC_TF32):
+    nres = {}
+    for prec in (_ffi.PREC_FP32, _ffi.PREC_TF32, _ffi.PREC_BF16):
         idx = _ffi.DeviceArray(ctx, (G, B), np.int32)
         best = _ffi.DeviceArray(ctx, (G, B), np.float32)
         gap = _ffi.DeviceArray(ctx, (G, B), np.float32)
@@ -244,16 +245,43 @@ def test_vq_assign_tensor_core_equals_fp32_path(ctx, G, B, D, K):
         finally:
             ctx.set_precision(_ffi.PREC_FP32)
         out[prec] = (idx.numpy(), best.numpy(), gap.numpy())
-    n = C.c_int(0)
-    _ffi.check(L.pgmvae_vq_assign_rescored(ctx.h, G, K, C.byref(n)))
+        n = C.c_int(0)
+        if prec != _ffi.PREC_FP32:
+            _ffi.check(L.pgmvae_vq_assign_rescored(ctx.h, G, K, C.byref(n)))
+        nres[prec] = n.value
     i32, b32, g32 = out[_ffi.PREC_FP32]
-    itc, btc, gtc = out[_ffi.PREC_TF32]
-    mism = int((i32 != itc).sum())
-    print(f"vq tc: G={G} B={B} D={D} K={K}: rescored {n.value}/{G * B} rows, mismatches {mism}")
-    assert mism == 0
-    assert 0 <= n.value <= G * B
-    # untouched rows report tf32 distances: close to fp32; re-scored rows are exact
-    np.testing.assert_allclose(btc, b32, rtol=0, atol=2e-2 * max(1.0, float(np.abs(b32).max())))
     idx_o, gap_o = O.vq_assign(z, np.ascontiguousarray(e.transpose(0, 2, 1)))
     safe = gap_o.numpy() > 1e-5
-    np.testing.assert_array_equal(itc[safe], idx_o.numpy()[safe])
+    for prec, nm in ((_ffi.PREC_TF32, "tf32"), (_ffi.PREC_BF16, "f16")):
+        itc, btc, gtc = out[prec]
+        mism = int((i32 != itc).sum())
+        print(f"vq tc {nm}: G={G} B={B} D={D} K={K}: full-scan rows {nres[prec]}/{G * B}, mismatches {mism}")
+        assert mism == 0
+        assert 0 <= nres[prec] <= G * B // 100 + 1
+        np.testing.assert_array_equal(btc, b32)          # candidates are re-scored with the fp32 arithmetic
+        np.testing.assert_array_equal(itc[safe], idx_o.numpy()[safe])
+
+
+def test_vq_assign_tensor_core_dead_codes(ctx):
+    """Many identical (dead, all-zero) codes tie exactly: the candidate list overflows and the exact full
+    scan must still return the lowest index, as tf.argmin does."""
+    from pgmvae import _ffi
+    G, B, D, K = 2, 700, 16, 256
+    rng = np.random.default_rng(3)
+    e = rng.uniform(-0.3, 0.3, (G, K, D)).astype(np.float32)
+    e[:, 40:, :] = 0.0                                      # 216 dead codes
+    z = (0.02 * rng.standard_normal((G, B, D))).astype(np.float32)      # closest to the zero vector
+    dz, de = _ffi.DeviceArray.from_numpy(ctx, z), _ffi.DeviceArray.from_numpy(ctx, e)
+    res = {}
+    for prec in (_ffi.PREC_FP32, _ffi.PREC_TF32, _ffi.PREC_BF16):
+        idx = _ffi.DeviceArray(ctx, (G, B), np.int32)
+        ctx.set_precision(prec)
+        try:
+            _ffi.check(_ffi.lib().pgmvae_vq_assign(ctx.h, None, dz.ptr, B * D, D, de.ptr, K * D, D, idx.ptr, B, None, None,
+                                                   G, B, D, K))
+        finally:
+            ctx.set_precision(_ffi.PREC_FP32)
+        res[prec] = idx.numpy()
+    np.testing.assert_array_equal(res[_ffi.PREC_TF32], res[_ffi.PREC_FP32])
+    np.testing.assert_array_equal(res[_ffi.PREC_BF16], res[_ffi.PREC_FP32])
+    assert (res[_ffi.PREC_FP32] == 40).mean() > 0.5
