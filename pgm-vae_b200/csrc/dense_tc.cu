@@ -1,0 +1,411 @@
+// Kernel (a), tensor-core flavour: the packed per-variable dense layer as a grouped GEMM on
+// tcgen05 (kind::tf32 directly on the fp32 tensors as they lie in HBM, fp32 accumulation in
+// TMEM), operands staged by TMA with the 128-byte swizzle, fused epilogues.  Replaces
+// tf.matmul + bias + activation of FatDense.call (reference core/dense.py:99-111) and the
+// gradient GEMMs of its autodiff (run.py:62).
+//
+//   forward : C[B,out] = A[B,in]   (K-major)  x  W[in,out]  (N contiguous -> MN-major B)
+//   dgrad   : C[B,in]  = dY[B,out] (K-major)  x  W[in,out] read as [n=in][k=out] (K-major B)
+//   wgrad   : C[in,out]= X[B,in] read as [k=b][m=in] (MN-major A) x dY[B,out] (MN-major B),
+//             reduction over the batch split across CTAs, fp32 reductions into dW
+//
+// One CTA computes one 128 x BN output tile of one variable: warp 0 = TMA producer over the
+// k-blocks (32 fp32 = one swizzle row per k-block, `stages`-deep ring), warp 1 = MMA issuer,
+// then all four warps run the epilogue (tcgen05.ld 32x32b: one output row per thread).
+// Tiles are small and many, so latency is hidden by 2-3 resident CTAs per SM rather than by a
+// persistent tile loop.  Out-of-bounds rows / columns / k are zero-filled by TMA, so ragged
+// batches and the awkward layer widths (15, 14, 13, 50, 1555 ...) need no host-side padding
+// beyond 16-byte row strides.
+#include "common.cuh"
+#include "ops.cuh"
+#include "tc_common.cuh"
+
+namespace {
+
+constexpr int TM = 128;
+constexpr int KBLK = 32;                          // fp32 elements per k-block (128 bytes)
+constexpr int A_STAGE_BYTES = TM * 128;           // 16 KB
+constexpr int MAX_STAGES = 4;
+
+enum { EPI_BIAS_ACT = 0, EPI_SIGMOID_MSE = 1, EPI_DGRAD = 2, EPI_WGRAD = 3 };
+
+struct DenseTcP {
+    int M, N, K;                     // per-variable problem: C[M,N] = A[M,K] * B[K,N]
+    int BN, kblocks, stages, tmem_cols;
+    int a_mn, b_mn;                  // operand is MN-major (panels of 128 bytes along M / N)
+    int a_shared;                    // A is one matrix shared by all variables (the raw data y)
+    int vecC;                        // rows of C / aux are 16-byte aligned
+    int S, kb_per_split;             // split of the k-blocks over CTAs (wgrad)
+    float* C; long long c_gs; int ldc;
+    const float* bias; long long bias_gs; int act;
+    const float* aux; long long aux_gs; int ldaux;          // SIGMOID_MSE: y (shared); DGRAD: h_in
+    float* C2; double* acc; float gscale; int g0;
+    const float* z; const float* q; long long zq_gs; int ldzq; float cscale;
+    int zero_row_base;
+};
+
+// one thread moves (up to) 32 consecutive floats of its row; 128-bit accesses when the row is aligned
+__device__ __forceinline__ void store_row(float* dst, const float (&v)[32], int nv, int vec) {
+    if (vec && nv == 32) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+            if (j < nv) dst[j] = v[j];
+    }
+}
+__device__ __forceinline__ void load_row(const float* src, float (&v)[32], int nv, int vec) {
+    if (vec && nv == 32) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+            const float4 t = *reinterpret_cast<const float4*>(src + j);
+            v[j] = t.x; v[j + 1] = t.y; v[j + 2] = t.z; v[j + 3] = t.w;
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = j < nv ? src[j] : 0.f;
+    }
+}
+
+template <int EPI>
+__global__ void __launch_bounds__(128) dense_tc_kernel(const __grid_constant__ CUtensorMap mapA,
+                                                       const __grid_constant__ CUtensorMap mapB, const DenseTcP p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int b_stage_bytes = p.BN * 128;
+    uint8_t* sA = smem;                                           // [stages][16 KB]
+    uint8_t* sB = sA + (size_t)p.stages * A_STAGE_BYTES;          // [stages][BN*128]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sB + (size_t)p.stages * b_stage_bytes);
+    uint64_t* full = bars;                       // [MAX_STAGES]
+    uint64_t* empty = bars + MAX_STAGES;         // [MAX_STAGES]
+    uint64_t* acc_full = bars + 2 * MAX_STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 1);
+    __shared__ double red[2][4];
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = blockIdx.z / p.S, split = blockIdx.z - g * p.S;
+    const int m0 = blockIdx.y * TM, n0 = blockIdx.x * p.BN;
+    const int kb_beg = split * p.kb_per_split;
+    const int kb_end = min(p.kblocks, kb_beg + p.kb_per_split);
+    const int nkb = kb_end - kb_beg;
+
+    if (warp == 0 && lane == 0) {
+        tc::tma_prefetch_desc(&mapA);
+        tc::tma_prefetch_desc(&mapB);
+        for (int s = 0; s < MAX_STAGES; ++s) {
+            tc::mbar_init(&full[s], 1);
+            tc::mbar_init(&empty[s], 1);
+        }
+        tc::mbar_init(acc_full, 1);
+        tc::fence_barrier_init();
+    }
+    if (warp == 2) {
+        tc::tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+        tc::tmem_relinquish();
+    }
+    tc::fence_before_thread_sync();
+    __syncthreads();
+    tc::fence_after_thread_sync();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (nkb > 0) {
+        if (warp == 0 && lane == 0) {
+            // ===================== TMA producer =====================
+            const uint32_t stage_tx = (uint32_t)(A_STAGE_BYTES + b_stage_bytes);
+            uint32_t s = 0, ph = 0;
+            const int ga = p.a_shared ? 0 : g;
+            for (int kb = kb_beg; kb < kb_end; ++kb) {
+                tc::mbar_wait(&empty[s], ph ^ 1);
+                tc::mbar_arrive_expect_tx(&full[s], stage_tx);
+                uint8_t* a_dst = sA + (size_t)s * A_STAGE_BYTES;
+                uint8_t* b_dst = sB + (size_t)s * b_stage_bytes;
+                if (!p.a_mn) {
+                    tc::tma_load_3d(a_dst, &mapA, &full[s], kb * KBLK, m0, ga);                 // [128 m][32 k]
+                } else {
+                    for (int pn = 0; pn < TM / 32; ++pn)                                        // 4 panels [32 k][32 m]
+                        tc::tma_load_3d(a_dst + pn * 4096, &mapA, &full[s], m0 + pn * 32, kb * KBLK, ga);
+                }
+                if (!p.b_mn) {
+                    tc::tma_load_3d(b_dst, &mapB, &full[s], kb * KBLK, n0, g);                 // [BN n][32 k]
+                } else {
+                    for (int pn = 0; pn < p.BN / 32; ++pn)                                      // panels [32 k][32 n]
+                        tc::tma_load_3d(b_dst + pn * 4096, &mapB, &full[s], n0 + pn * 32, kb * KBLK, g);
+                }
+                if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1; }
+            }
+        } else if (warp == 1 && lane == 0) {
+            // ===================== MMA issuer =====================
+            const uint32_t idesc = tc::make_idesc(2, TM, p.BN, p.a_mn, p.b_mn);
+            // K-major: rows of 128 B along k, 8-row atoms 1024 B apart; one MMA (k = 8) advances 32 B.
+            // MN-major: panels of [32 k][128 B along m/n], 4096 B apart (LBO), 8-k atoms 1024 B apart
+            //           (SBO); one MMA (k = 8) advances one atom = 1024 B.
+            const uint64_t dA0 = tc::make_smem_desc(tc::smem_u32(sA), p.a_mn ? 4096 : 16, 1024);
+            const uint64_t dB0 = tc::make_smem_desc(tc::smem_u32(sB), p.b_mn ? 4096 : 16, 1024);
+            const uint32_t a_step = (p.a_mn ? 1024u : 32u) >> 4, b_step = (p.b_mn ? 1024u : 32u) >> 4;
+            const uint32_t a_stage = (uint32_t)A_STAGE_BYTES >> 4, b_stage = (uint32_t)b_stage_bytes >> 4;
+            uint32_t s = 0, ph = 0;
+            for (int kb = kb_beg; kb < kb_end; ++kb) {
+                tc::mbar_wait(&full[s], ph);
+                tc::fence_after_thread_sync();
+                const uint64_t dA = dA0 + (uint64_t)(s * a_stage), dB = dB0 + (uint64_t)(s * b_stage);
+#pragma unroll
+                for (int k4 = 0; k4 < 4; ++k4)
+                    tc::mma_tf32(tmem_base, dA + (uint64_t)(k4 * a_step), dB + (uint64_t)(k4 * b_step), idesc,
+                                 (kb > kb_beg || k4 > 0) ? 1u : 0u);
+                tc::mma_commit(&empty[s]);
+                if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1; }
+            }
+            tc::mma_commit(acc_full);
+        }
+        __syncwarp();
+        tc::mbar_wait(acc_full, 0);
+        tc::fence_after_thread_sync();
+    }
+
+    // ===================== epilogue: thread = output row =====================
+    const int row = m0 + warp * 32 + lane;
+    const bool rvalid = row < p.M;
+    const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
+    float sq = 0.f, ab = 0.f;
+    for (int c = 0; c < p.BN; c += 32) {
+        if (n0 + c >= p.N) break;                                   // uniform across the CTA
+        float v[32];
+        if (nkb > 0) {
+            tc::tmem_ld_32x32(taddr + c, v);
+            tc::tmem_ld_wait(v);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = 0.f;
+        }
+        const int nb = n0 + c;
+        if (!rvalid) continue;
+        const int nv = min(32, p.N - nb);                           // valid columns of this chunk
+        const long long off = (long long)g * p.c_gs + (long long)row * p.ldc + nb;
+        if (EPI == EPI_BIAS_ACT) {
+            const float* bias = p.bias ? p.bias + (long long)g * p.bias_gs + nb : nullptr;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const float x = v[j] + ((bias && j < nv) ? __ldg(bias + j) : 0.f);
+                v[j] = p.act == PGMVAE_ACT_SELU ? pg_selu(x) : (p.act == PGMVAE_ACT_SIGMOID ? pg_sigmoid(x) : x);
+            }
+            store_row(p.C + off, v, nv, p.vecC);
+        } else if (EPI == EPI_SIGMOID_MSE) {
+            const float* bias = p.bias ? p.bias + (long long)g * p.bias_gs + nb : nullptr;
+            float yv[32], o[32];
+            load_row(p.aux + (long long)row * p.ldaux + nb, yv, nv, p.vecC);
+            const int self = p.g0 + g;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                o[j] = pg_sigmoid(v[j] + ((bias && j < nv) ? __ldg(bias + j) : 0.f));
+                float dpre = 0.f;
+                if (j < nv && nb + j != self) {
+                    const float d = o[j] - yv[j];
+                    sq = fmaf(d, d, sq);
+                    ab += fabsf(d);
+                    dpre = p.gscale * d * o[j] * (1.0f - o[j]);
+                }
+                v[j] = dpre;
+            }
+            store_row(p.C + off, v, nv, p.vecC);
+            if (p.C2) store_row(p.C2 + off, o, nv, p.vecC);
+        } else if (EPI == EPI_DGRAD) {
+            if (p.z) {
+                float zv[32], qv[32];
+                const long long zo = (long long)g * p.zq_gs + (long long)row * p.ldzq + nb;
+                load_row(p.z + zo, zv, nv, p.vecC);
+                load_row(p.q + zo, qv, nv, p.vecC);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = fmaf(p.cscale, zv[j] - qv[j], v[j]);
+            }
+            if (p.aux) {
+                float hv[32];
+                load_row(p.aux + (long long)g * p.aux_gs + (long long)row * p.ldaux + nb, hv, nv, p.vecC);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    if (p.act == PGMVAE_ACT_SELU) v[j] *= pg_dselu_from_out(hv[j]);
+                    else if (p.act == PGMVAE_ACT_SIGMOID) v[j] *= hv[j] * (1.0f - hv[j]);
+                }
+            }
+            store_row(p.C + off, v, nv, p.vecC);
+        } else {  // EPI_WGRAD: rows are weight rows (input features), reduced over the batch splits
+            if (p.zero_row_base >= 0 && row == p.zero_row_base + g) continue;
+            float* dst = p.C + off;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+                if (j < nv) atomicAdd(dst + j, v[j]);
+        }
+    }
+    if (EPI == EPI_SIGMOID_MSE) {
+        const double dsq = pg_warp_sum_d((double)sq), dab = pg_warp_sum_d((double)ab);
+        if (lane == 0) { red[0][warp] = dsq; red[1][warp] = dab; }
+    }
+    tc::fence_before_thread_sync();
+    __syncthreads();
+    if (EPI == EPI_SIGMOID_MSE && threadIdx.x == 0) {
+        atomicAdd(p.acc, red[0][0] + red[0][1] + red[0][2] + red[0][3]);
+        atomicAdd(p.acc + 1, red[1][0] + red[1][1] + red[1][2] + red[1][3]);
+    }
+    if (warp == 2) {
+        tc::fence_after_thread_sync();
+        tc::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+    }
+}
+
+// column sums of dy: db[g][n] += sum_b dy[g][b][n]   (bias gradient)
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ dy, long long dy_gs, int lddy,
+                                                     float* __restrict__ db, long long db_gs, int B, int N,
+                                                     int rows_per_cta) {
+    __shared__ float part[8][33];
+    const int g = blockIdx.z;
+    const int n = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int r0 = blockIdx.y * rows_per_cta, r1 = min(B, r0 + rows_per_cta);
+    float s = 0.f;
+    if (n < N)
+        for (int b = r0 + (threadIdx.x >> 5); b < r1; b += 8) s += dy[(long long)g * dy_gs + (long long)b * lddy + n];
+    part[threadIdx.x >> 5][threadIdx.x & 31] = s;
+    __syncthreads();
+    if (threadIdx.x < 32 && n < N) {
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += part[w][threadIdx.x];
+        atomicAdd(db + (long long)g * db_gs + n, t);
+    }
+}
+
+inline bool tma_ok(const float* p, int64_t gs, int ld) { return !((uintptr_t)p & 15) && ld % 4 == 0 && gs % 4 == 0; }
+
+int pick_bn(int N) {
+    int bn = pg_round_up(N, 32);
+    return bn > 128 ? 128 : bn;
+}
+
+template <int EPI>
+int launch_tc(pgmvae_ctx* ctx, cudaStream_t st, DenseTcP& p, const CUtensorMap& mapA, const CUtensorMap& mapB, int G,
+              const char* name, double bytes) {
+    p.tmem_cols = 32;
+    while (p.tmem_cols < p.BN) p.tmem_cols <<= 1;
+    const size_t stage = (size_t)A_STAGE_BYTES + (size_t)p.BN * 128;
+    int kb_cta = p.kb_per_split < p.kblocks ? p.kb_per_split : p.kblocks;
+    p.stages = kb_cta < 3 ? (kb_cta < 1 ? 1 : kb_cta) : 3;
+    const size_t smem = 1024 + p.stages * stage + 128;
+    static size_t configured = 0;
+    if (smem > configured) {
+        PG_CUDA(cudaFuncSetAttribute(dense_tc_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    dim3 grid((unsigned)pg_cdiv(p.N, p.BN), (unsigned)pg_cdiv(p.M, TM), (unsigned)(G * p.S));
+    if (grid.y > 65535u || grid.z > 65535u) {
+        pgmvae_set_error("dense (tensor core): grid too large (%u,%u,%u)", grid.x, grid.y, grid.z);
+        return PGMVAE_EINVAL;
+    }
+    PG_KERNEL(ctx, st, name, bytes, 2.0 * G * (double)p.M * p.N * p.K);
+    dense_tc_kernel<EPI><<<grid, 128, smem, st>>>(mapA, mapB, p);
+    PG_LAUNCHED(ctx);
+    return PGMVAE_OK;
+}
+
+}  // namespace
+
+bool pg_dense_tc_supported(const float* a, int64_t a_gs, int lda, const float* b, int64_t b_gs, int ldb) {
+    return tma_ok(a, a_gs, lda) && tma_ok(b, b_gs, ldb);
+}
+
+int pg_dense_fwd_tc(pgmvae_ctx* ctx, cudaStream_t st, const float* x, int64_t x_gs, int ldx, const float* w,
+                    int64_t w_gs, int ldw, const float* bias, int64_t bias_gs, float* out, int64_t out_gs, int ldo, int G,
+                    int B, int in, int out_dim, int act) {
+    if (G <= 0 || B <= 0) return PGMVAE_OK;
+    DenseTcP p{};
+    p.M = B; p.N = out_dim; p.K = in; p.BN = pick_bn(out_dim);
+    p.kblocks = (int)pg_cdiv(in, KBLK); p.S = 1; p.kb_per_split = p.kblocks;
+    p.a_mn = 0; p.b_mn = 1;
+    p.C = out; p.c_gs = out_gs; p.ldc = ldo; p.bias = bias; p.bias_gs = bias_gs; p.act = act;
+    p.a_shared = x_gs == 0; p.vecC = tma_ok(out, out_gs, ldo);
+    CUtensorMap mA, mB;
+    PG_TRY(tc::make_map(&mA, x, 4, (uint64_t)in, (uint64_t)B, (uint64_t)G, (uint64_t)ldx, (uint64_t)x_gs, 32, TM));
+    PG_TRY(tc::make_map(&mB, w, 4, (uint64_t)out_dim, (uint64_t)in, (uint64_t)G, (uint64_t)ldw, (uint64_t)w_gs, 32, 32));
+    const double xg = x_gs == 0 ? 1.0 : (double)G;
+    return launch_tc<EPI_BIAS_ACT>(ctx, st, p, mA, mB, G, "dense_fwd_tc",
+                                   4.0 * (xg * B * in + (double)G * in * out_dim + (double)G * out_dim +
+                                          (double)G * B * out_dim));
+}
+
+int pg_dense_fwd_sigmoid_mse_tc(pgmvae_ctx* ctx, cudaStream_t st, const float* x, int64_t x_gs, int ldx, const float* w,
+                                int64_t w_gs, int ldw, const float* bias, int64_t bias_gs, const float* y, int ldy,
+                                float* dpre, int64_t dpre_gs, int ldd, float* out_opt, double* acc2, int G, int g0, int B,
+                                int in, int V, float grad_scale) {
+    if (G <= 0 || B <= 0) return PGMVAE_OK;
+    DenseTcP p{};
+    p.M = B; p.N = V; p.K = in; p.BN = pick_bn(V);
+    p.kblocks = (int)pg_cdiv(in, KBLK); p.S = 1; p.kb_per_split = p.kblocks;
+    p.a_mn = 0; p.b_mn = 1;
+    p.C = dpre; p.c_gs = dpre_gs; p.ldc = ldd; p.C2 = out_opt; p.bias = bias; p.bias_gs = bias_gs;
+    p.aux = y; p.ldaux = ldy; p.acc = acc2; p.gscale = grad_scale; p.g0 = g0;
+    p.a_shared = x_gs == 0;
+    p.vecC = tma_ok(dpre, dpre_gs, ldd) && tma_ok(y, 0, ldy) && (!out_opt || tma_ok(out_opt, dpre_gs, ldd));
+    CUtensorMap mA, mB;
+    PG_TRY(tc::make_map(&mA, x, 4, (uint64_t)in, (uint64_t)B, (uint64_t)G, (uint64_t)ldx, (uint64_t)x_gs, 32, TM));
+    PG_TRY(tc::make_map(&mB, w, 4, (uint64_t)V, (uint64_t)in, (uint64_t)G, (uint64_t)ldw, (uint64_t)w_gs, 32, 32));
+    return launch_tc<EPI_SIGMOID_MSE>(ctx, st, p, mA, mB, G, "dense_fwd_sigmoid_mse_tc",
+                                      4.0 * ((double)G * B * in + (double)G * in * V + (double)G * V + (double)B * V +
+                                             (double)G * B * V * (out_opt ? 2 : 1)));
+}
+
+int pg_dense_dgrad_tc(pgmvae_ctx* ctx, cudaStream_t st, const float* dy, int64_t dy_gs, int lddy, const float* w,
+                      int64_t w_gs, int ldw, const float* h_in, int64_t h_gs, int ldh, const float* z, const float* q,
+                      int64_t zq_gs, int ldzq, float cscale, float* dx, int64_t dx_gs, int lddx, int G, int B, int in,
+                      int out_dim, int act_below) {
+    if (G <= 0 || B <= 0) return PGMVAE_OK;
+    DenseTcP p{};
+    p.M = B; p.N = in; p.K = out_dim; p.BN = pick_bn(in);
+    p.kblocks = (int)pg_cdiv(out_dim, KBLK); p.S = 1; p.kb_per_split = p.kblocks;
+    p.a_mn = 0; p.b_mn = 0;
+    p.C = dx; p.c_gs = dx_gs; p.ldc = lddx; p.aux = h_in; p.aux_gs = h_gs; p.ldaux = ldh; p.act = act_below;
+    p.z = z; p.q = q; p.zq_gs = zq_gs; p.ldzq = ldzq; p.cscale = cscale;
+    p.a_shared = dy_gs == 0;
+    p.vecC = tma_ok(dx, dx_gs, lddx) && (!h_in || tma_ok(h_in, h_gs, ldh)) && (!z || (tma_ok(z, zq_gs, ldzq) && tma_ok(q, zq_gs, ldzq)));
+    CUtensorMap mA, mB;
+    PG_TRY(tc::make_map(&mA, dy, 4, (uint64_t)out_dim, (uint64_t)B, (uint64_t)G, (uint64_t)lddy, (uint64_t)dy_gs, 32, TM));
+    // W[in][out] read as rows n = in, contiguous k = out
+    PG_TRY(tc::make_map(&mB, w, 4, (uint64_t)out_dim, (uint64_t)in, (uint64_t)G, (uint64_t)ldw, (uint64_t)w_gs, 32,
+                        (uint32_t)p.BN));
+    return launch_tc<EPI_DGRAD>(ctx, st, p, mA, mB, G, "dense_dgrad_tc",
+                                4.0 * ((double)G * B * out_dim + (double)G * in * out_dim +
+                                       (double)G * B * in * (h_in ? 2 : 1) + (z ? 2.0 * G * B * in : 0.0)));
+}
+
+int pg_dense_wgrad_tc(pgmvae_ctx* ctx, cudaStream_t st, const float* x, int64_t x_gs, int ldx, const float* dy,
+                      int64_t dy_gs, int lddy, float* dw, int64_t dw_gs, int lddw, float* db, int64_t db_gs, int G, int B,
+                      int in, int out_dim, int zero_row_base) {
+    if (G <= 0 || B <= 0) return PGMVAE_OK;
+    DenseTcP p{};
+    p.M = in; p.N = out_dim; p.K = B; p.BN = pick_bn(out_dim);
+    p.kblocks = (int)pg_cdiv(B, KBLK);
+    p.a_mn = 1; p.b_mn = 1;
+    p.C = dw; p.c_gs = dw_gs; p.ldc = lddw; p.zero_row_base = zero_row_base;
+    p.a_shared = x_gs == 0;
+    // split the batch so that ~3 CTAs per SM are in flight, at least 8 k-blocks (256 samples) per CTA
+    const int64_t tiles = pg_cdiv(out_dim, p.BN) * pg_cdiv(in, TM) * (int64_t)G;
+    int S = (int)pg_cdiv((int64_t)ctx->sm_count * 3, tiles > 0 ? tiles : 1);
+    const int maxS = (int)pg_cdiv(p.kblocks, 8);
+    if (S > maxS) S = maxS;
+    if (S < 1) S = 1;
+    while ((int64_t)G * S > 65535 && S > 1) --S;
+    p.kb_per_split = (int)pg_cdiv(p.kblocks, S);
+    p.S = (int)pg_cdiv(p.kblocks, p.kb_per_split);
+    CUtensorMap mA, mB;
+    // x[B][in] read as rows k = b, contiguous m = in; boxes of [32 b][32 m]
+    PG_TRY(tc::make_map(&mA, x, 4, (uint64_t)in, (uint64_t)B, (uint64_t)G, (uint64_t)ldx, (uint64_t)x_gs, 32, 32));
+    PG_TRY(tc::make_map(&mB, dy, 4, (uint64_t)out_dim, (uint64_t)B, (uint64_t)G, (uint64_t)lddy, (uint64_t)dy_gs, 32, 32));
+    const double xg = x_gs == 0 ? 1.0 : (double)G;
+    PG_TRY(launch_tc<EPI_WGRAD>(ctx, st, p, mA, mB, G, "dense_wgrad_tc",
+                                4.0 * (xg * B * in + (double)G * B * out_dim + (double)G * in * out_dim)));
+    if (db) {
+        int rows = 1024;
+        dim3 grid((unsigned)pg_cdiv(out_dim, 32), (unsigned)pg_cdiv(B, rows), (unsigned)G);
+        PG_KERNEL(ctx, st, "dense_bias_grad", 4.0 * ((double)G * B * out_dim + (double)G * out_dim), (double)G * B * out_dim);
+        colsum_kernel<<<grid, 256, 0, st>>>(dy, dy_gs, lddy, db, db_gs, B, out_dim, rows);
+        PG_LAUNCHED(ctx);
+    }
+    return PGMVAE_OK;
+}

@@ -1,0 +1,123 @@
+"""GPU parity tests of the tcgen05 tensor-core path (ctx precision TF32): the grouped dense
+GEMMs (forward / dgrad / wgrad with their fused epilogues) and the VQ assignment run on the
+tensor cores; results are compared with the oracle and with the exact-fp32 CUDA-core path.
+tf32 keeps 10 explicit mantissa bits (operands are truncated by the MMA), so the floating
+point tolerances here are 10x looser than in test_gpu_model.py; codes stay exact because the
+VQ kernel re-scores its candidates in fp32."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+import pgmvae_oracle as O
+from test_oracle import load_case, make_oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def rel_err(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-12)
+
+
+@pytest.fixture
+def tf32(ctx):
+    from pgmvae import _ffi
+    ctx.set_precision(_ffi.PREC_TF32)
+    yield ctx
+    ctx.set_precision(_ffi.PREC_FP32)
+
+
+@pytest.mark.parametrize("V,B,fin,fout,act", [
+    (16, 256, 16, 12, "selu"), (3, 1, 4, 12, "selu"), (5, 200, 68, 52, "selu"), (2, 129, 132, 68, "sigmoid"),
+    (4, 64, 16, 24, None), (69, 300, 20, 16, "selu"), (2, 1000, 400, 200, "selu"), (1, 333, 1556, 400, "selu"),
+])
+def test_fatdense_forward_tensor_core(tf32, V, B, fin, fout, act):
+    from core.dense import FatDense
+    rng = np.random.default_rng(V * 1000 + B)
+    x = rng.standard_normal((V, B, fin)).astype(np.float32)
+    layer = FatDense(fout, activation=act, kernel_initializer="he_uniform")
+    layer.build(x.shape)
+    layer.bias = rng.standard_normal((V, 1, fout)).astype(np.float32) * 0.1
+    l0 = tf32.launches
+    got = layer(x).numpy()
+    exp = O.fatdense_call(torch.from_numpy(x), torch.from_numpy(layer.kernel), torch.from_numpy(layer.bias), act).numpy()
+    err = np.abs(got - exp).max()
+    scale = np.abs(x).max() * np.abs(layer.kernel).max() * np.sqrt(fin)
+    print(f"dense tc fwd V={V} B={B} {fin}->{fout}: max abs err {err:.2e} (scale {scale:.2e})")
+    assert err <= 4e-3 * scale
+
+
+def _grads_case(name, prec_ctx):
+    from core.model import VqVAE, Adam
+    from pgmvae import _ffi
+    z, cfg, params = load_case(name)
+    m = VqVAE(cfg["units"], cfg["V"], cfg["D"], cfg["K"], cost=cfg["cost"], decay=cfg["decay"], ema=cfg["ema"],
+              max_batch=max(cfg["B"], 256))
+    m.set_weights_from(params)
+    y = np.ascontiguousarray(z["y_train"][0])
+    met = (C.c_double * 4)()
+    _ffi.check(_ffi.lib().pgmvae_model_train_step(m._h, y.ctypes.data, 0, y.shape[0], y.shape[0], cfg["lr"], None, 1, met))
+    return z, cfg, m, list(met)
+
+
+@pytest.mark.parametrize("name", ["v4_ema", "v9_grad", "v16_ema"])
+def test_gradients_tensor_core(tf32, name):
+    z, cfg, m, met = _grads_case(name, tf32)
+    np.testing.assert_allclose(met, z["metrics"][0], rtol=2e-3)
+    worst = 0.0
+    for k in z.files:
+        if k.startswith("grad1."):
+            e = rel_err(m._get_tensor("grad." + k[6:]), z[k])
+            worst = max(worst, e)
+            assert e < 2e-2, (k, e)
+    print(f"{name}: tf32 gradient max rel err {worst:.2e}")
+    if cfg["ema"]:
+        assert rel_err(m._get_tensor("vq.stat_w"), z["stat1.dw"]) < 5e-3
+
+
+@pytest.mark.parametrize("ema,B", [(True, 256), (False, 300)])
+def test_training_tensor_core_vs_oracle_plants_scale(tf32, ema, B):
+    from core.model import VqVAE, Adam
+    units, V, D, K = [50, 40, 30, 20], 69, 16, 128
+    params = O.init_params(units, V, D, K, seed=9)
+    cfg = dict(units=units, V=V, D=D, K=K, cost=0.25, decay=0.99, ema=ema, B=B, lr=1e-3)
+    m = VqVAE(units, V, D, K, cost=0.25, decay=0.99, ema=ema, max_batch=512)
+    m.set_weights_from({k: v.numpy() for k, v in params.items()})
+    m.compile(optimizer=Adam(lr=1e-3))
+    om = make_oracle(cfg, {k: v.numpy() for k, v in params.items()})
+    ys = O.synthetic_binary(3 * B, V, seed=2).reshape(3, B, V)
+    for s in range(3):
+        met = m.train_on_batch(np.ascontiguousarray(ys[s]))
+        exp = om.train_step(O.make_xs(ys[s]), lr=1e-3)
+        for k in ("loss", "mse", "mae"):
+            assert abs(met[k] - exp[k]) <= 1e-3 * abs(exp[k]), (s, k, met[k], exp[k])
+        assert abs(met["vq_loss"] - exp["vq_loss"]) <= 2e-2 * abs(exp["vq_loss"]) + 1e-9, (s, met, exp)
+    n1, n0 = m.count(ys.reshape(-1, V))
+    assert (n1 + n0).sum() == 3 * B * V
+
+
+def test_tensor_core_matches_fp32_path_cfg2_full_batch(ctx):
+    """Same weights, same batch (B=4096): tf32 tensor-core step vs exact-fp32 CUDA-core step."""
+    from core.model import VqVAE, Adam
+    from pgmvae import _ffi, data
+    V, D, K, B = 69, 16, 128, 4096
+    y = data.synthetic_binary(B, V, seed=3)
+    res = {}
+    for prec in (_ffi.PREC_FP32, _ffi.PREC_TF32):
+        ctx.set_precision(prec)
+        try:
+            m = VqVAE([50, 40, 30, 20], V, D, K, cost=0.25, decay=0.99, ema=True, seed=1, max_batch=B)
+            met = (C.c_double * 4)()
+            _ffi.check(_ffi.lib().pgmvae_model_train_step(m._h, y.ctypes.data, 0, B, B, 1e-3, None, 1, met))
+            res[prec] = (list(met), {n: m._get_tensor("grad." + n) for n in ("fd0.kernel", "fd4.kernel", "fd9.kernel", "fd9.bias")},
+                         m._get_tensor("vq.stat_c"))
+        finally:
+            ctx.set_precision(_ffi.PREC_FP32)
+    a, b = res[_ffi.PREC_FP32], res[_ffi.PREC_TF32]
+    np.testing.assert_allclose(b[0][:3], a[0][:3], rtol=1e-3)
+    for n in a[1]:
+        assert rel_err(b[1][n], a[1][n]) < 2e-2, n
+    # a handful of samples may flip codes because z itself differs by tf32 rounding
+    assert np.abs(a[2] - b[2]).sum() <= 0.01 * B * V
