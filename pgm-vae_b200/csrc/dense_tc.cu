@@ -138,10 +138,12 @@ __global__ void __launch_bounds__(128) dense_tc_kernel(const __grid_constant__ C
             // ===================== MMA issuer =====================
             const uint32_t idesc = tc::make_idesc(2, TM, p.BN, p.a_mn, p.b_mn);
             // K-major: rows of 128 B along k, 8-row atoms 1024 B apart; one MMA (k = 8) advances 32 B.
-            // MN-major: panels of [32 k][128 B along m/n], 4096 B apart (LBO), 8-k atoms 1024 B apart
-            //           (SBO); one MMA (k = 8) advances one atom = 1024 B.
-            const uint64_t dA0 = tc::make_smem_desc(tc::smem_u32(sA), p.a_mn ? 4096 : 16, 1024);
-            const uint64_t dB0 = tc::make_smem_desc(tc::smem_u32(sB), p.b_mn ? 4096 : 16, 1024);
+            // MN-major (32-byte-atom swizzle): panels of [32 k][128 B along m/n], 4096 B apart (LBO),
+            //           4-k atoms 512 B apart (SBO); one MMA (k = 8) advances two atoms = 1024 B.
+            const uint64_t dA0 = p.a_mn ? tc::make_smem_desc(tc::smem_u32(sA), 4096, 512, 1)
+                                        : tc::make_smem_desc(tc::smem_u32(sA), 16, 1024, 2);
+            const uint64_t dB0 = p.b_mn ? tc::make_smem_desc(tc::smem_u32(sB), 4096, 512, 1)
+                                        : tc::make_smem_desc(tc::smem_u32(sB), 16, 1024, 2);
             const uint32_t a_step = (p.a_mn ? 1024u : 32u) >> 4, b_step = (p.b_mn ? 1024u : 32u) >> 4;
             const uint32_t a_stage = (uint32_t)A_STAGE_BYTES >> 4, b_stage = (uint32_t)b_stage_bytes >> 4;
             uint32_t s = 0, ph = 0;
@@ -252,7 +254,8 @@ __global__ void __launch_bounds__(128) dense_tc_kernel(const __grid_constant__ C
     }
 }
 
-// column sums of dy: db[g][n] += sum_b dy[g][b][n]   (bias gradient)
+// column sums of dy: db[g][n] += sum_b dy[g][b][n]   (bias gradient).  One warp reads whole 128-byte row
+// segments; four rows in flight per warp hide the load latency.
 __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ dy, long long dy_gs, int lddy,
                                                      float* __restrict__ db, long long db_gs, int B, int N,
                                                      int rows_per_cta) {
@@ -260,10 +263,19 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ d
     const int g = blockIdx.z;
     const int n = blockIdx.x * 32 + (threadIdx.x & 31);
     const int r0 = blockIdx.y * rows_per_cta, r1 = min(B, r0 + rows_per_cta);
-    float s = 0.f;
-    if (n < N)
-        for (int b = r0 + (threadIdx.x >> 5); b < r1; b += 8) s += dy[(long long)g * dy_gs + (long long)b * lddy + n];
-    part[threadIdx.x >> 5][threadIdx.x & 31] = s;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    if (n < N) {
+        const float* base = dy + (long long)g * dy_gs + n;
+        int b = r0 + (threadIdx.x >> 5);
+        for (; b + 24 < r1; b += 32) {
+            s0 += base[(long long)b * lddy];
+            s1 += base[(long long)(b + 8) * lddy];
+            s2 += base[(long long)(b + 16) * lddy];
+            s3 += base[(long long)(b + 24) * lddy];
+        }
+        for (; b < r1; b += 8) s0 += base[(long long)b * lddy];
+    }
+    part[threadIdx.x >> 5][threadIdx.x & 31] = (s0 + s1) + (s2 + s3);
     __syncthreads();
     if (threadIdx.x < 32 && n < N) {
         float t = 0.f;
@@ -323,7 +335,7 @@ int pg_dense_fwd_tc(pgmvae_ctx* ctx, cudaStream_t st, const float* x, int64_t x_
     p.a_shared = x_gs == 0; p.vecC = tma_ok(out, out_gs, ldo);
     CUtensorMap mA, mB;
     PG_TRY(tc::make_map(&mA, x, 4, (uint64_t)in, (uint64_t)B, (uint64_t)G, (uint64_t)ldx, (uint64_t)x_gs, 32, TM));
-    PG_TRY(tc::make_map(&mB, w, 4, (uint64_t)out_dim, (uint64_t)in, (uint64_t)G, (uint64_t)ldw, (uint64_t)w_gs, 32, 32));
+    PG_TRY(tc::make_map(&mB, w, 4, (uint64_t)out_dim, (uint64_t)in, (uint64_t)G, (uint64_t)ldw, (uint64_t)w_gs, 32, 32, true));
     const double xg = x_gs == 0 ? 1.0 : (double)G;
     return launch_tc<EPI_BIAS_ACT>(ctx, st, p, mA, mB, G, "dense_fwd_tc",
                                    4.0 * (xg * B * in + (double)G * in * out_dim + (double)G * out_dim +
@@ -345,7 +357,7 @@ int pg_dense_fwd_sigmoid_mse_tc(pgmvae_ctx* ctx, cudaStream_t st, const float* x
     p.vecC = tma_ok(dpre, dpre_gs, ldd) && tma_ok(y, 0, ldy) && (!out_opt || tma_ok(out_opt, dpre_gs, ldd));
     CUtensorMap mA, mB;
     PG_TRY(tc::make_map(&mA, x, 4, (uint64_t)in, (uint64_t)B, (uint64_t)G, (uint64_t)ldx, (uint64_t)x_gs, 32, TM));
-    PG_TRY(tc::make_map(&mB, w, 4, (uint64_t)V, (uint64_t)in, (uint64_t)G, (uint64_t)ldw, (uint64_t)w_gs, 32, 32));
+    PG_TRY(tc::make_map(&mB, w, 4, (uint64_t)V, (uint64_t)in, (uint64_t)G, (uint64_t)ldw, (uint64_t)w_gs, 32, 32, true));
     return launch_tc<EPI_SIGMOID_MSE>(ctx, st, p, mA, mB, G, "dense_fwd_sigmoid_mse_tc",
                                       4.0 * ((double)G * B * in + (double)G * in * V + (double)G * V + (double)B * V +
                                              (double)G * B * V * (out_opt ? 2 : 1)));
@@ -395,13 +407,13 @@ int pg_dense_wgrad_tc(pgmvae_ctx* ctx, cudaStream_t st, const float* x, int64_t 
     p.S = (int)pg_cdiv(p.kblocks, p.kb_per_split);
     CUtensorMap mA, mB;
     // x[B][in] read as rows k = b, contiguous m = in; boxes of [32 b][32 m]
-    PG_TRY(tc::make_map(&mA, x, 4, (uint64_t)in, (uint64_t)B, (uint64_t)G, (uint64_t)ldx, (uint64_t)x_gs, 32, 32));
-    PG_TRY(tc::make_map(&mB, dy, 4, (uint64_t)out_dim, (uint64_t)B, (uint64_t)G, (uint64_t)lddy, (uint64_t)dy_gs, 32, 32));
+    PG_TRY(tc::make_map(&mA, x, 4, (uint64_t)in, (uint64_t)B, (uint64_t)G, (uint64_t)ldx, (uint64_t)x_gs, 32, 32, true));
+    PG_TRY(tc::make_map(&mB, dy, 4, (uint64_t)out_dim, (uint64_t)B, (uint64_t)G, (uint64_t)lddy, (uint64_t)dy_gs, 32, 32, true));
     const double xg = x_gs == 0 ? 1.0 : (double)G;
     PG_TRY(launch_tc<EPI_WGRAD>(ctx, st, p, mA, mB, G, "dense_wgrad_tc",
                                 4.0 * (xg * B * in + (double)G * B * out_dim + (double)G * in * out_dim)));
     if (db) {
-        int rows = 1024;
+        int rows = 512;
         dim3 grid((unsigned)pg_cdiv(out_dim, 32), (unsigned)pg_cdiv(B, rows), (unsigned)G);
         PG_KERNEL(ctx, st, "dense_bias_grad", 4.0 * ((double)G * B * out_dim + (double)G * out_dim), (double)G * B * out_dim);
         colsum_kernel<<<grid, 256, 0, st>>>(dy, dy_gs, lddy, db, db_gs, B, out_dim, rows);

@@ -28,9 +28,10 @@ inline EncodeTiledFn encode_fn() {
 
 // tensor [groups][rows][cols] of fp32 (esize 4) or fp16 (esize 2): cols contiguous, row stride ld
 // and group stride gs in ELEMENTS (gs == 0 = one shared matrix); box = [1][box_rows][box_cols]
-// with box_cols * esize = 128 bytes, 128-byte swizzle, out-of-bounds elements read as zero.
+// with box_cols * esize = 128 bytes, 128-byte swizzle (16-byte atoms; atom32 = 32-byte atoms, the
+// only layout tcgen05 accepts for MN-major 32-bit operands), out-of-bounds elements read as zero.
 inline int make_map(CUtensorMap* map, const void* base, int esize, uint64_t cols, uint64_t rows, uint64_t groups,
-                    uint64_t ld, uint64_t gs, uint32_t box_cols, uint32_t box_rows) {
+                    uint64_t ld, uint64_t gs, uint32_t box_cols, uint32_t box_rows, bool atom32 = false) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) {
         pgmvae_set_error("cuTensorMapEncodeTiled unavailable");
@@ -47,7 +48,8 @@ inline int make_map(CUtensorMap* map, const void* base, int esize, uint64_t cols
     cuuint32_t box[3] = {box_cols, box_rows, 1};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = fn(map, esize == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, (void*)base,
-                    dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                    dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         pgmvae_set_error("cuTensorMapEncodeTiled failed (%d): cols %llu rows %llu groups %llu ld %llu gs %llu", (int)r,
@@ -194,14 +196,17 @@ __device__ __forceinline__ void tmem_ld_wait(float (&r)[32]) {
 // swizzle atom, consecutive atoms 1024 bytes apart (SBO).
 //   K-major operand : a row is one M/N index, the 128 bytes run along K  -> LBO unused
 //   MN-major operand: a row is one K index, the 128 bytes run along M/N  -> LBO = byte
-//                     distance between consecutive 128-byte panels along M/N
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+//                     distance between consecutive 128-byte panels along M/N.  32-bit (tf32)
+//                     MN-major operands must use the 32-byte-atom swizzle (layout type 1,
+//                     TMA SWIZZLE_128B_ATOM_32B): 4 rows per 512-byte atom (SBO = 512)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                                   uint32_t layout_type = 2) {
     uint64_t d = 0;
     d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);          // start address   bits [0,14)
     d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;     // leading offset  bits [16,30)
     d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;     // stride offset   bits [32,46)
     d |= (uint64_t)1 << 46;                               // descriptor version (Blackwell)
-    d |= (uint64_t)2 << 61;                               // layout type: SWIZZLE_128B
+    d |= (uint64_t)layout_type << 61;                     // 2 = SWIZZLE_128B, 1 = SWIZZLE_128B_BASE32B
     return d;
 }
 // Instruction descriptor: fp32 accumulate, dense.  fmt: 0 = f16, 1 = bf16, 2 = tf32.
