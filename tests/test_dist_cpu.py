@@ -1,0 +1,80 @@
+"""world_size-2 gloo tests (CPU) of the data-parallel host logic: batch sharding, global
+normalisation of the sharded gradients, EMA-statistic and PLL-count reductions.  Compute is
+the oracle (this file is test code); the reductions go through pgmvae.dist.GlooComm, which
+has the interface of the NCCL communicator the product path uses."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, out):
+    for p in (os.path.join(ROOT, "pgm-vae_b200"), os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
+        sys.path.insert(0, p)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(1)
+    import pgmvae_oracle as O
+    import np_expanded as NE
+    from pgmvae.dist import GlooComm, shard_bounds
+    comm = GlooComm()
+    units, V, D, K, B = [6, 5, 4, 3], 5, 2, 4, 22
+    params = {k: v.numpy() for k, v in O.init_params(units, V, D, K, seed=3).items()}
+    y = O.synthetic_binary(B, V, seed=1)
+    lo, hi = shard_bounds(B, rank, world)
+    # each rank: gradients of its share with GLOBAL normalisation, then sum over ranks
+    met, g_local, aux = NE.step_grads(params, y[lo:hi], D, K, 0.25, True, global_B=B)
+    g_sum = {n: comm.allreduce_f64(g) for n, g in g_local.items()}
+    m_sum = comm.allreduce_f64(np.array([met["mse"], met["mae"], met["vq_loss"]]))
+    # EMA statistics of the shard, reduced before the update
+    c, dw = O.ema_stats(aux["z"].astype(np.float32), aux["idx"], K)
+    c_sum, dw_sum = comm.allreduce_f32(c.numpy()), comm.allreduce_f32(dw.numpy())
+    # PLL counts of the shard
+    n1 = np.zeros((V, K), np.uint64)
+    for v in range(V):
+        np.add.at(n1[v], aux["idx"][v][y[lo:hi, v] != 0], 1)
+    n1_sum = comm.allreduce_u64(n1)
+    if rank == 0:
+        met_f, g_full, aux_f = NE.step_grads(params, y, D, K, 0.25, True)
+        for n in g_full:
+            np.testing.assert_allclose(g_sum[n], g_full[n], rtol=1e-9, atol=1e-12)
+        np.testing.assert_allclose(m_sum, [met_f["mse"], met_f["mae"], met_f["vq_loss"]], rtol=1e-9)
+        cf, dwf = O.ema_stats(aux_f["z"].astype(np.float32), aux_f["idx"], K)
+        np.testing.assert_array_equal(c_sum, cf.numpy())
+        np.testing.assert_allclose(dw_sum, dwf.numpy(), rtol=1e-5, atol=1e-6)
+        n1f = np.zeros((V, K), np.uint64)
+        for v in range(V):
+            np.add.at(n1f[v], aux_f["idx"][v][y[:, v] != 0], 1)
+        np.testing.assert_array_equal(n1_sum, n1f)
+        out.put("ok")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_data_parallel_reductions_gloo_world2():
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert out.get(timeout=5) == "ok"
+
+
+def test_shard_bounds_partition():
+    from pgmvae.dist import shard_bounds
+    for n in (0, 1, 7, 4096, 16181):
+        for w in (1, 2, 3, 8):
+            b = [shard_bounds(n, r, w) for r in range(w)]
+            assert b[0][0] == 0 and b[-1][1] == n
+            assert all(b[i][1] == b[i + 1][0] for i in range(w - 1))
+            assert max(h - l for l, h in b) - min(h - l for l, h in b) <= 1
