@@ -189,6 +189,18 @@ int pgmvae_ema_stats(pgmvae_ctx* ctx, void* stream,
                      float* dw, int64_t dw_gs, int lddw,
                      int G, int B, int D, int K);
 
+/* Kernels (b)+(c) fused (BASELINE.json configs[3]: "fused distance-GEMM + argmin + EMA scatter"):
+ * assignment as pgmvae_vq_assign, and in the same kernel counts[g,k] += 1 ; dw[g,k,:] += z[g,b,:]
+ * for the chosen k, while the row is still hot (core/quantizer.py:135-138 + :144-146).
+ * Tensor-core fp16 path only (needs D <= 126); ACCUMULATES into counts/dw.              */
+int pgmvae_vq_assign_ema(pgmvae_ctx* ctx, void* stream,
+                         const float* z, int64_t z_gs, int ldz,
+                         const float* e, int64_t e_gs, int lde,
+                         int32_t* idx, int64_t idx_gs,
+                         float* counts, int64_t c_gs,
+                         float* dw, int64_t dw_gs, int lddw,
+                         int G, int B, int D, int K);
+
 /* TF assign_moving_average(zero_debias=True) x2 + Laplace smoothing + normalise + write-back
  * (core/quantizer.py:144-152).  step = value of the hidden local_step AFTER this update.  */
 int pgmvae_ema_apply(pgmvae_ctx* ctx, void* stream,

@@ -67,12 +67,29 @@ int pgmvae_vq_assign(pgmvae_ctx* ctx, void* stream, const float* z, int64_t z_gs
                      int B, int D, int K) {
     PG_CHECK_ARG(ctx && z && e && idx);
     PG_CHECK_ARG(G >= 0 && B >= 0 && D > 0 && K > 0 && ldz >= D && lde >= D);
-    if (ctx->precision != PGMVAE_PREC_FP32 &&
+    if (ctx->precision == PGMVAE_PREC_BF16 && pg_vq_assign_f16_supported(D, K))
+        return pg_vq_assign_f16(ctx, pg_stream(ctx, stream), z, z_gs, ldz, e, e_gs, lde, idx, idx_gs, best_opt, gap_opt,
+                                nullptr, 0, nullptr, 0, 0, G, B, D, K);
+    if (ctx->precision == PGMVAE_PREC_TF32 &&
         pg_vq_assign_tc_supported(ctx->precision, D, K, ldz, lde, z, e, z_gs, e_gs))
         return pg_vq_assign_tc(ctx, pg_stream(ctx, stream), ctx->precision, z, z_gs, ldz, e, e_gs, lde, idx, idx_gs,
                                best_opt, gap_opt, G, B, D, K);
     return pg_vq_assign_fp32(ctx, pg_stream(ctx, stream), z, z_gs, ldz, e, e_gs, lde, idx, idx_gs, best_opt, gap_opt,
                              G, B, D, K);
+}
+
+int pgmvae_vq_assign_ema(pgmvae_ctx* ctx, void* stream, const float* z, int64_t z_gs, int ldz, const float* e,
+                         int64_t e_gs, int lde, int32_t* idx, int64_t idx_gs, float* counts, int64_t c_gs, float* dw,
+                         int64_t dw_gs, int lddw, int G, int B, int D, int K) {
+    PG_CHECK_ARG(ctx && z && e && idx && counts && dw);
+    PG_CHECK_ARG(G >= 0 && B >= 0 && D > 0 && K > 0 && ldz >= D && lde >= D && lddw >= D);
+    if (!pg_vq_assign_f16_supported(D, K)) {
+        pgmvae_set_error("pgmvae_vq_assign_ema: D = %d exceeds the fused tensor-core kernel (D <= 126); "
+                         "call pgmvae_vq_assign + pgmvae_ema_stats", D);
+        return PGMVAE_EINVAL;
+    }
+    return pg_vq_assign_f16(ctx, pg_stream(ctx, stream), z, z_gs, ldz, e, e_gs, lde, idx, idx_gs, nullptr, nullptr,
+                            counts, c_gs, dw, dw_gs, lddw, G, B, D, K);
 }
 
 /* rows of the last tensor-core vq_assign on this context that were re-scored in fp32 */

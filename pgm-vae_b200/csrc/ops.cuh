@@ -27,6 +27,10 @@ bool pg_vq_assign_tc_supported(int prec, int D, int K, int ldz, int lde, const f
 int pg_vq_assign_tc(pgmvae_ctx* ctx, cudaStream_t st, int prec, const float* z, int64_t z_gs, int ldz, const float* e,
                     int64_t e_gs, int lde, int32_t* idx, int64_t idx_gs, float* best_opt, float* gap_opt, int G, int B,
                     int D, int K);
+bool pg_vq_assign_f16_supported(int D, int K);
+int pg_vq_assign_f16(pgmvae_ctx* ctx, cudaStream_t st, const float* z, int64_t z_gs, int ldz, const float* e,
+                     int64_t e_gs, int lde, int32_t* idx, int64_t idx_gs, float* best_opt, float* gap_opt,
+                     float* cnt_opt, int64_t c_gs, float* dw_opt, int64_t dw_gs, int lddw, int G, int B, int D, int K);
 int pg_vq_assign_tc_last_flagged(pgmvae_ctx* ctx, int G, int K, int* out);
 bool pg_dense_tc_supported(const float* a, int64_t a_gs, int lda, const float* b, int64_t b_gs, int ldb);
 int pg_dense_fwd_tc(pgmvae_ctx* ctx, cudaStream_t st, const float* x, int64_t x_gs, int ldx, const float* w,

@@ -1,0 +1,539 @@
+// Kernel (b), fp16 tensor-core flavour (PGMVAE_PREC_BF16): single-pass VQ assignment with the
+// |e|^2 term folded into the contraction, the z operand resident in TENSOR MEMORY and an
+// (optional) fused EMA scatter.  Reference: core/quantizer.py:44-47 / :135-138 (distances +
+// argmin) and :144-146 (per-code counts and sums); the [V,B,K] distance tensor and the one-hot
+// matrix are never materialised.
+//
+// Score instead of distance:  s_k = z.e_k - |e_k|^2 / 2   (argmax s == argmin d, d = |z|^2 - 2 s).
+// The correction rides in the contraction: the codebook copy is [e_k (fp16), hi, lo, 0..] with
+// hi + lo = -|e_k|^2/2 split over two fp16 columns, and z is extended by two 1.0 columns, so the
+// epilogue is a bare maximum (FMNMX3: two scores per instruction).
+//
+// Per CTA (persistent over row tiles of SUB x 128 samples of one variable):
+//   z      each epilogue thread owns one row: reads it from HBM (fp32), rounds it to fp16 and
+//          writes it with tcgen05.st into TMEM, where it stays as the A operand of every MMA of
+//          the row tile (no fp16 copy of z in HBM, no shared-memory traffic for A)
+//   E      [BN codes, KD] fp16 tiles, TMA -> shared-memory ring (128-byte swizzle), B operand
+//   acc    SUB x [128, BN] fp32 in TMEM, double buffered (MMA of tile t+1 overlaps epilogue t)
+//   warp 0 TMA producer | warp 1 MMA issuer | warp 2 TMEM allocator | warps 4.. epilogue
+//
+// Exactness.  fp16 products only PROPOSE candidates; fp32 decides.  eps bounds the error of an
+// approximate score (2^-10 |z| max|e| for round-to-nearest fp16 operands).  In ONE pass each
+// row keeps a running maximum m and records every code whose score is >= m - 2 eps at the time
+// it is seen, together with the maximum of its 32-code chunk.  m only grows, so the final
+// candidate set {k : s~_k >= m_final - 2 eps} is a subset of the recorded codes, and the true
+// arg-min is in it (header of vq_tc.cu).  A row with a single candidate is decided; rows with
+// several are re-scored with exactly the fp32 arithmetic of the CUDA-core kernel (lowest index
+// on ties).  Rows whose record ring overflowed with still-relevant entries (many identical dead
+// codes) or whose fp16 image is not finite go to the exact full-scan kernel.
+#include <cuda_fp16.h>
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "ops.cuh"
+#include "tc_common.cuh"
+
+namespace {
+
+constexpr int TM = 128;                       // rows per MMA (TMEM lanes)
+constexpr int KB_BYTES = 128;                 // one k-block = one 128-byte swizzle row = 64 halves
+constexpr int RING = 16;                      // recorded (chunk max, code) pairs kept per row
+constexpr int MAX_STAGES = 6;
+constexpr int A_COLS = 128;                   // TMEM columns reserved for the z operand
+
+template <int SUB>
+struct Cfg {
+    static constexpr int BN = SUB == 2 ? 96 : 64;          // codes per tile: 128 + 2*SUB*BN == 512 columns
+    static constexpr int NCH = BN / 32;                    // 32-column chunks per tile
+    static constexpr int TMR = TM * SUB;                   // rows per CTA row tile
+    static constexpr int EPI_WARPS = 4 * SUB;
+    static constexpr int THREADS = 128 + 32 * EPI_WARPS;
+};
+
+struct Vq16P {
+    int G, B, D, K;
+    int KD, ksteps, kblocks, tiles_m, tiles_n, Kpad, stages, zvec;
+    const float* z; long long z_gs; int ldz;
+    const float* e; long long e_gs; int lde;
+    const float* ee;        // [G][Kpad] exact fp32 squared norms
+    const float* emax;      // [1] max_k |e_k| over all groups
+    int32_t* idx; long long idx_gs;
+    float* best; float* gap;
+    float* cnt; long long c_gs;             // fused EMA statistics (optional)
+    float* dw; long long dw_gs; int lddw;
+    int* flag_count; int2* flag_list;
+    float margin_scale, margin_abs;
+};
+
+// Per code: exact |e|^2 (sequential fmaf, the order every fp32 path uses), the fp16 row
+// [e, hi, lo, 0..] with hi + lo = -|e|^2/2, and max |e|.  Padding codes k >= K score -60000.
+__global__ void e_prep_kernel(const float* __restrict__ e, long long e_gs, int lde, float* __restrict__ ee,
+                              float* __restrict__ emax, __half* __restrict__ e16, int G, int K, int Kpad, int D, int KD) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    float s = 0.f;
+    if (i < (long long)G * Kpad) {
+        const int g = (int)(i / Kpad), k = (int)(i - (long long)g * Kpad);
+        __half* dst = e16 + i * KD;
+        if (k < K) {
+            const float* row = e + (long long)g * e_gs + (long long)k * lde;
+            for (int d = 0; d < D; ++d) {
+                const float v = row[d];
+                s = fmaf(v, v, s);
+                dst[d] = __float2half_rn(v);
+            }
+            ee[i] = s;
+            const float h = -0.5f * s;
+            const __half hi = __float2half_rn(h);
+            dst[D] = hi;
+            dst[D + 1] = __float2half_rn(h - __half2float(hi));
+            for (int d = D + 2; d < KD; ++d) dst[d] = __half(0.f);
+        } else {
+            ee[i] = INFINITY;
+            for (int d = 0; d < KD; ++d) dst[d] = __half(d == D ? -60000.f : 0.f);
+        }
+    }
+    float m = sqrtf(s);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<int*>(emax), __float_as_int(m));   // m >= 0
+}
+
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+// EMA statistics of one row: counts[k] += 1, dw[k,:] += z[row,:]   (core/quantizer.py:144-146)
+__device__ __forceinline__ void scatter_row(const Vq16P& p, int g, const float* zr, int k) {
+    float* dst = p.dw + (long long)g * p.dw_gs + (long long)k * p.lddw;
+    if (p.zvec && !(p.lddw & 3) && !(p.D & 3)) {
+        for (int d = 0; d < p.D; d += 4) {
+            const float4 v = *reinterpret_cast<const float4*>(zr + d);
+            red_add_v4(dst + d, v.x, v.y, v.z, v.w);
+        }
+    } else {
+        for (int d = 0; d < p.D; ++d) atomicAdd(dst + d, zr[d]);
+    }
+    atomicAdd(p.cnt + (long long)g * p.c_gs + k, 1.0f);
+}
+
+template <int SUB>
+__global__ void __launch_bounds__(Cfg<SUB>::THREADS, 1)
+vq_assign_f16_kernel(const __grid_constant__ CUtensorMap mapE, const Vq16P p) {
+    using C = Cfg<SUB>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    constexpr int B_KB_BYTES = C::BN * KB_BYTES;                       // one k-block of one code tile
+    const int stage_bytes = p.kblocks * B_KB_BYTES;
+    uint8_t* sB = smem;                                                // [stages][kblocks][BN * 128]
+    float2* ring = reinterpret_cast<float2*>(sB + (size_t)p.stages * stage_bytes);   // [RING][TMR]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(ring + RING * C::TMR);
+    uint64_t* a_full = bars + 0;
+    uint64_t* acc_full = bars + 1;                 // [2]
+    uint64_t* acc_empty = bars + 3;                // [2]
+    uint64_t* b_full = bars + 5;                   // [MAX_STAGES]
+    uint64_t* b_empty = bars + 5 + MAX_STAGES;     // [MAX_STAGES]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5 + 2 * MAX_STAGES);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int items = p.G * p.tiles_m;
+
+    if (warp == 0 && lane == 0) tc::tma_prefetch_desc(&mapE);
+    if (warp == 1 && lane == 0) {
+        tc::mbar_init(a_full, C::EPI_WARPS);
+        for (int s = 0; s < 2; ++s) {
+            tc::mbar_init(&acc_full[s], 1);
+            tc::mbar_init(&acc_empty[s], C::EPI_WARPS);      // one arrival per epilogue warp
+        }
+        for (int s = 0; s < MAX_STAGES; ++s) {
+            tc::mbar_init(&b_full[s], 1);
+            tc::mbar_init(&b_empty[s], 1);
+        }
+        tc::fence_barrier_init();
+    }
+    if (warp == 2) {
+        tc::tmem_alloc(tmem_slot, 512u);
+        tc::tmem_relinquish();
+    }
+    tc::fence_before_thread_sync();
+    __syncthreads();
+    tc::fence_after_thread_sync();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer: code tiles =====================
+        if (lane == 0) {
+            uint32_t s = 0, ph = 0;
+            for (int item = blockIdx.x; item < items; item += gridDim.x) {
+                const int g = item / p.tiles_m;
+                for (int t = 0; t < p.tiles_n; ++t) {
+                    tc::mbar_wait(&b_empty[s], ph ^ 1);
+                    tc::mbar_arrive_expect_tx(&b_full[s], (uint32_t)stage_bytes);
+                    for (int kb = 0; kb < p.kblocks; ++kb)
+                        tc::tma_load_3d(sB + (size_t)s * stage_bytes + (size_t)kb * B_KB_BYTES, &mapE, &b_full[s],
+                                        kb * 64, t * C::BN, g);
+                    if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            const uint32_t idesc = tc::make_idesc(0, TM, C::BN, 0, 0);
+            const uint64_t descB0 = tc::make_smem_desc(tc::smem_u32(sB), 16, 1024);
+            const uint32_t stage_stride = (uint32_t)stage_bytes >> 4;
+            uint32_t offB[8];
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks) offB[ks] = (uint32_t)((ks >> 2) * B_KB_BYTES + (ks & 3) * 32) >> 4;
+            const uint32_t a_sub = (uint32_t)(p.KD >> 1);        // TMEM columns of one sub-tile's z operand
+            uint32_t it = 0, item_n = 0, s = 0, ph = 0;
+            for (int item = blockIdx.x; item < items; item += gridDim.x, ++item_n) {
+                tc::mbar_wait(a_full, item_n & 1);               // z of this row tile sits in TMEM
+                tc::fence_after_thread_sync();
+                for (int t = 0; t < p.tiles_n; ++t, ++it) {
+                    const uint32_t ab = it & 1, aph = (it >> 1) & 1;
+                    tc::mbar_wait(&b_full[s], ph);
+                    tc::mbar_wait(&acc_empty[ab], aph ^ 1);
+                    tc::fence_after_thread_sync();
+                    const uint64_t descB = descB0 + (uint64_t)(s * stage_stride);
+#pragma unroll
+                    for (int sub = 0; sub < SUB; ++sub) {
+                        const uint32_t d_tmem = tmem_base + A_COLS + (ab * SUB + sub) * C::BN;
+                        const uint32_t a_tmem = tmem_base + sub * a_sub;
+#pragma unroll
+                        for (int ks = 0; ks < 8; ++ks)
+                            if (ks < p.ksteps)
+                                tc::mma_f16_ts(d_tmem, a_tmem + ks * 8, descB + offB[ks], idesc, ks > 0 ? 1u : 0u);
+                    }
+                    tc::mma_commit(&b_empty[s]);      // smem stage free once these MMAs have read it
+                    tc::mma_commit(&acc_full[ab]);    // scores ready for the epilogue
+                    if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue: one row per thread =====================
+        const int q = warp & 3;                        // TMEM lane quarter == warp % 4
+        const int sub = (warp - 4) >> 2;               // 128-row sub-tile
+        const int r = sub * TM + q * 32 + lane;
+        const float emax = *p.emax;
+        float2* myring = ring + r;                     // slot i at myring[i * TMR]
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+        uint32_t it = 0;
+        for (int item = blockIdx.x; item < items; item += gridDim.x) {
+            const int g = item / p.tiles_m, mt = item - g * p.tiles_m;
+            const int row = mt * C::TMR + r;
+            const bool valid = row < p.B;
+            const float* zr = p.z + (long long)g * p.z_gs + (long long)(valid ? row : 0) * p.ldz;
+            // ---- z row: fp32 -> fp16 (+ two 1.0 columns) -> TMEM; |z|^2 in the reference's order
+            float zz = 0.f;
+            {
+                const uint32_t a_addr = lane_addr + sub * (uint32_t)(p.KD >> 1);
+                for (int ks = 0; ks < p.ksteps; ++ks) {
+                    const int d0 = ks * 16;
+                    float f[16];
+                    if (p.zvec && d0 + 16 <= p.D) {
+#pragma unroll
+                        for (int j = 0; j < 16; j += 4) {
+                            const float4 v = *reinterpret_cast<const float4*>(zr + d0 + j);
+                            f[j] = v.x; f[j + 1] = v.y; f[j + 2] = v.z; f[j + 3] = v.w;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const int d = d0 + j;
+                            f[j] = d < p.D ? zr[d] : ((d == p.D || d == p.D + 1) ? 1.0f : 0.f);
+                        }
+                    }
+                    uint32_t u[8];
+#pragma unroll
+                    for (int j = 0; j < 16; j += 2) {
+                        if (d0 + j < p.D) zz = fmaf(f[j], f[j], zz);
+                        if (d0 + j + 1 < p.D) zz = fmaf(f[j + 1], f[j + 1], zz);
+                        const __half2 h = __floats2half2_rn(f[j], f[j + 1]);
+                        u[j >> 1] = *reinterpret_cast<const uint32_t*>(&h);
+                    }
+                    tc::tmem_st_32x8(a_addr + ks * 8, u);
+                }
+                tc::tmem_st_wait();
+                tc::fence_before_thread_sync();
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(a_full);
+            }
+            const float znorm = sqrtf(zz);
+            // margins in distance units (d = |z|^2 - 2 s); the scores use half of them
+            const float margin_d = p.margin_scale * znorm * emax + p.margin_abs * (1.0f + znorm + emax);
+            const float margin = 0.5f * margin_d;
+            // the fp16 image must be finite and the codebook representable
+            // (|z_d| < 65504; -|e|^2/2 must stay above the -60000 of the padding codes)
+            const bool zbad = !(zz < 1.0e9f) || !(emax < 250.0f);
+            float runmax = -INFINITY, thr = -INFINITY, evmax = -INFINITY;
+            int cnt = 0;
+
+            const int nchunks = p.tiles_n * C::NCH;
+            const uint32_t acc_addr = lane_addr + A_COLS + sub * C::BN;
+            int ld_tile = 0, ld_c = 0;                           // next chunk to load
+            int rt_c = 0;  uint32_t rt_it = it;                  // next chunk to retire
+            auto issue = [&](float (&buf)[32]) {
+                const uint32_t git = it + ld_tile, ab = git & 1;
+                if (ld_c == 0) {
+                    tc::mbar_wait(&acc_full[ab], (git >> 1) & 1);
+                    tc::fence_after_thread_sync();
+                }
+                tc::tmem_ld_32x32(acc_addr + ab * SUB * C::BN + ld_c * 32, buf);
+                if (++ld_c == C::NCH) { ld_c = 0; ++ld_tile; }
+            };
+            auto retire = [&]() {                                // after wait::ld: the chunk is in registers
+                if (++rt_c == C::NCH) {
+                    rt_c = 0;
+                    tc::fence_before_thread_sync();
+                    __syncwarp();
+                    if (lane == 0) tc::mbar_arrive(&acc_empty[rt_it & 1]);
+                    ++rt_it;
+                }
+            };
+            auto consume = [&](const float (&v)[32], int n) {
+                // chunk maximum: 17 instructions for 32 scores
+                const float a0 = tc::max3(v[0], v[1], v[2]), a1 = tc::max3(v[3], v[4], v[5]);
+                const float a2 = tc::max3(v[6], v[7], v[8]), a3 = tc::max3(v[9], v[10], v[11]);
+                const float a4 = tc::max3(v[12], v[13], v[14]), a5 = tc::max3(v[15], v[16], v[17]);
+                const float a6 = tc::max3(v[18], v[19], v[20]), a7 = tc::max3(v[21], v[22], v[23]);
+                const float a8 = tc::max3(v[24], v[25], v[26]), a9 = tc::max3(v[27], v[28], v[29]);
+                const float b0 = tc::max3(a0, a1, a2), b1 = tc::max3(a3, a4, a5), b2 = tc::max3(a6, a7, a8);
+                const float b3 = tc::max3(a9, v[30], v[31]);
+                const float cm = fmaxf(tc::max3(b0, b1, b2), b3);
+                if (__any_sync(0xffffffffu, cm >= thr)) {
+                    // some row of this warp has a score within the band of its running maximum
+                    runmax = fmaxf(runmax, cm);
+                    thr = runmax - margin;
+                    uint32_t mask = 0;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) mask |= (v[j] >= thr) ? (1u << j) : 0u;
+                    const int kbase = n * 32;                    // chunks are consecutive 32-code blocks
+                    while (mask) {
+                        const int j = __ffs(mask) - 1;
+                        mask &= mask - 1;
+                        float2* slot = myring + (cnt & (RING - 1)) * C::TMR;
+                        if (cnt >= RING) evmax = fmaxf(evmax, slot->x);
+                        *slot = make_float2(cm, __int_as_float(kbase + j));
+                        ++cnt;
+                    }
+                }
+            };
+            float va[32], vb[32];
+            issue(va);
+            for (int n = 0; n < nchunks; n += 2) {
+                tc::tmem_ld_wait(va);
+                retire();
+                if (n + 1 < nchunks) issue(vb);
+                consume(va, n);
+                if (n + 1 < nchunks) {
+                    tc::tmem_ld_wait(vb);
+                    retire();
+                    if (n + 2 < nchunks) issue(va);
+                    consume(vb, n + 1);
+                }
+            }
+            it += p.tiles_n;
+
+            if (valid) {
+                const long long o = (long long)g * p.idx_gs + row;
+                const float thr_f = runmax - margin;
+                // NaN-safe: every comparison below is false for NaN, which routes the row to the full scan
+                bool ok = !zbad && (runmax > -3.0e38f) && (runmax < 3.0e38f) && !(evmax >= thr_f) && cnt > 0;
+                int nq = 0, k0 = 0;
+                const int nring = cnt < RING ? cnt : RING;
+                if (ok) {
+                    for (int i = 0; i < nring; ++i) {
+                        const float2 c = myring[i * C::TMR];
+                        if (c.x >= thr_f && __float_as_int(c.y) < p.K) { k0 = __float_as_int(c.y); ++nq; }
+                    }
+                    ok = nq >= 1;
+                }
+                if (ok) {
+                    int bi = k0;
+                    if (nq > 1 || p.best || p.gap) {
+                        // exact fp32 distances of the candidates: same arithmetic as the CUDA-core kernel
+                        float best = INFINITY, second = INFINITY;
+                        bi = 0x7fffffff;
+                        const float* eg = p.e + (long long)g * p.e_gs;
+                        for (int i = 0; i < nring; ++i) {
+                            const float2 c = myring[i * C::TMR];
+                            const int k = __float_as_int(c.y);
+                            if (!(c.x >= thr_f) || k >= p.K) continue;
+                            const float* er = eg + (long long)k * p.lde;
+                            float acc = 0.f;
+                            for (int d = 0; d < p.D; ++d) acc = fmaf(zr[d], __ldg(er + d), acc);
+                            const float dist = (zz - 2.0f * acc) + __ldg(p.ee + (long long)g * p.Kpad + k);
+                            if (dist < best || (dist == best && k < bi)) { second = best; best = dist; bi = k; }
+                            else if (dist < second) second = dist;
+                        }
+                        if (p.best) p.best[o] = best;
+                        // exact gap when a runner-up lies inside the error band, otherwise a lower bound
+                        if (p.gap) p.gap[o] = nq > 1 ? second - best : margin_d;
+                    }
+                    p.idx[o] = bi;
+                    if (p.dw) scatter_row(p, g, zr, bi);
+                } else {
+                    p.idx[o] = 0;
+                    const int slot = atomicAdd(p.flag_count, 1);
+                    p.flag_list[slot] = make_int2(g, row);
+                }
+            }
+        }
+    }
+    tc::fence_before_thread_sync();
+    __syncthreads();
+    if (warp == 2) {
+        tc::fence_after_thread_sync();
+        tc::tmem_dealloc(tmem_base, 512u);
+    }
+}
+
+// Exact fp32 full scan of the flagged rows: one warp per row, lanes over codes; identical
+// arithmetic to vq_assign_kernel (sequential fmaf over d, (zz - 2 dot) + ee, lowest index on ties).
+__global__ void __launch_bounds__(256) vq16_rescore_kernel(const Vq16P p) {
+    extern __shared__ float zsm[];                 // [8 warps][D]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* zs = zsm + warp * p.D;
+    const int n = *p.flag_count;
+    for (int w = blockIdx.x * 8 + warp; w < n; w += gridDim.x * 8) {
+        const int2 gr = p.flag_list[w];
+        const float* zr = p.z + (long long)gr.x * p.z_gs + (long long)gr.y * p.ldz;
+        __syncwarp();
+        for (int d = lane; d < p.D; d += 32) zs[d] = zr[d];
+        __syncwarp();
+        float zz = 0.f;
+        for (int d = 0; d < p.D; ++d) zz = fmaf(zs[d], zs[d], zz);
+        float best = INFINITY, second = INFINITY;
+        int bi = 0x7fffffff;
+        const float* eg = p.e + (long long)gr.x * p.e_gs;
+        for (int k = lane; k < p.K; k += 32) {
+            const float* er = eg + (long long)k * p.lde;
+            float acc = 0.f;
+            for (int d = 0; d < p.D; ++d) acc = fmaf(zs[d], __ldg(er + d), acc);
+            const float dist = (zz - 2.0f * acc) + __ldg(p.ee + (long long)gr.x * p.Kpad + k);
+            if (dist < best) { second = best; best = dist; bi = k; }
+            else if (dist < second) second = dist;
+        }
+        float gb = best; int gi = bi;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ob = __shfl_xor_sync(0xffffffffu, gb, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, gi, o);
+            if (ob < gb || (ob == gb && oi < gi)) { gb = ob; gi = oi; }
+        }
+        if (gi == 0x7fffffff) gi = 0;              // every distance NaN: tf.argmin returns 0
+        float cand = (bi == gi) ? second : best;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) cand = fminf(cand, __shfl_xor_sync(0xffffffffu, cand, o));
+        if (lane == 0) {
+            const long long o = (long long)gr.x * p.idx_gs + gr.y;
+            p.idx[o] = gi;
+            if (p.best) p.best[o] = gb;
+            if (p.gap) p.gap[o] = cand - gb;
+            if (p.dw) scatter_row(p, gr.x, zr, gi);
+        }
+    }
+}
+
+inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+int ensure_scratch(pgmvae_ctx* ctx, size_t bytes) {
+    if (ctx->scratch_bytes >= bytes) return PGMVAE_OK;
+    if (ctx->scratch) {
+        PG_CUDA(cudaStreamSynchronize(ctx->stream));
+        PG_CUDA(cudaFree(ctx->scratch));
+        ctx->scratch = nullptr;
+        ctx->scratch_bytes = 0;
+    }
+    PG_CUDA(cudaMalloc(&ctx->scratch, bytes));
+    ctx->scratch_bytes = bytes;
+    return PGMVAE_OK;
+}
+
+template <int SUB>
+int launch16(pgmvae_ctx* ctx, cudaStream_t st, const CUtensorMap& mapE, Vq16P& p) {
+    using C = Cfg<SUB>;
+    p.tiles_m = (int)pg_cdiv(p.B, C::TMR);
+    const size_t fixed = 1024 + (size_t)RING * C::TMR * sizeof(float2) + 256;
+    const size_t stage_bytes = (size_t)p.kblocks * C::BN * KB_BYTES;
+    p.stages = MAX_STAGES;
+    while (p.stages > 2 && fixed + p.stages * stage_bytes > ctx->smem_optin) --p.stages;
+    const size_t smem = fixed + p.stages * stage_bytes;
+    if (smem > ctx->smem_optin) {
+        pgmvae_set_error("vq_assign (fp16 tensor core): shared memory %zu exceeds %zu", smem, ctx->smem_optin);
+        return PGMVAE_EINVAL;
+    }
+    static size_t configured = 0;
+    if (smem > configured) {
+        PG_CUDA(cudaFuncSetAttribute(vq_assign_f16_kernel<SUB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    const int items = p.G * p.tiles_m;
+    const int grid = items < ctx->sm_count ? items : ctx->sm_count;
+    vq_assign_f16_kernel<SUB><<<grid, C::THREADS, smem, st>>>(mapE, p);
+    return PGMVAE_OK;
+}
+
+}  // namespace
+
+bool pg_vq_assign_f16_supported(int D, int K) { return K >= 1 && D >= 1 && D + 2 <= 128; }
+
+// assignment (+ optional fused EMA statistics when cnt/dw are given; they are accumulated into)
+int pg_vq_assign_f16(pgmvae_ctx* ctx, cudaStream_t st, const float* z, int64_t z_gs, int ldz, const float* e,
+                     int64_t e_gs, int lde, int32_t* idx, int64_t idx_gs, float* best_opt, float* gap_opt,
+                     float* cnt_opt, int64_t c_gs, float* dw_opt, int64_t dw_gs, int lddw, int G, int B, int D, int K) {
+    if (G <= 0 || B <= 0) return PGMVAE_OK;
+    Vq16P p{};
+    p.G = G; p.B = B; p.D = D; p.K = K;
+    p.KD = pg_round_up(D + 2, 16);
+    p.ksteps = p.KD / 16;
+    p.kblocks = (int)pg_cdiv(p.KD, 64);
+    // three 128-row sub-tiles (12 epilogue warps, 64-code tiles) when the z operand fits 128 TMEM columns
+    int sub = 2;
+    if (const char* ev = getenv("PGMVAE_VQ_SUB")) sub = atoi(ev) == 3 ? 3 : 2;
+    if (3 * (p.KD / 2) > A_COLS) sub = 2;
+    const int BN = sub == 2 ? Cfg<2>::BN : Cfg<3>::BN;
+    p.tiles_n = (int)pg_cdiv(K, BN);
+    p.Kpad = p.tiles_n * BN;
+    const size_t off_ee = 0, off_emax = align256((size_t)G * p.Kpad * 4), off_cnt = off_emax + 256,
+                 off_list = off_cnt + 256, off_e16 = align256(off_list + (size_t)G * B * sizeof(int2)),
+                 total = off_e16 + (size_t)G * p.Kpad * p.KD * 2;
+    PG_TRY(ensure_scratch(ctx, total));
+    ctx->vq_cnt_off = off_cnt;
+    uint8_t* sc = (uint8_t*)ctx->scratch;
+    float* ee = (float*)(sc + off_ee);
+    float* emax = (float*)(sc + off_emax);
+    int* cnt = (int*)(sc + off_cnt);
+    int2* list = (int2*)(sc + off_list);
+    __half* e16 = (__half*)(sc + off_e16);
+    p.z = z; p.z_gs = z_gs; p.ldz = ldz; p.e = e; p.e_gs = e_gs; p.lde = lde; p.ee = ee; p.emax = emax;
+    p.zvec = !((uintptr_t)z & 15) && ldz % 4 == 0 && z_gs % 4 == 0;
+    p.idx = idx; p.idx_gs = idx_gs; p.best = best_opt; p.gap = gap_opt;
+    p.cnt = cnt_opt; p.c_gs = c_gs; p.dw = (cnt_opt && dw_opt) ? dw_opt : nullptr; p.dw_gs = dw_gs; p.lddw = lddw;
+    p.flag_count = cnt; p.flag_list = list;
+    // 2 eps in distance units: fp16 rounds to nearest (2^-11 per operand) -> |d~ - d| <= 2^-9 |z| |e|
+    p.margin_scale = 0.00390625f;
+    p.margin_abs = 2e-5f;
+
+    PG_CUDA(cudaMemsetAsync(emax, 0, 512, st));       // emax and the flag counter
+    PG_KERNEL(ctx, st, "vq_e_prep", (double)G * K * (4.0 * D + 4.0 + 2.0 * p.KD), 2.0 * G * K * D);
+    e_prep_kernel<<<(unsigned)pg_cdiv((int64_t)G * p.Kpad, 128), 128, 0, st>>>(e, e_gs, lde, ee, emax, e16, G, K, p.Kpad, D,
+                                                                              p.KD);
+    PG_LAUNCHED(ctx);
+
+    CUtensorMap mapE;
+    PG_TRY(tc::make_map(&mapE, e16, 2, (uint64_t)p.KD, (uint64_t)p.Kpad, (uint64_t)G, (uint64_t)p.KD,
+                        (uint64_t)p.Kpad * p.KD, 64, (uint32_t)BN));
+    const double fused = p.dw ? 4.0 * G * (double)K * (D + 1.0) : 0.0;
+    PG_KERNEL(ctx, st, p.dw ? "vq_assign_ema_tc_f16" : "vq_assign_tc_f16",
+              4.0 * ((double)G * B * D + (double)G * K * D + (double)G * B) + fused, 2.0 * G * B * (double)D * K);
+    if (sub == 3) PG_TRY(launch16<3>(ctx, st, mapE, p));
+    else PG_TRY(launch16<2>(ctx, st, mapE, p));
+    PG_LAUNCHED(ctx);
+
+    PG_KERNEL(ctx, st, "vq_rescore_fp32", 0.0, 0.0);
+    vq16_rescore_kernel<<<ctx->sm_count * 4, 256, 8 * D * sizeof(float), st>>>(p);
+    PG_LAUNCHED(ctx);
+    return PGMVAE_OK;
+}

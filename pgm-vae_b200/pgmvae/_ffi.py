@@ -69,6 +69,8 @@ SIGNATURES = {
     "pgmvae_dense_wgrad": (_i, [_vp, _vp, _vp, _i64, _i, _vp, _i64, _i, _vp, _i64, _i, _vp, _i64,
                                 _i, _i, _i, _i, _i]),
     "pgmvae_vq_assign": (_i, [_vp, _vp, _vp, _i64, _i, _vp, _i64, _i, _vp, _i64, _vp, _vp, _i, _i, _i, _i]),
+    "pgmvae_vq_assign_ema": (_i, [_vp, _vp, _vp, _i64, _i, _vp, _i64, _i, _vp, _i64, _vp, _i64, _vp, _i64, _i,
+                                  _i, _i, _i, _i]),
     "pgmvae_vq_assign_rescored": (_i, [_vp, _i, _i, C.POINTER(_i)]),
     "pgmvae_vq_quantize": (_i, [_vp, _vp, _vp, _i64, _i, _vp, _i64, _i, _vp, _i64, _vp, _vp, _i64, _i, _vp,
                                 _i, _i, _i, _i]),

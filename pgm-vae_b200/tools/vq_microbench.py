@@ -21,7 +21,8 @@ def main():
     ap.add_argument("--prec", default="tf32", choices=["fp32", "tf32", "f16"])
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--clustered", action="store_true")
-    ap.add_argument("--scatter", action="store_true")
+    ap.add_argument("--scatter", action="store_true", help="follow the assignment by the stand-alone EMA scatter")
+    ap.add_argument("--fused", action="store_true", help="pgmvae_vq_assign_ema: scatter fused into the f16 kernel")
     a = ap.parse_args()
     ctx = _ffi.get_context(0)
     L = _ffi.lib()
@@ -38,6 +39,10 @@ def main():
     ctx.set_precision({"fp32": _ffi.PREC_FP32, "tf32": _ffi.PREC_TF32, "f16": _ffi.PREC_BF16}[a.prec])
 
     def run():
+        if a.fused:
+            _ffi.check(L.pgmvae_vq_assign_ema(ctx.h, None, dz.ptr, a.n * a.d, a.d, de.ptr, a.k * a.d, a.d, idx.ptr, a.n,
+                                              cnt.ptr, a.k, dw.ptr, a.k * a.d, a.d, 1, a.n, a.d, a.k))
+            return
         _ffi.check(L.pgmvae_vq_assign(ctx.h, None, dz.ptr, a.n * a.d, a.d, de.ptr, a.k * a.d, a.d, idx.ptr, a.n,
                                       None, None, 1, a.n, a.d, a.k))
         if a.scatter:
@@ -57,7 +62,7 @@ def main():
     if a.prec != "fp32":
         _ffi.check(L.pgmvae_vq_assign_rescored(ctx.h, 1, a.k, C.byref(n)))
     flops = 2.0 * a.n * a.d * a.k
-    print(json.dumps({"n": a.n, "d": a.d, "k": a.k, "prec": a.prec, "clustered": a.clustered, "scatter": a.scatter,
+    print(json.dumps({"n": a.n, "d": a.d, "k": a.k, "prec": a.prec, "clustered": a.clustered, "scatter": a.scatter, "fused": a.fused, "sub": os.environ.get("PGMVAE_VQ_SUB", "2"),
                       "ms": ms, "vectors_per_s": a.n / (ms * 1e-3), "useful_tflops": flops / (ms * 1e-3) / 1e12,
                       "rescored_rows": n.value, "kernels": prof}))
 

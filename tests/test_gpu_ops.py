@@ -285,3 +285,35 @@ def test_vq_assign_tensor_core_dead_codes(ctx):
     np.testing.assert_array_equal(res[_ffi.PREC_TF32], res[_ffi.PREC_FP32])
     np.testing.assert_array_equal(res[_ffi.PREC_BF16], res[_ffi.PREC_FP32])
     assert (res[_ffi.PREC_FP32] == 40).mean() > 0.5
+
+
+@pytest.mark.parametrize("G,B,D,K,sub", [(1, 3000, 64, 8192, 2), (1, 3000, 64, 8192, 3), (3, 700, 16, 200, 2),
+                                         (2, 515, 30, 97, 3), (1, 100, 126, 300, 2)])
+def test_vq_assign_ema_fused_equals_separate(ctx, G, B, D, K, sub, monkeypatch):
+    """Fused single-pass fp16 tensor-core assignment + EMA scatter (pgmvae_vq_assign_ema) against the exact
+    fp32 assignment followed by the stand-alone scatter: indices and counts bit-exact, sums to fp32 rounding."""
+    from pgmvae import _ffi
+    monkeypatch.setenv("PGMVAE_VQ_SUB", str(sub))
+    rng = np.random.default_rng(G * 7 + B + D + K)
+    e = (rng.uniform(-1, 1, (G, K, D)) * np.sqrt(3.0 / D)).astype(np.float32)
+    pick = rng.integers(0, K, (G, B))
+    z = (np.take_along_axis(e, pick[..., None], 1) + 0.3 * rng.standard_normal((G, B, D))).astype(np.float32)
+    dz, de = _ffi.DeviceArray.from_numpy(ctx, z), _ffi.DeviceArray.from_numpy(ctx, e)
+    L = _ffi.lib()
+    idx_ref = _ffi.DeviceArray(ctx, (G, B), np.int32)
+    cnt_ref, dw_ref = _ffi.DeviceArray(ctx, (G, K)), _ffi.DeviceArray(ctx, (G, K, D))
+    _ffi.check(L.pgmvae_vq_assign(ctx.h, None, dz.ptr, B * D, D, de.ptr, K * D, D, idx_ref.ptr, B, None, None, G, B, D, K))
+    _ffi.check(L.pgmvae_ema_stats(ctx.h, None, dz.ptr, B * D, D, idx_ref.ptr, B, cnt_ref.ptr, K, dw_ref.ptr, K * D, D,
+                                  G, B, D, K))
+    idx = _ffi.DeviceArray(ctx, (G, B), np.int32)
+    cnt, dw = _ffi.DeviceArray(ctx, (G, K)), _ffi.DeviceArray(ctx, (G, K, D))
+    _ffi.check(L.pgmvae_vq_assign_ema(ctx.h, None, dz.ptr, B * D, D, de.ptr, K * D, D, idx.ptr, B, cnt.ptr, K, dw.ptr,
+                                      K * D, D, G, B, D, K))
+    n = C.c_int(0)
+    _ffi.check(L.pgmvae_vq_assign_rescored(ctx.h, G, K, C.byref(n)))
+    print(f"fused vq+ema: G={G} B={B} D={D} K={K} sub={sub}: full-scan rows {n.value}/{G * B}")
+    assert n.value <= G * B // 50 + 1
+    np.testing.assert_array_equal(idx.numpy(), idx_ref.numpy())
+    np.testing.assert_array_equal(cnt.numpy(), cnt_ref.numpy())
+    assert cnt.numpy().sum() == G * B
+    np.testing.assert_allclose(dw.numpy(), dw_ref.numpy(), rtol=1e-5, atol=1e-5)
