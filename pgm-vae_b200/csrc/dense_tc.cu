@@ -110,32 +110,35 @@ __global__ void __launch_bounds__(128) dense_tc_kernel(const __grid_constant__ C
     const uint32_t tmem_base = *tmem_slot;
 
     if (nkb > 0) {
-        if (warp == 0 && lane == 0) {
-            // ===================== TMA producer =====================
+        if (warp == 0) {
+            // ===================== TMA producer (warp-uniform loop, one elected lane issues) =====================
             const uint32_t stage_tx = (uint32_t)(A_STAGE_BYTES + b_stage_bytes);
             uint32_t s = 0, ph = 0;
             const int ga = p.a_shared ? 0 : g;
             for (int kb = kb_beg; kb < kb_end; ++kb) {
                 tc::mbar_wait(&empty[s], ph ^ 1);
-                tc::mbar_arrive_expect_tx(&full[s], stage_tx);
-                uint8_t* a_dst = sA + (size_t)s * A_STAGE_BYTES;
-                uint8_t* b_dst = sB + (size_t)s * b_stage_bytes;
-                if (!p.a_mn) {
-                    tc::tma_load_3d(a_dst, &mapA, &full[s], kb * KBLK, m0, ga);                 // [128 m][32 k]
-                } else {
-                    for (int pn = 0; pn < TM / 32; ++pn)                                        // 4 panels [32 k][32 m]
-                        tc::tma_load_3d(a_dst + pn * 4096, &mapA, &full[s], m0 + pn * 32, kb * KBLK, ga);
+                if (tc::elect_one()) {
+                    tc::mbar_arrive_expect_tx(&full[s], stage_tx);
+                    uint8_t* a_dst = sA + (size_t)s * A_STAGE_BYTES;
+                    uint8_t* b_dst = sB + (size_t)s * b_stage_bytes;
+                    if (!p.a_mn) {
+                        tc::tma_load_3d(a_dst, &mapA, &full[s], kb * KBLK, m0, ga);                 // [128 m][32 k]
+                    } else {
+                        for (int pn = 0; pn < TM / 32; ++pn)                                        // 4 panels [32 k][32 m]
+                            tc::tma_load_3d(a_dst + pn * 4096, &mapA, &full[s], m0 + pn * 32, kb * KBLK, ga);
+                    }
+                    if (!p.b_mn) {
+                        tc::tma_load_3d(b_dst, &mapB, &full[s], kb * KBLK, n0, g);                 // [BN n][32 k]
+                    } else {
+                        for (int pn = 0; pn < p.BN / 32; ++pn)                                      // panels [32 k][32 n]
+                            tc::tma_load_3d(b_dst + pn * 4096, &mapB, &full[s], n0 + pn * 32, kb * KBLK, g);
+                    }
                 }
-                if (!p.b_mn) {
-                    tc::tma_load_3d(b_dst, &mapB, &full[s], kb * KBLK, n0, g);                 // [BN n][32 k]
-                } else {
-                    for (int pn = 0; pn < p.BN / 32; ++pn)                                      // panels [32 k][32 n]
-                        tc::tma_load_3d(b_dst + pn * 4096, &mapB, &full[s], n0 + pn * 32, kb * KBLK, g);
-                }
+                __syncwarp();
                 if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1; }
             }
-        } else if (warp == 1 && lane == 0) {
-            // ===================== MMA issuer =====================
+        } else if (warp == 1) {
+            // ===================== MMA issuer (warp-uniform loop, one elected lane issues) =====================
             const uint32_t idesc = tc::make_idesc(2, TM, p.BN, p.a_mn, p.b_mn);
             // K-major: rows of 128 B along k, 8-row atoms 1024 B apart; one MMA (k = 8) advances 32 B.
             // MN-major (32-byte-atom swizzle): panels of [32 k][128 B along m/n], 4096 B apart (LBO),
@@ -150,15 +153,18 @@ __global__ void __launch_bounds__(128) dense_tc_kernel(const __grid_constant__ C
             for (int kb = kb_beg; kb < kb_end; ++kb) {
                 tc::mbar_wait(&full[s], ph);
                 tc::fence_after_thread_sync();
-                const uint64_t dA = dA0 + (uint64_t)(s * a_stage), dB = dB0 + (uint64_t)(s * b_stage);
+                if (tc::elect_one()) {
+                    const uint64_t dA = dA0 + (uint64_t)(s * a_stage), dB = dB0 + (uint64_t)(s * b_stage);
 #pragma unroll
-                for (int k4 = 0; k4 < 4; ++k4)
-                    tc::mma_tf32(tmem_base, dA + (uint64_t)(k4 * a_step), dB + (uint64_t)(k4 * b_step), idesc,
-                                 (kb > kb_beg || k4 > 0) ? 1u : 0u);
-                tc::mma_commit(&empty[s]);
+                    for (int k4 = 0; k4 < 4; ++k4)
+                        tc::mma_tf32(tmem_base, dA + (uint64_t)(k4 * a_step), dB + (uint64_t)(k4 * b_step), idesc,
+                                     (kb > kb_beg || k4 > 0) ? 1u : 0u);
+                    tc::mma_commit(&empty[s]);
+                    if (kb == kb_end - 1) tc::mma_commit(acc_full);
+                }
+                __syncwarp();
                 if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1; }
             }
-            tc::mma_commit(acc_full);
         }
         __syncwarp();
         tc::mbar_wait(acc_full, 0);

@@ -90,6 +90,41 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
             : "memory");
     } while (!done);
 }
+// The same with a suspend-time hint: the hardware parks the thread until the phase completes (or the
+// hint expires) instead of returning to the polling loop every few hundred cycles.  For the
+// single-lane producer / MMA roles, whose polling would otherwise eat the issue slots of the
+// epilogue warps that share their scheduler.
+__device__ __forceinline__ void mbar_wait_parked(uint64_t* bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}\n"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680)
+            : "memory");
+    } while (!done);
+}
+
+// One lane of a fully converged warp.  The single-thread roles (TMA producer, MMA issuer) run
+// their loops WARP-UNIFORMLY and gate only the issuing instructions with this: addresses and
+// descriptors then live in uniform registers.  Gating the whole role with `lane == 0` instead makes
+// every operand of UTCHMMA / UTMALDG a per-thread value that has to be moved to a uniform register
+// through a VOTE / ELECT / R2UR sequence (~150 cycles per MMA in the first version of these kernels).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
 
 // ------------------------------------------------------------------ device: TMA
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {

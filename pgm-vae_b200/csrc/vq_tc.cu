@@ -158,85 +158,74 @@ vq_assign_tc_kernel(const __grid_constant__ CUtensorMap mapZ, const __grid_const
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        // ===================== TMA producer =====================
-        if (lane == 0) {
-            uint32_t item_n = 0, s = 0, ph = 0;
-            for (int item = blockIdx.x; item < items; item += gridDim.x, ++item_n) {
-                const int g = item / p.tiles_m, mt = item - g * p.tiles_m;
-                tc::mbar_wait(a_empty, (item_n & 1) ^ 1);
+        // ===================== TMA producer (warp-uniform loop, one elected lane issues) =====================
+        uint32_t item_n = 0, s = 0, ph = 0;
+        for (int item = blockIdx.x; item < items; item += gridDim.x, ++item_n) {
+            const int g = item / p.tiles_m, mt = item - g * p.tiles_m;
+            tc::mbar_wait(a_empty, (item_n & 1) ^ 1);
+            if (tc::elect_one()) {
                 tc::mbar_arrive_expect_tx(a_full, (uint32_t)(SUB * p.kblocks * A_TILE_BYTES));
                 for (int sub = 0; sub < SUB; ++sub)
                     for (int kb = 0; kb < p.kblocks; ++kb)
                         tc::tma_load_3d(sA + (size_t)(sub * p.kblocks + kb) * A_TILE_BYTES, &mapZ, a_full,
                                         kb * KB_ELEMS, mt * TMR + sub * TM, g);
-                // |e|^2 of this group's codes: reloaded once the epilogue has left the previous item
-                tc::mbar_wait(e_done, (item_n & 1) ^ 1);
+            }
+            __syncwarp();
+            // |e|^2 of this group's codes: reloaded once the epilogue has left the previous item
+            tc::mbar_wait(e_done, (item_n & 1) ^ 1);
+            if (tc::elect_one()) {
                 tc::mbar_arrive_expect_tx(ee_full, (uint32_t)(p.Kpad * 4));
                 tc::bulk_load_1d(sEE, p.ee + (long long)g * p.Kpad, (uint32_t)(p.Kpad * 4), ee_full);
-                for (int tt = 0; tt < tiles_item; ++tt) {
-                    const int t = tt < p.tiles_n ? tt : tt - p.tiles_n;
-                    tc::mbar_wait(&b_empty[s], ph ^ 1);
+            }
+            __syncwarp();
+            for (int tt = 0; tt < tiles_item; ++tt) {
+                const int t = tt < p.tiles_n ? tt : tt - p.tiles_n;
+                tc::mbar_wait(&b_empty[s], ph ^ 1);
+                if (tc::elect_one()) {
                     tc::mbar_arrive_expect_tx(&b_full[s], (uint32_t)(p.kblocks * b_tile_bytes));
                     for (int kb = 0; kb < p.kblocks; ++kb)
                         tc::tma_load_3d(sB + ((size_t)s * p.kblocks + kb) * b_tile_bytes, &mapE, &b_full[s],
                                         kb * KB_ELEMS, t * p.BN, g);
-                    if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1; }
                 }
+                __syncwarp();
+                if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1; }
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
-            const uint32_t idesc = tc::make_idesc(F16 ? 0 : 2, TM, p.BN, 0, 0);
-            // The issuing thread is a serial instruction stream: everything loop-invariant is hoisted.
-            // Descriptors differ only in the 14-bit start-address field (units of 16 bytes).
-            const uint64_t descA0 = tc::make_smem_desc(tc::smem_u32(sA), 16, 1024);
-            const uint64_t descB0 = tc::make_smem_desc(tc::smem_u32(sB), 16, 1024);
-            const uint32_t sub_stride = (uint32_t)(p.kblocks * A_TILE_BYTES) >> 4;
-            const uint32_t stage_stride = (uint32_t)(p.kblocks * b_tile_bytes) >> 4;
-            uint32_t offA[8], offB[8];
-#pragma unroll
-            for (int ks = 0; ks < 8; ++ks) {
-                offA[ks] = (uint32_t)((ks >> 2) * A_TILE_BYTES + (ks & 3) * 32) >> 4;
-                offB[ks] = (uint32_t)((ks >> 2) * b_tile_bytes + (ks & 3) * 32) >> 4;
-            }
-            uint32_t it = 0, item_n = 0, s = 0, ph = 0;
-            for (int item = blockIdx.x; item < items; item += gridDim.x, ++item_n) {
-                tc::mbar_wait(a_full, item_n & 1);
+        // ===================== MMA issuer (warp-uniform loop, one elected lane issues) =====================
+        const uint32_t idesc = tc::make_idesc(F16 ? 0 : 2, TM, p.BN, 0, 0);
+        // Descriptors differ only in the 14-bit start-address field (units of 16 bytes).
+        const uint64_t descA0 = tc::make_smem_desc(tc::smem_u32(sA), 16, 1024);
+        const uint64_t descB0 = tc::make_smem_desc(tc::smem_u32(sB), 16, 1024);
+        const uint32_t sub_stride = (uint32_t)(p.kblocks * A_TILE_BYTES) >> 4;
+        const uint32_t stage_stride = (uint32_t)(p.kblocks * b_tile_bytes) >> 4;
+        uint32_t it = 0, item_n = 0, s = 0, ph = 0;
+        for (int item = blockIdx.x; item < items; item += gridDim.x, ++item_n) {
+            tc::mbar_wait(a_full, item_n & 1);
+            for (int tt = 0; tt < tiles_item; ++tt, ++it) {
+                const uint32_t ab = it & 1, aph = (it >> 1) & 1;
+                tc::mbar_wait(&b_full[s], ph);
+                tc::mbar_wait(&acc_empty[ab], aph ^ 1);
                 tc::fence_after_thread_sync();
-                for (int tt = 0; tt < tiles_item; ++tt, ++it) {
-                    const uint32_t ab = it & 1, aph = (it >> 1) & 1;
-                    tc::mbar_wait(&b_full[s], ph);
-                    if (!(p.dbg & 16)) tc::mbar_wait(&acc_empty[ab], aph ^ 1);
-                    tc::fence_after_thread_sync();
+                if (tc::elect_one()) {
                     const uint64_t descB = descB0 + (uint64_t)(s * stage_stride);
 #pragma unroll
                     for (int sub = 0; sub < SUB; ++sub) {
                         const uint32_t d_tmem = tmem_base + (ab * SUB + sub) * p.BN;
                         const uint64_t descA = descA0 + (uint64_t)(sub * sub_stride);
-#pragma unroll
-                        for (int ks = 0; ks < 8; ++ks) {
-                            if (ks < p.ksteps) {
-                                uint64_t da = descA + offA[ks], db = descB + offB[ks];
-                                if (p.dbg & 8) {
-                                    const int kb = ks >> 2, k4 = ks & 3;
-                                    da = tc::make_smem_desc(tc::smem_u32(sA + (size_t)(sub * p.kblocks + kb) * A_TILE_BYTES) + k4 * 32, 16, 1024);
-                                    db = tc::make_smem_desc(tc::smem_u32(sB + ((size_t)s * p.kblocks + kb) * b_tile_bytes) + k4 * 32, 16, 1024);
-                                    if ((da != descA + offA[ks] || db != descB + offB[ks]) && blockIdx.x == 0 && it < 4)
-                                        printf("desc mismatch it %u sub %d ks %d: %llx vs %llx | %llx vs %llx\n", it, sub, ks,
-                                               (unsigned long long)da, (unsigned long long)(descA + offA[ks]),
-                                               (unsigned long long)db, (unsigned long long)(descB + offB[ks]));
-                                }
-                                if (F16) tc::mma_f16(d_tmem, da, db, idesc, ks > 0 ? 1u : 0u);
-                                else tc::mma_tf32(d_tmem, da, db, idesc, ks > 0 ? 1u : 0u);
-                            }
+                        for (int ks = 0; ks < p.ksteps; ++ks) {
+                            const uint32_t offA = (uint32_t)((ks >> 2) * A_TILE_BYTES + (ks & 3) * 32) >> 4;
+                            const uint32_t offB = (uint32_t)((ks >> 2) * b_tile_bytes + (ks & 3) * 32) >> 4;
+                            if (F16) tc::mma_f16(d_tmem, descA + offA, descB + offB, idesc, ks > 0 ? 1u : 0u);
+                            else tc::mma_tf32(d_tmem, descA + offA, descB + offB, idesc, ks > 0 ? 1u : 0u);
                         }
                     }
                     tc::mma_commit(&b_empty[s]);      // smem stage free once these MMAs have read it
                     tc::mma_commit(&acc_full[ab]);    // accumulators ready for the epilogue
-                    if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1; }
+                    if (tt == tiles_item - 1) tc::mma_commit(a_empty);    // z tile may be overwritten
                 }
-                tc::mma_commit(a_empty);              // z tile may be overwritten
+                __syncwarp();
+                if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1; }
             }
         }
     } else if (warp >= 4) {
@@ -307,11 +296,6 @@ vq_assign_tc_kernel(const __grid_constant__ CUtensorMap mapZ, const __grid_const
                 if (++cs_c == cpt) { cs_c = 0; ++cs_tile; }
             };
             float va[32], vb[32];
-            if (p.dbg & 16) {          // timing experiment: producer + MMA pipeline only
-                __syncwarp();
-                if (lane == 0) tc::mbar_arrive(e_done);
-                continue;
-            }
             if (p.dbg & 2) {
 #pragma unroll
                 for (int j = 0; j < 32; ++j) { va[j] = (float)(j + lane) * 1e-3f; vb[j] = va[j] + 0.5f; }

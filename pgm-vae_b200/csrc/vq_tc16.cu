@@ -20,7 +20,7 @@
 // Exactness.  fp16 products only PROPOSE candidates; fp32 decides.  eps bounds the error of an
 // approximate score (2^-10 |z| max|e| for round-to-nearest fp16 operands).  In ONE pass each
 // row keeps a running maximum m and records every code whose score is >= m - 2 eps at the time
-// it is seen, together with the maximum of its 32-code chunk.  m only grows, so the final
+// it is seen, together with the maximum of its 8-code group.  m only grows, so the final
 // candidate set {k : s~_k >= m_final - 2 eps} is a subset of the recorded codes, and the true
 // arg-min is in it (header of vq_tc.cu).  A row with a single candidate is decided; rows with
 // several are re-scored with exactly the fp32 arithmetic of the CUDA-core kernel (lowest index
@@ -160,54 +160,52 @@ vq_assign_f16_kernel(const __grid_constant__ CUtensorMap mapE, const Vq16P p) {
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        // ===================== TMA producer: code tiles =====================
-        if (lane == 0) {
-            uint32_t s = 0, ph = 0;
-            for (int item = blockIdx.x; item < items; item += gridDim.x) {
-                const int g = item / p.tiles_m;
-                for (int t = 0; t < p.tiles_n; ++t) {
-                    tc::mbar_wait(&b_empty[s], ph ^ 1);
+        // ===================== TMA producer: code tiles (warp-uniform loop, one elected lane issues)
+        uint32_t s = 0, ph = 0;
+        for (int item = blockIdx.x; item < items; item += gridDim.x) {
+            const int g = item / p.tiles_m;
+            for (int t = 0; t < p.tiles_n; ++t) {
+                tc::mbar_wait_parked(&b_empty[s], ph ^ 1);
+                if (tc::elect_one()) {
                     tc::mbar_arrive_expect_tx(&b_full[s], (uint32_t)stage_bytes);
                     for (int kb = 0; kb < p.kblocks; ++kb)
                         tc::tma_load_3d(sB + (size_t)s * stage_bytes + (size_t)kb * B_KB_BYTES, &mapE, &b_full[s],
                                         kb * 64, t * C::BN, g);
-                    if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1; }
                 }
+                __syncwarp();
+                if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1; }
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
-            const uint32_t idesc = tc::make_idesc(0, TM, C::BN, 0, 0);
-            const uint64_t descB0 = tc::make_smem_desc(tc::smem_u32(sB), 16, 1024);
-            const uint32_t stage_stride = (uint32_t)stage_bytes >> 4;
-            uint32_t offB[8];
-#pragma unroll
-            for (int ks = 0; ks < 8; ++ks) offB[ks] = (uint32_t)((ks >> 2) * B_KB_BYTES + (ks & 3) * 32) >> 4;
-            const uint32_t a_sub = (uint32_t)(p.KD >> 1);        // TMEM columns of one sub-tile's z operand
-            uint32_t it = 0, item_n = 0, s = 0, ph = 0;
-            for (int item = blockIdx.x; item < items; item += gridDim.x, ++item_n) {
-                tc::mbar_wait(a_full, item_n & 1);               // z of this row tile sits in TMEM
+        // ===================== MMA issuer (warp-uniform loop, one elected lane issues)
+        const uint32_t idesc = tc::make_idesc(0, TM, C::BN, 0, 0);
+        const uint64_t descB0 = tc::make_smem_desc(tc::smem_u32(sB), 16, 1024);
+        const uint32_t stage_stride = (uint32_t)stage_bytes >> 4;
+        const uint32_t a_sub = (uint32_t)(p.KD >> 1);        // TMEM columns of one sub-tile's z operand
+        uint32_t it = 0, item_n = 0, s = 0, ph = 0;
+        for (int item = blockIdx.x; item < items; item += gridDim.x, ++item_n) {
+            tc::mbar_wait_parked(a_full, item_n & 1);        // z of this row tile sits in TMEM
+            for (int t = 0; t < p.tiles_n; ++t, ++it) {
+                const uint32_t ab = it & 1, aph = (it >> 1) & 1;
+                tc::mbar_wait_parked(&b_full[s], ph);
+                tc::mbar_wait_parked(&acc_empty[ab], aph ^ 1);
                 tc::fence_after_thread_sync();
-                for (int t = 0; t < p.tiles_n; ++t, ++it) {
-                    const uint32_t ab = it & 1, aph = (it >> 1) & 1;
-                    tc::mbar_wait(&b_full[s], ph);
-                    tc::mbar_wait(&acc_empty[ab], aph ^ 1);
-                    tc::fence_after_thread_sync();
+                if (tc::elect_one()) {
                     const uint64_t descB = descB0 + (uint64_t)(s * stage_stride);
 #pragma unroll
                     for (int sub = 0; sub < SUB; ++sub) {
                         const uint32_t d_tmem = tmem_base + A_COLS + (ab * SUB + sub) * C::BN;
                         const uint32_t a_tmem = tmem_base + sub * a_sub;
-#pragma unroll
-                        for (int ks = 0; ks < 8; ++ks)
-                            if (ks < p.ksteps)
-                                tc::mma_f16_ts(d_tmem, a_tmem + ks * 8, descB + offB[ks], idesc, ks > 0 ? 1u : 0u);
+                        for (int ks = 0; ks < p.ksteps; ++ks) {
+                            const uint32_t offB = (uint32_t)((ks >> 2) * B_KB_BYTES + (ks & 3) * 32) >> 4;
+                            tc::mma_f16_ts(d_tmem, a_tmem + ks * 8, descB + offB, idesc, ks > 0 ? 1u : 0u);
+                        }
                     }
                     tc::mma_commit(&b_empty[s]);      // smem stage free once these MMAs have read it
                     tc::mma_commit(&acc_full[ab]);    // scores ready for the epilogue
-                    if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1; }
                 }
+                __syncwarp();
+                if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1; }
             }
         }
     } else if (warp >= 4) {
@@ -276,7 +274,7 @@ vq_assign_f16_kernel(const __grid_constant__ CUtensorMap mapE, const Vq16P p) {
             auto issue = [&](float (&buf)[32]) {
                 const uint32_t git = it + ld_tile, ab = git & 1;
                 if (ld_c == 0) {
-                    tc::mbar_wait(&acc_full[ab], (git >> 1) & 1);
+                    tc::mbar_wait_parked(&acc_full[ab], (git >> 1) & 1);
                     tc::fence_after_thread_sync();
                 }
                 tc::tmem_ld_32x32(acc_addr + ab * SUB * C::BN + ld_c * 32, buf);
@@ -292,30 +290,34 @@ vq_assign_f16_kernel(const __grid_constant__ CUtensorMap mapE, const Vq16P p) {
                 }
             };
             auto consume = [&](const float (&v)[32], int n) {
-                // chunk maximum: 17 instructions for 32 scores
-                const float a0 = tc::max3(v[0], v[1], v[2]), a1 = tc::max3(v[3], v[4], v[5]);
-                const float a2 = tc::max3(v[6], v[7], v[8]), a3 = tc::max3(v[9], v[10], v[11]);
-                const float a4 = tc::max3(v[12], v[13], v[14]), a5 = tc::max3(v[15], v[16], v[17]);
-                const float a6 = tc::max3(v[18], v[19], v[20]), a7 = tc::max3(v[21], v[22], v[23]);
-                const float a8 = tc::max3(v[24], v[25], v[26]), a9 = tc::max3(v[27], v[28], v[29]);
-                const float b0 = tc::max3(a0, a1, a2), b1 = tc::max3(a3, a4, a5), b2 = tc::max3(a6, a7, a8);
-                const float b3 = tc::max3(a9, v[30], v[31]);
-                const float cm = fmaxf(tc::max3(b0, b1, b2), b3);
+                // maxima of the four 8-code groups and of the chunk: 18 instructions for 32 scores
+                float gm[4];
+#pragma unroll
+                for (int qq = 0; qq < 4; ++qq)
+                    gm[qq] = tc::max3(tc::max3(v[8 * qq], v[8 * qq + 1], v[8 * qq + 2]),
+                                      tc::max3(v[8 * qq + 3], v[8 * qq + 4], v[8 * qq + 5]),
+                                      fmaxf(v[8 * qq + 6], v[8 * qq + 7]));
+                const float cm = fmaxf(tc::max3(gm[0], gm[1], gm[2]), gm[3]);
                 if (__any_sync(0xffffffffu, cm >= thr)) {
                     // some row of this warp has a score within the band of its running maximum
                     runmax = fmaxf(runmax, cm);
                     thr = runmax - margin;
-                    uint32_t mask = 0;
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) mask |= (v[j] >= thr) ? (1u << j) : 0u;
-                    const int kbase = n * 32;                    // chunks are consecutive 32-code blocks
-                    while (mask) {
-                        const int j = __ffs(mask) - 1;
-                        mask &= mask - 1;
-                        float2* slot = myring + (cnt & (RING - 1)) * C::TMR;
-                        if (cnt >= RING) evmax = fmaxf(evmax, slot->x);
-                        *slot = make_float2(cm, __int_as_float(kbase + j));
-                        ++cnt;
+                    for (int qq = 0; qq < 4; ++qq) {
+                        if (!__any_sync(0xffffffffu, gm[qq] >= thr)) continue;
+                        uint32_t mask = 0;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            if (v[8 * qq + j] >= thr) mask |= 1u << j;
+                        const int kbase = n * 32 + 8 * qq;       // chunks are consecutive 32-code blocks
+                        while (mask) {
+                            const int j = __ffs(mask) - 1;
+                            mask &= mask - 1;
+                            float2* slot = myring + (cnt & (RING - 1)) * C::TMR;
+                            if (cnt >= RING) evmax = fmaxf(evmax, slot->x);
+                            *slot = make_float2(gm[qq], __int_as_float(kbase + j));   // bound: s_k <= group max
+                            ++cnt;
+                        }
                     }
                 }
             };
@@ -490,7 +492,8 @@ int pg_vq_assign_f16(pgmvae_ctx* ctx, cudaStream_t st, const float* z, int64_t z
     p.ksteps = p.KD / 16;
     p.kblocks = (int)pg_cdiv(p.KD, 64);
     // three 128-row sub-tiles (12 epilogue warps, 64-code tiles) when the z operand fits 128 TMEM columns
-    int sub = 2;
+    // three 128-row sub-tiles (12 epilogue warps, 64-code tiles) when the z operand fits 128 TMEM columns
+    int sub = B >= 3 * TM ? 3 : 2;
     if (const char* ev = getenv("PGMVAE_VQ_SUB")) sub = atoi(ev) == 3 ? 3 : 2;
     if (3 * (p.KD / 2) > A_COLS) sub = 2;
     const int BN = sub == 2 ? Cfg<2>::BN : Cfg<3>::BN;

@@ -1,12 +1,10 @@
 set -x
 mkdir -p gpurun_out
 timeout 600 python -m pytest tests/test_gpu_ops.py -m gpu -x -q -k "vq" > gpurun_out/pytest_vq.log 2>&1; echo "rc=$?" >> gpurun_out/pytest_vq.log
-tail -15 gpurun_out/pytest_vq.log
+tail -4 gpurun_out/pytest_vq.log
 for sub in 2 3; do
   PGMVAE_VQ_SUB=$sub timeout 300 python pgm-vae_b200/tools/vq_microbench.py --n 1048576 --prec f16 --reps 5 > gpurun_out/vqmb_f16_sub$sub.json 2> gpurun_out/vqmb_f16_sub$sub.err
-  cut -c1-400 gpurun_out/vqmb_f16_sub$sub.json; tail -3 gpurun_out/vqmb_f16_sub$sub.err
+  cut -c1-330 gpurun_out/vqmb_f16_sub$sub.json; tail -3 gpurun_out/vqmb_f16_sub$sub.err
 done
-PGMVAE_VQ_SUB=2 timeout 300 python pgm-vae_b200/tools/vq_microbench.py --n 1048576 --prec f16 --reps 5 --fused > gpurun_out/vqmb_f16_fused.json 2>&1
-cut -c1-400 gpurun_out/vqmb_f16_fused.json
 PGMVAE_VQ_SUB=2 timeout 300 python pgm-vae_b200/tools/vq_microbench.py --n 1048576 --prec f16 --reps 5 --clustered > gpurun_out/vqmb_f16_clustered.json 2>&1
-cut -c1-400 gpurun_out/vqmb_f16_clustered.json
+cut -c1-330 gpurun_out/vqmb_f16_clustered.json
