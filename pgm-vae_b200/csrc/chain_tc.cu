@@ -1,0 +1,522 @@
+// Chain kernels: a whole stack of packed per-variable dense layers in ONE launch, the
+// activations of a 128-sample tile never leaving the SM.
+//
+//   forward (training)  fd0..fd4 -> VQ (assignment, straight-through, commitment loss, EMA
+//                       statistics) -> fd5..fd9 -> sigmoid + MSE/MAE + d(loss)/d(pre-activation)
+//                       reference core/model.py:39-55, core/quantizer.py:120-162, run.py:61
+//   encode              fd0..fd4 -> VQ assignment (-> PLL histogram)   core/model.py:48, :58-82
+//   backward            the dgrad chain fd9 -> fd1 (autodiff of core/dense.py:106-110) with the
+//                       commitment gradient injected at the VQ boundary
+//
+// Layout of one CTA (192 threads, persistent over (variable, 128-row tile) items):
+//   warp 0   TMA producer: streams the weight k-blocks of every layer of every item through a
+//            shared-memory ring; weights do not depend on activations, so it runs ahead of the
+//            compute across layers AND items
+//   warp 1   MMA issuer (tcgen05.mma kind::tf32, M = 128): the A operand is read from TENSOR
+//            MEMORY, where the previous layer's epilogue left the activations; B = weights from
+//            the ring; D = a second TMEM region.  Owns the TMEM allocation.
+//   warps 2-5 epilogue, one sample row per thread: tcgen05.ld the pre-activations, bias +
+//            activation (or the VQ / loss / act' step), store the row to HBM for the kernels that
+//            need it later (wgrad, backward), and tcgen05.st it back IN PLACE as the next A operand
+//   Two TMEM regions ping-pong: layer j reads region (j & 1), writes region (~j & 1).
+//
+// What leaves the SM per layer is one write of the activations; nothing is read back except the
+// weights (L2-resident) -- against one read + one write per layer and ~47 launches per step for
+// the layer-by-layer kernels in dense_tc.cu.  Chains are used when the network is narrow
+// enough for TMEM (every padded width <= 256 and both regions within 512 columns), the codebook
+// fits shared memory and D <= 32; otherwise the per-layer kernels run.
+#include <algorithm>
+
+#include "common.cuh"
+#include "ops.cuh"
+#include "tc_common.cuh"
+
+namespace {
+
+constexpr int CH_TM = 128;
+constexpr int CH_RING = 8;              // weight k-block stages: the producer runs ~4 layers ahead of the MMAs
+constexpr int CH_THREADS = 192;
+
+struct ChainMaps { CUtensorMap m[PG_CHAIN_MAX_STAGES]; };
+
+struct ChainP {
+    int mode;                            // PG_CHAIN_*
+    int nst;
+    PgChainStage st[PG_CHAIN_MAX_STAGES];
+    int G, g0, B, V, Vp, D, Dp, K, vq_stage;
+    int tiles_m, tmem_cols, nbias, items_per_cta;
+    uint32_t stage_bytes;
+    // layer-0 operand / targets
+    const float* a0; long long a0_gs; int lda0, a0_cols;    // fwd: yf [B][Vp] (shared); bwd: dpre of the top layer
+    const float* yf; int ldyf;
+    const uint8_t* y8; int ldy8;
+    // VQ
+    const float* E; long long e_gs;
+    float* q; float* stq; long long zq_gs; int ldzq;
+    int32_t* idx; long long idx_gs;
+    float* stat_c; float* stat_w;
+    double* acc;
+    float gscale, cscale;
+    unsigned long long* n1; unsigned long long* n0;
+    const float* z; const float* qv;
+};
+
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+__device__ __forceinline__ void store_chunk(float* dst, const float (&v)[32], int nv) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 4)
+        if (j < nv) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+}
+__device__ __forceinline__ void load_chunk(const float* src, float (&v)[32], int nv) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+        if (j < nv) {
+            const float4 t = *reinterpret_cast<const float4*>(src + j);
+            v[j] = t.x; v[j + 1] = t.y; v[j + 2] = t.z; v[j + 3] = t.w;
+        } else {
+            v[j] = v[j + 1] = v[j + 2] = v[j + 3] = 0.f;
+        }
+    }
+}
+
+// Activations of the tensor-core chains: ex2.approx based (2 ulp); the pre-activations they act on
+// already carry the 2^-11 relative error of the tf32 operands.  The exact-fp32 path (dense_simt.cu)
+// keeps expf.
+__device__ __forceinline__ float ch_selu(float x) {      // branch-free: 32 independent elements interleave
+    const float e = PG_SELU_SCALE_ALPHA * (__expf(fminf(x, 0.f)) - 1.0f);
+    return x < 0.f ? e : PG_SELU_SCALE * x;
+}
+__device__ __forceinline__ float ch_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+
+// Exact fp32 arg-min of one row against the codebook in shared memory ([Kp][4*NV4] floats, Kp a
+// multiple of 4, |e|^2 = +inf for the padding codes).  Four codes in flight (independent fmaf chains),
+// each chain in the sequential order over d of the fp32 kernels: distances are bit-identical to
+// vq_assign_kernel, lowest index on ties.
+template <int NV4>
+__device__ __forceinline__ int vq_row_argmin(const float (&v)[32], float zz, const float* __restrict__ sE,
+                                             const float* __restrict__ sEE, int Kp) {
+    float best = INFINITY;
+    int bi = 0;
+    for (int k0 = 0; k0 < Kp; k0 += 4) {
+        float dot[4] = {0.f, 0.f, 0.f, 0.f};
+        const float* er = sE + k0 * (4 * NV4);
+#pragma unroll
+        for (int d4 = 0; d4 < NV4; ++d4) {
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+                const float4 e4 = *reinterpret_cast<const float4*>(er + kk * (4 * NV4) + d4 * 4);
+                dot[kk] = fmaf(v[d4 * 4 + 0], e4.x, dot[kk]);
+                dot[kk] = fmaf(v[d4 * 4 + 1], e4.y, dot[kk]);
+                dot[kk] = fmaf(v[d4 * 4 + 2], e4.z, dot[kk]);
+                dot[kk] = fmaf(v[d4 * 4 + 3], e4.w, dot[kk]);
+            }
+        }
+        const float4 ee4 = *reinterpret_cast<const float4*>(sEE + k0);
+        const float d0 = (zz - 2.0f * dot[0]) + ee4.x, d1 = (zz - 2.0f * dot[1]) + ee4.y;
+        const float d2 = (zz - 2.0f * dot[2]) + ee4.z, d3 = (zz - 2.0f * dot[3]) + ee4.w;
+        if (d0 < best) { best = d0; bi = k0; }
+        if (d1 < best) { best = d1; bi = k0 + 1; }
+        if (d2 < best) { best = d2; bi = k0 + 2; }
+        if (d3 < best) { best = d3; bi = k0 + 3; }
+    }
+    return bi;
+}
+
+__global__ void __launch_bounds__(CH_THREADS, 2)
+chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ ChainP p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-byte aligned, still a shared-space pointer
+    uint8_t* sB = smem;                                                          // [CH_RING][stage_bytes]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sB + (size_t)CH_RING * p.stage_bytes);
+    uint64_t* b_full = bars;                   // [CH_RING]
+    uint64_t* b_empty = bars + CH_RING;        // [CH_RING]
+    uint64_t* a_ready = bars + 2 * CH_RING;
+    uint64_t* d_full = bars + 2 * CH_RING + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * CH_RING + 2);
+    float* sE = reinterpret_cast<float*>(bars + 2 * CH_RING + 4);                             // [K][Dp]
+    const int Kp = (p.K + 3) & ~3;                                               // codes padded to a multiple of 4
+    float* sEE = sE + (size_t)Kp * p.Dp;                                         // [Kp]
+    uint32_t* sHist = reinterpret_cast<uint32_t*>(sEE + Kp);                     // [2][K]  (count mode)
+    float* sBias = reinterpret_cast<float*>(sHist + 2 * Kp);                    // biases of all stages, this variable
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int items = p.G * p.tiles_m;
+    // consecutive items per CTA: mostly the same variable, so its codebook and biases stay in shared memory
+    const int item_beg = blockIdx.x * p.items_per_cta, item_end = min(items, item_beg + p.items_per_cta);
+
+    if (warp == 0 && lane == 0) {
+        for (int j = 0; j < p.nst; ++j) tc::tma_prefetch_desc(&maps.m[j]);
+        for (int s = 0; s < CH_RING; ++s) {
+            tc::mbar_init(&b_full[s], 1);
+            tc::mbar_init(&b_empty[s], 1);
+        }
+        tc::mbar_init(a_ready, 4);             // one arrival per epilogue warp
+        tc::mbar_init(d_full, 1);
+        tc::fence_barrier_init();
+    }
+    if (warp == 1) {
+        tc::tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+        tc::tmem_relinquish();
+    }
+    tc::fence_before_thread_sync();
+    __syncthreads();
+    tc::fence_after_thread_sync();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer: weight k-blocks of every stage of every item
+        uint32_t s = 0, ph = 0;
+        for (int item = item_beg; item < item_end; ++item) {
+            const int g = item / p.tiles_m;
+            for (int j = 0; j < p.nst; ++j) {
+                const PgChainStage& S = p.st[j];
+                for (int kb = 0; kb < S.kblocks; ++kb) {
+                    tc::mbar_wait(&b_empty[s], ph ^ 1);
+                    if (tc::elect_one()) {
+                        uint8_t* dst = sB + (size_t)s * p.stage_bytes;
+                        tc::mbar_arrive_expect_tx(&b_full[s], S.kb_bytes);
+                        if (S.b_mn) {
+                            for (int pn = 0; pn < (S.N >> 5); ++pn)                  // panels [32 k][32 n]
+                                tc::tma_load_3d(dst + pn * 4096, &maps.m[j], &b_full[s], pn * 32, kb * 32, g);
+                        } else {
+                            tc::tma_load_3d(dst, &maps.m[j], &b_full[s], kb * 32, 0, g);   // [N n][32 k]
+                        }
+                    }
+                    __syncwarp();
+                    if (++s == CH_RING) { s = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer
+        const uint64_t dB_mn = tc::make_smem_desc(tc::smem_u32(sB), 4096, 512, 1);
+        const uint64_t dB_k = tc::make_smem_desc(tc::smem_u32(sB), 16, 1024, 2);
+        const uint32_t stage_stride = p.stage_bytes >> 4;
+        uint32_t s = 0, ph = 0, aph = 0;
+        for (int item = item_beg; item < item_end; ++item) {
+            for (int j = 0; j < p.nst; ++j) {
+                const PgChainStage& S = p.st[j];
+                const uint32_t idesc = tc::make_idesc(2, CH_TM, S.N, 0, S.b_mn);
+                const uint64_t dB0 = S.b_mn ? dB_mn : dB_k;
+                const uint32_t bstep = (S.b_mn ? 1024u : 32u) >> 4;
+                tc::mbar_wait(a_ready, aph);                // the A operand of this stage sits in TMEM
+                aph ^= 1;
+                for (int kb = 0; kb < S.kblocks; ++kb) {
+                    tc::mbar_wait(&b_full[s], ph);
+                    tc::fence_after_thread_sync();
+                    if (tc::elect_one()) {
+                        const uint64_t dB = dB0 + (uint64_t)(s * stage_stride);
+                        const int nk = min(4, S.ksteps - kb * 4);
+                        for (int k4 = 0; k4 < nk; ++k4)
+                            tc::mma_tf32_ts(tmem_base + S.d_col, tmem_base + S.a_col + kb * 32 + k4 * 8,
+                                            dB + (uint64_t)(k4 * bstep), idesc, (kb | k4) ? 1u : 0u);
+                        tc::mma_commit(&b_empty[s]);
+                        if (kb == S.kblocks - 1) tc::mma_commit(d_full);
+                    }
+                    __syncwarp();
+                    if (++s == CH_RING) { s = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else {
+        // ===================== epilogue: one sample row per thread
+        const int q4 = warp & 3;                              // TMEM lane quarter == warp % 4
+        const int r = q4 * 32 + lane;
+        const int et = (warp - 2) * 32 + lane;                // 0..127 among the epilogue threads
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(q4 * 32) << 16);
+        uint32_t dph = 0;
+        int cur_g = -1;
+        double acc_sq = 0.0, acc_ab = 0.0, acc_vq = 0.0;
+        for (int item = item_beg; item < item_end; ++item) {
+            const int g = item / p.tiles_m, mt = item - g * p.tiles_m;
+            const int row = mt * CH_TM + r;
+            const bool valid = row < p.B;
+            const int rowc = valid ? row : 0;
+            // ---- codebook of this variable -> shared memory, |e|^2 in the order every fp32 path uses
+            if (g != cur_g) {
+                epi_bar();                                    // everyone has left the previous variable's tables
+                for (int j = 0; j < p.nst; ++j) {
+                    const PgChainStage& S = p.st[j];
+                    if (S.bias)
+                        for (int i = et; i < S.pout; i += 128) sBias[S.bias_off + i] = S.bias[(long long)g * S.bias_gs + i];
+                }
+                if (p.vq_stage >= 0) {
+                    const float* eg = p.E + (long long)g * p.e_gs;
+                    for (int i = et * 4; i < p.K * p.Dp; i += 128 * 4)
+                        *reinterpret_cast<float4*>(sE + i) = *reinterpret_cast<const float4*>(eg + i);
+                    for (int i = p.K * p.Dp + et; i < Kp * p.Dp; i += 128) sE[i] = 0.f;
+                    epi_bar();
+                    for (int k = et; k < Kp; k += 128) {
+                        float s2 = 0.f;
+                        for (int d = 0; d < p.D; ++d) s2 = fmaf(sE[k * p.Dp + d], sE[k * p.Dp + d], s2);
+                        sEE[k] = k < p.K ? s2 : INFINITY;
+                        if (p.mode == PG_CHAIN_ENCODE && p.n1 && k < p.K) { sHist[k] = 0; sHist[p.K + k] = 0; }
+                    }
+                }
+                epi_bar();
+                cur_g = g;
+            }
+            // ---- operand of the first stage: this thread's row -> TMEM
+            {
+                const float* ar = p.a0 + (long long)g * p.a0_gs + (long long)rowc * p.lda0;
+                const uint32_t a_addr = lane_addr + p.st[0].a_col;
+                for (int c = 0; c < p.a0_cols; c += 8) {
+                    float4 x0 = make_float4(0.f, 0.f, 0.f, 0.f), x1 = x0;
+                    if (valid) {
+                        x0 = *reinterpret_cast<const float4*>(ar + c);
+                        x1 = *reinterpret_cast<const float4*>(ar + c + 4);
+                    }
+                    const uint32_t u[8] = {__float_as_uint(x0.x), __float_as_uint(x0.y), __float_as_uint(x0.z),
+                                           __float_as_uint(x0.w), __float_as_uint(x1.x), __float_as_uint(x1.y),
+                                           __float_as_uint(x1.z), __float_as_uint(x1.w)};
+                    tc::tmem_st_32x8(a_addr + c, u);
+                }
+                tc::tmem_st_wait();
+                tc::fence_before_thread_sync();
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(a_ready);
+            }
+            float sq = 0.f, ab = 0.f, vq = 0.f;
+            for (int j = 0; j < p.nst; ++j) {
+                const PgChainStage& S = p.st[j];
+                // operands that come from HBM are requested before waiting for the MMAs of this stage
+                float hv[32];
+                if (S.kind == PG_CHAIN_EPI_DGRAD)
+                    load_chunk(S.aux + (long long)g * S.aux_gs + (long long)rowc * S.ldaux, hv, min(32, S.pout));
+                else if (S.kind == PG_CHAIN_EPI_SIGMOID_MSE)
+                    load_chunk(p.yf + (long long)rowc * p.ldyf, hv, min(32, S.pout));
+                tc::mbar_wait(d_full, dph);
+                dph ^= 1;
+                tc::fence_after_thread_sync();
+                const bool last = j + 1 == p.nst;
+                const float* bias = sBias + S.bias_off;       // this variable's biases (shared memory)
+                for (int c = 0; c < S.pout; c += 32) {
+                    float v[32];
+                    tc::tmem_ld_32x32(lane_addr + S.d_col + c, v);
+                    tc::tmem_ld_wait(v);
+                    const int nv = min(32, S.pout - c);
+                    float* orow = S.outp ? S.outp + (long long)g * S.out_gs + (long long)rowc * S.ldo + c : nullptr;
+                    if (S.kind == PG_CHAIN_EPI_SELU) {
+#pragma unroll
+                        for (int jj = 0; jj < 32; ++jj)
+                            v[jj] = ch_selu(v[jj] + bias[c + jj]);        // columns >= pout are never consumed
+                        if (valid && orow) store_chunk(orow, v, nv);
+                        if (j == p.vq_stage) {
+#pragma unroll
+                            for (int d = 0; d < 32; ++d)
+                                if (d >= p.Dp) v[d] = 0.f;
+                            // ---- VQ on this row (Dp <= 32: the whole latent sits in v[0..Dp))
+                            float zz = 0.f;
+#pragma unroll
+                            for (int d = 0; d < 32; ++d)
+                                if (d < p.D) zz = fmaf(v[d], v[d], zz);
+                            int bi;
+                            switch (p.Dp >> 2) {
+                                case 2: bi = vq_row_argmin<2>(v, zz, sE, sEE, Kp); break;
+                                case 4: bi = vq_row_argmin<4>(v, zz, sE, sEE, Kp); break;
+                                case 6: bi = vq_row_argmin<6>(v, zz, sE, sEE, Kp); break;
+                                default: bi = vq_row_argmin<8>(v, zz, sE, sEE, Kp); break;
+                            }
+                            const long long io = (long long)g * p.idx_gs + rowc;
+                            if (valid && p.idx) p.idx[io] = bi;
+                            if (p.mode == PG_CHAIN_ENCODE) {
+                                if (valid && p.n1) {
+                                    const int bit = p.y8[(long long)row * p.ldy8 + p.g0 + g] != 0;
+                                    atomicAdd(&sHist[(bit ? 0 : p.K) + bi], 1u);
+                                }
+                            } else {
+                                // q = E[idx]; straight-through st = z + (q - z); commitment / codebook loss
+                                const float* er = sE + bi * p.Dp;
+                                float qv[32];
+#pragma unroll
+                                for (int d = 0; d < 32; ++d) qv[d] = d < p.Dp ? er[d] : 0.f;
+                                const long long zo = (long long)g * p.zq_gs + (long long)rowc * p.ldzq;
+                                if (valid) {
+                                    store_chunk(p.q + zo, qv, p.Dp);
+                                    if (p.stat_w) {
+                                        float* dw = p.stat_w + ((long long)g * p.K + bi) * p.Dp;
+#pragma unroll
+                                        for (int d = 0; d < 32; d += 4)
+                                            if (d < p.Dp) red_add_v4(dw + d, v[d], v[d + 1], v[d + 2], v[d + 3]);
+                                        atomicAdd(p.stat_c + (long long)g * p.K + bi, 1.0f);
+                                    }
+                                }
+#pragma unroll
+                                for (int d = 0; d < 32; ++d) {
+                                    const float diff = qv[d] - v[d];
+                                    if (valid && d < p.D) vq = fmaf(diff, diff, vq);
+                                    v[d] = v[d] + diff;
+                                }
+                                if (valid) store_chunk(p.stq + zo, v, p.Dp);
+                            }
+                        }
+                    } else if (S.kind == PG_CHAIN_EPI_SIGMOID_MSE) {
+                        if (c > 0) load_chunk(p.yf + (long long)rowc * p.ldyf + c, hv, nv);
+                        const int self = p.g0 + g;
+                        const float live = valid ? 1.0f : 0.f;
+#pragma unroll
+                        for (int jj = 0; jj < 32; ++jj) {
+                            const float o = ch_sigmoid(v[jj] + bias[c + jj]);
+                            const bool on = jj < nv && c + jj < p.V && c + jj != self;    // the net's own variable is masked
+                            const float d = on ? o - hv[jj] : 0.f;
+                            sq = fmaf(live * d, d, sq);
+                            ab += live * fabsf(d);
+                            v[jj] = p.gscale * d * o * (1.0f - o);
+                        }
+                        if (valid && orow) store_chunk(orow, v, nv);
+                    } else {   // PG_CHAIN_EPI_DGRAD: dX = (dY W^T [+ commitment gradient]) * act'(h)
+                        if (S.add_commit) {
+                            float zv[32], qv[32];
+                            const long long zo = (long long)g * p.zq_gs + (long long)rowc * p.ldzq + c;
+                            load_chunk(p.z + zo, zv, nv);
+                            load_chunk(p.qv + zo, qv, nv);
+#pragma unroll
+                            for (int jj = 0; jj < 32; ++jj) v[jj] = fmaf(p.cscale, zv[jj] - qv[jj], v[jj]);
+                        }
+                        if (c > 0) load_chunk(S.aux + (long long)g * S.aux_gs + (long long)rowc * S.ldaux + c, hv, nv);
+#pragma unroll
+                        for (int jj = 0; jj < 32; ++jj) v[jj] *= pg_dselu_from_out(hv[jj]);   // hv = 0 beyond nv
+                        if (valid && orow) store_chunk(orow, v, nv);
+                    }
+                    if (!last) tc::tmem_st_32x32(lane_addr + S.d_col + c, v);
+                }
+                if (!last) {
+                    tc::tmem_st_wait();
+                    tc::fence_before_thread_sync();
+                    __syncwarp();
+                    if (lane == 0) tc::mbar_arrive(a_ready);
+                }
+            }
+            acc_sq += (double)sq; acc_ab += (double)ab; acc_vq += (double)vq;
+            // ---- PLL histogram of this item -> global counters
+            if (p.mode == PG_CHAIN_ENCODE && p.n1) {
+                epi_bar();
+                for (int k = et; k < 2 * p.K; k += 128) {
+                    const uint32_t c = sHist[k];
+                    if (c) {
+                        sHist[k] = 0;
+                        unsigned long long* dst = k < p.K ? p.n1 + (long long)g * p.K + k
+                                                          : p.n0 + (long long)g * p.K + (k - p.K);
+                        atomicAdd(dst, (unsigned long long)c);
+                    }
+                }
+                epi_bar();
+            }
+        }
+        if (p.acc && p.mode == PG_CHAIN_FWD) {
+            acc_sq = pg_warp_sum_d(acc_sq); acc_ab = pg_warp_sum_d(acc_ab); acc_vq = pg_warp_sum_d(acc_vq);
+            if (lane == 0) {
+                atomicAdd(p.acc + 0, acc_sq);
+                atomicAdd(p.acc + 1, acc_ab);
+                atomicAdd(p.acc + 2, acc_vq);
+            }
+        }
+    }
+    tc::fence_before_thread_sync();
+    __syncthreads();
+    if (warp == 1) {
+        tc::fence_after_thread_sync();
+        tc::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+    }
+}
+
+}  // namespace
+
+// Builds the launch from the stage table prepared by model.cu (which owns the layer geometry).
+int pg_chain_launch(pgmvae_ctx* ctx, cudaStream_t st, const PgChainArgs& a) {
+    if (a.G <= 0 || a.B <= 0) return PGMVAE_OK;
+    ChainP p{};
+    ChainMaps maps{};
+    p.mode = a.mode; p.nst = a.nst;
+    p.G = a.G; p.g0 = a.g0; p.B = a.B; p.V = a.V; p.Vp = a.Vp; p.D = a.D; p.Dp = a.Dp; p.K = a.K;
+    p.vq_stage = a.vq_stage;
+    if (a.vq_stage < 0) p.K = 0;          // no codebook tables in shared memory
+    p.tiles_m = (int)pg_cdiv(a.B, CH_TM);
+    int regw[2] = {a.a0_cols, 0};
+    uint32_t stage_bytes = 0;
+    double flops = 0.0, bytes = 0.0;
+    for (int j = 0; j < a.nst; ++j) {
+        PgChainStage S = a.st[j];
+        S.N = pg_round_up(S.pout, 32);
+        S.ksteps = S.K / 8;
+        S.kblocks = (int)pg_cdiv(S.K, 32);
+        S.kb_bytes = S.b_mn ? (uint32_t)(S.N / 32) * 4096u : (uint32_t)S.N * 128u;
+        stage_bytes = std::max(stage_bytes, S.kb_bytes);
+        regw[(j + 1) & 1] = std::max(regw[(j + 1) & 1], S.N);
+        regw[j & 1] = std::max(regw[j & 1], S.K);
+        S.bias_off = p.nbias;
+        if (S.bias) p.nbias += S.pout;
+        p.st[j] = S;
+        if (S.b_mn)    // W[K = in][N = out], N contiguous: boxes [32 k][32 n], 32-byte-atom swizzle
+            PG_TRY(tc::make_map(&maps.m[j], S.w, 4, (uint64_t)S.n_valid, (uint64_t)S.k_valid, (uint64_t)a.G,
+                                (uint64_t)S.ldw, (uint64_t)S.w_gs, 32, 32, true));
+        else           // W[N = in][K = out], K contiguous: boxes [N n][32 k]
+            PG_TRY(tc::make_map(&maps.m[j], S.w, 4, (uint64_t)S.k_valid, (uint64_t)S.n_valid, (uint64_t)a.G,
+                                (uint64_t)S.ldw, (uint64_t)S.w_gs, 32, (uint32_t)S.N));
+        flops += 2.0 * a.G * (double)a.B * S.k_valid * S.n_valid;
+        bytes += 4.0 * a.G * ((double)S.k_valid * S.n_valid + (S.outp ? (double)a.B * S.n_valid : 0.0) +
+                              (S.aux ? (double)a.B * S.n_valid : 0.0));
+    }
+    const int w0 = pg_round_up(regw[0], 32), w1 = pg_round_up(regw[1], 32);
+    for (int j = 0; j < a.nst; ++j) {
+        p.st[j].a_col = (j & 1) ? w0 : 0;
+        p.st[j].d_col = (j & 1) ? 0 : w0;
+    }
+    p.tmem_cols = 32;
+    while (p.tmem_cols < w0 + w1) p.tmem_cols <<= 1;
+    p.stage_bytes = stage_bytes;
+    p.a0 = a.a0; p.a0_gs = a.a0_gs; p.lda0 = a.lda0; p.a0_cols = a.a0_cols;
+    p.yf = a.yf; p.ldyf = a.ldyf; p.y8 = a.y8; p.ldy8 = a.ldy8;
+    p.E = a.E; p.e_gs = a.e_gs; p.q = a.q; p.stq = a.stq; p.zq_gs = a.zq_gs; p.ldzq = a.ldzq;
+    p.idx = a.idx; p.idx_gs = a.idx_gs; p.stat_c = a.stat_c; p.stat_w = a.stat_w; p.acc = a.acc;
+    p.gscale = a.gscale; p.cscale = a.cscale; p.n1 = a.n1; p.n0 = a.n0; p.z = a.z; p.qv = a.qv;
+    bytes += 4.0 * (a.a0_gs ? (double)a.G : 1.0) * a.B * a.a0_cols;
+    if (a.vq_stage >= 0) { flops += 2.0 * a.G * (double)a.B * a.D * a.K; bytes += 4.0 * a.G * (double)a.K * a.D; }
+
+    const size_t Kp = (size_t)((a.K + 3) & ~3);
+    const size_t vq_smem = ((a.vq_stage >= 0 ? Kp * a.Dp + 3 * Kp : 0) + p.nbias + 40) * 4;
+    const size_t smem = 1024 + (size_t)CH_RING * stage_bytes + vq_smem + 512;
+    if (smem > ctx->smem_optin || w0 + w1 > 512) {
+        pgmvae_set_error("chain kernel: configuration does not fit (smem %zu, tmem columns %d)", smem, w0 + w1);
+        return PGMVAE_EINVAL;
+    }
+    static size_t configured = 0;
+    if (smem > configured) {
+        PG_CUDA(cudaFuncSetAttribute(chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    const int items = a.G * p.tiles_m;
+    const int per_sm = std::max(1, std::min(512 / p.tmem_cols, (int)(ctx->smem_optin / smem)));
+    int grid = std::min(items, ctx->sm_count * std::min(per_sm, 2));
+    p.items_per_cta = (int)pg_cdiv(items, grid);
+    grid = (int)pg_cdiv(items, p.items_per_cta);
+    PG_KERNEL(ctx, st, a.mode == PG_CHAIN_FWD ? "chain_fwd_tc" : (a.mode == PG_CHAIN_ENCODE ? "chain_encode_tc" : "chain_bwd_tc"),
+              bytes, flops);
+    chain_kernel<<<grid, CH_THREADS, smem, st>>>(maps, p);
+    PG_LAUNCHED(ctx);
+    return PGMVAE_OK;
+}
+
+// Can this network run as chains?  (model.cu asks once at model creation)
+bool pg_chain_supported(const int* pin, const int* pout, int nlayers, int Vp, int Dp, int K, size_t smem_optin) {
+    int reg[2] = {Vp, 0};
+    size_t stage = 0;
+    for (int l = 0; l < nlayers; ++l) {
+        if (pout[l] > 256 || pin[l] > 256) return false;
+        const int N = pg_round_up(pout[l], 32);
+        reg[(l + 1) & 1] = std::max(reg[(l + 1) & 1], N);
+        reg[l & 1] = std::max(reg[l & 1], pin[l]);
+        stage = std::max(stage, (size_t)(N / 32) * 4096);
+        stage = std::max(stage, (size_t)pg_round_up(pin[l], 32) * 128);
+    }
+    if (pg_round_up(reg[0], 32) + pg_round_up(reg[1], 32) > 512) return false;
+    if (Dp > 32) return false;
+    size_t nbias = 0;
+    for (int l = 0; l < nlayers; ++l) nbias += pout[l];
+    const size_t smem = 1024 + CH_RING * stage + ((size_t)(K + 3) * Dp + 3 * (K + 3) + nbias + 40) * 4 + 512;
+    return smem <= smem_optin && smem <= 112 * 1024;
+}

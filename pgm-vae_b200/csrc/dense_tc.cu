@@ -72,7 +72,7 @@ template <int EPI>
 __global__ void __launch_bounds__(128) dense_tc_kernel(const __grid_constant__ CUtensorMap mapA,
                                                        const __grid_constant__ CUtensorMap mapB, const DenseTcP p) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-byte aligned, still a shared-space pointer
     const int b_stage_bytes = p.BN * 128;
     uint8_t* sA = smem;                                           // [stages][16 KB]
     uint8_t* sB = sA + (size_t)p.stages * A_STAGE_BYTES;          // [stages][BN*128]
@@ -191,21 +191,30 @@ __global__ void __launch_bounds__(128) dense_tc_kernel(const __grid_constant__ C
         const int nv = min(32, p.N - nb);                           // valid columns of this chunk
         const long long off = (long long)g * p.c_gs + (long long)row * p.ldc + nb;
         if (EPI == EPI_BIAS_ACT) {
-            const float* bias = p.bias ? p.bias + (long long)g * p.bias_gs + nb : nullptr;
+            float bv[32];
+            if (p.bias) load_row(p.bias + (long long)g * p.bias_gs + nb, bv, nv, p.vecC && !(p.bias_gs & 3));
+            else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) bv[j] = 0.f;
+            }
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-                const float x = v[j] + ((bias && j < nv) ? __ldg(bias + j) : 0.f);
+                const float x = v[j] + bv[j];
                 v[j] = p.act == PGMVAE_ACT_SELU ? pg_selu(x) : (p.act == PGMVAE_ACT_SIGMOID ? pg_sigmoid(x) : x);
             }
             store_row(p.C + off, v, nv, p.vecC);
         } else if (EPI == EPI_SIGMOID_MSE) {
-            const float* bias = p.bias ? p.bias + (long long)g * p.bias_gs + nb : nullptr;
-            float yv[32], o[32];
+            float yv[32], o[32], bv[32];
+            if (p.bias) load_row(p.bias + (long long)g * p.bias_gs + nb, bv, nv, p.vecC && !(p.bias_gs & 3));
+            else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) bv[j] = 0.f;
+            }
             load_row(p.aux + (long long)row * p.ldaux + nb, yv, nv, p.vecC);
             const int self = p.g0 + g;
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-                o[j] = pg_sigmoid(v[j] + ((bias && j < nv) ? __ldg(bias + j) : 0.f));
+                o[j] = pg_sigmoid(v[j] + bv[j]);
                 float dpre = 0.f;
                 if (j < nv && nb + j != self) {
                     const float d = o[j] - yv[j];

@@ -15,6 +15,7 @@
 //     of different variables are independent, so a step walks the variables group by group
 //     and the workspace is sized for one group.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -65,6 +66,7 @@ struct pgmvae_model {
     int units[4] = {0, 0, 0, 0};
     double cost = 0.25, decay = 0.99, epsilon = 1e-5;
     int ema = 1, max_batch = 0, Vg = 0;
+    bool chain_ok = false;   // narrow enough for the TMEM-resident chain kernels (chain_tc.cu)
     Layer L[10];
     size_t n_dense = 0, e_off = 0, n_params = 0;   // floats
     float *params = nullptr, *grads = nullptr, *adam_m = nullptr, *adam_v = nullptr;
@@ -237,6 +239,48 @@ int upload_batch(pgmvae_model* m, const uint8_t* y, int on_device, int B, const 
     return pgmvae_y_to_f32(m->ctx, st, *y_dev, m->V, m->yf, m->Vp, B, m->V);
 }
 
+bool use_chain(const pgmvae_model* m) {
+    return m->chain_ok && getenv("PGMVAE_NO_CHAIN") == nullptr && m->ctx->precision != PGMVAE_PREC_FP32;
+}
+
+// forward stages fd[l0, l1) of variables [g0, g0 + Gn) as chain stages
+void chain_fwd_stages(const pgmvae_model* m, int g0, int l0, int l1, PgChainArgs& a) {
+    const int64_t MB = m->max_batch;
+    for (int l = l0; l < l1; ++l) {
+        const Layer& L = m->L[l];
+        PgChainStage& S = a.st[l - l0];
+        S = PgChainStage{};
+        S.K = L.pin; S.pout = L.pout; S.k_valid = L.in; S.n_valid = L.out; S.b_mn = 1;
+        S.kind = l == 9 ? PG_CHAIN_EPI_SIGMOID_MSE : PG_CHAIN_EPI_SELU;
+        S.w = m->params + L.w_off + (size_t)g0 * L.pin * L.pout; S.w_gs = (int64_t)L.pin * L.pout; S.ldw = L.pout;
+        S.bias = m->params + L.b_off + (size_t)g0 * L.pout; S.bias_gs = L.pout;
+        S.outp = l == 9 ? m->Gd[9] : m->H[l]; S.out_gs = MB * L.pout; S.ldo = L.pout;
+    }
+    a.nst = l1 - l0;
+}
+
+void chain_common(const pgmvae_model* m, int g0, int Gn, int B, PgChainArgs& a) {
+    a.G = Gn; a.g0 = g0; a.B = B; a.V = m->V; a.Vp = m->Vp; a.D = m->D; a.Dp = m->Dp; a.K = m->K;
+    a.yf = m->yf; a.ldyf = m->Vp;
+    a.E = m->E() + (size_t)g0 * m->K * m->Dp; a.e_gs = (int64_t)m->K * m->Dp;
+    a.q = m->q; a.stq = m->st; a.zq_gs = (int64_t)m->max_batch * m->Dp; a.ldzq = m->Dp;
+    a.idx = m->idx; a.idx_gs = B;
+}
+
+// encoder + assignment (+ PLL histogram when n1/n0 are given) in one launch
+int chain_encode(pgmvae_model* m, int g0, int Gn, int B, const uint8_t* y_dev, unsigned long long* n1,
+                 unsigned long long* n0) {
+    PgChainArgs a{};
+    a.mode = PG_CHAIN_ENCODE;
+    chain_fwd_stages(m, g0, 0, 5, a);
+    for (int j = 0; j < 5; ++j) a.st[j].outp = nullptr;        // nothing but the codes leaves the SM
+    chain_common(m, g0, Gn, B, a);
+    a.vq_stage = 4;
+    a.a0 = m->yf; a.a0_gs = 0; a.lda0 = m->Vp; a.a0_cols = m->Vp;
+    a.y8 = y_dev; a.ldy8 = m->V; a.n1 = n1; a.n0 = n0;
+    return pg_chain_launch(m->ctx, m->ctx->stream, a);
+}
+
 // encoder fd0..fd4 + assignment for variables [g0, g0+Gn) of the current batch (in m->yf)
 int encode_group(pgmvae_model* m, int g0, int Gn, int B) {
     pgmvae_ctx* ctx = m->ctx;
@@ -288,6 +332,11 @@ int pgmvae_model_create(pgmvae_ctx* ctx, const int* units4, int nvar, int dim, i
     m->e_off = off;
     off += (size_t)nvar * k * m->Dp;
     m->n_params = off;
+    {
+        int pin[10], pout[10];
+        for (int l = 0; l < 10; ++l) { pin[l] = m->L[l].pin; pout[l] = m->L[l].pout; }
+        m->chain_ok = pg_chain_supported(pin, pout, 10, m->Vp, m->Dp, k, ctx->smem_optin);
+    }
 
     int rc = PGMVAE_OK;
     auto A = [&](void** p, size_t bytes) { if (rc == PGMVAE_OK) rc = dev_alloc(m, p, bytes); };
@@ -471,7 +520,61 @@ int run_step(pgmvae_model* m, const uint8_t* y, int y_on_device, int B, int glob
     const float gscale = (float)(2.0 / n_out);
     const float cscale = (float)(m->cost * 2.0 / n_lat);
 
-    for (int g0 = 0; g0 < V; g0 += m->Vg) {
+    const bool chain = use_chain(m) && out_dev == nullptr;
+    for (int g0 = 0; g0 < V && chain; g0 += m->Vg) {
+        const int Gn = std::min(m->Vg, V - g0);
+        const int64_t MB = m->max_batch;
+        const bool stats = m->ema && !(flags & STEP_NO_EMA);
+        {   // forward chain: fd0..fd4, VQ (+ EMA statistics), fd5..fd9, loss and d(loss)/d(pre-activation)
+            PgChainArgs a{};
+            a.mode = PG_CHAIN_FWD;
+            chain_fwd_stages(m, g0, 0, 10, a);
+            chain_common(m, g0, Gn, B, a);
+            a.vq_stage = 4;
+            a.a0 = m->yf; a.a0_gs = 0; a.lda0 = m->Vp; a.a0_cols = m->Vp;
+            a.stat_c = stats ? m->stat_c + (size_t)g0 * K : nullptr;
+            a.stat_w = stats ? m->stat_w + (size_t)g0 * K * Dp : nullptr;
+            a.acc = m->acc; a.gscale = gscale;
+            PG_TRY(pg_chain_launch(ctx, st, a));
+        }
+        if (flags & STEP_FWD_ONLY) continue;
+        if (!m->ema)    // q_latent_loss gradient wrt the codebook: 2 (q - z) / (V B D)   (core/quantizer.py:51)
+            PG_TRY(pgmvae_vq_codebook_grad(ctx, st, m->H[4], m->q, MB * Dp, Dp, m->idx, B, m->dE() + (size_t)g0 * K * Dp,
+                                           (int64_t)K * Dp, Dp, (float)(2.0 / n_lat), Gn, B, D, K));
+        {   // backward chain: dgrad of fd9 .. fd1
+            PgChainArgs a{};
+            a.mode = PG_CHAIN_BWD;
+            a.nst = 9;
+            for (int j = 0; j < 9; ++j) {
+                const int l = 9 - j;
+                const Layer& L = m->L[l];
+                const Layer& P = m->L[l - 1];
+                PgChainStage& S = a.st[j];
+                S = PgChainStage{};
+                S.K = L.pout; S.pout = L.pin; S.k_valid = L.out; S.n_valid = L.in; S.b_mn = 0;
+                S.kind = PG_CHAIN_EPI_DGRAD; S.add_commit = l == 5;
+                S.w = m->params + L.w_off + (size_t)g0 * L.pin * L.pout; S.w_gs = (int64_t)L.pin * L.pout; S.ldw = L.pout;
+                S.outp = m->Gd[l - 1]; S.out_gs = MB * P.pout; S.ldo = P.pout;
+                S.aux = m->H[l - 1]; S.aux_gs = MB * P.pout; S.ldaux = P.pout;
+            }
+            chain_common(m, g0, Gn, B, a);
+            a.vq_stage = -1;
+            a.a0 = m->Gd[9]; a.a0_gs = MB * m->L[9].pout; a.lda0 = m->L[9].pout; a.a0_cols = m->L[9].pout;
+            a.z = m->H[4]; a.qv = m->q; a.cscale = cscale;
+            PG_TRY(pg_chain_launch(ctx, st, a));
+        }
+        for (int l = 9; l >= 0; --l) {
+            const Layer& L = m->L[l];
+            const float* x = l == 0 ? m->yf : (l == 5 ? m->st : m->H[l - 1]);
+            const int ldx = l == 0 ? m->Vp : (l == 5 ? Dp : m->L[l - 1].pout);
+            const int64_t x_gs = l == 0 ? 0 : MB * ldx;
+            PG_TRY(pgmvae_dense_wgrad(ctx, st, x, x_gs, ldx, m->Gd[l], MB * L.pout, L.pout,
+                                      m->grads + L.w_off + (size_t)g0 * L.pin * L.pout, (int64_t)L.pin * L.pout, L.pout,
+                                      m->grads + L.b_off + (size_t)g0 * L.pout, L.pout, Gn, B, L.in, L.out,
+                                      l == 0 ? g0 : -1));
+        }
+    }
+    for (int g0 = 0; g0 < V && !chain; g0 += m->Vg) {
         const int Gn = std::min(m->Vg, V - g0);
         PG_TRY(encode_group(m, g0, Gn, B));
         // m->idx rows [0, Gn) now hold this group's codes
@@ -584,7 +687,8 @@ int pgmvae_model_encode(pgmvae_model* m, const uint8_t* y, int y_on_device, int 
     PG_TRY(upload_batch(m, y, y_on_device, B, &y_dev));
     for (int g0 = 0; g0 < m->V; g0 += m->Vg) {
         const int Gn = std::min(m->Vg, m->V - g0);
-        PG_TRY(encode_group(m, g0, Gn, B));
+        if (use_chain(m)) PG_TRY(chain_encode(m, g0, Gn, B, y_dev, nullptr, nullptr));
+        else PG_TRY(encode_group(m, g0, Gn, B));
         PG_CUDA(cudaMemcpyAsync(idx_dev + (size_t)g0 * B, m->idx, (size_t)Gn * B * 4, cudaMemcpyDeviceToDevice,
                                 m->ctx->stream));
     }
@@ -606,6 +710,10 @@ int pgmvae_model_count(pgmvae_model* m, const uint8_t* y, int y_on_device, int64
         PG_TRY(upload_batch(m, y + (size_t)s * m->V, y_on_device, B, &y_dev));
         for (int g0 = 0; g0 < m->V; g0 += m->Vg) {
             const int Gn = std::min(m->Vg, m->V - g0);
+            if (use_chain(m)) {      // encoder + assignment + histogram in one launch
+                PG_TRY(chain_encode(m, g0, Gn, B, y_dev, m->n1 + (size_t)g0 * m->K, m->n0 + (size_t)g0 * m->K));
+                continue;
+            }
             PG_TRY(encode_group(m, g0, Gn, B));
             PG_TRY(pgmvae_pll_count(ctx, st, m->idx, B, y_dev, m->V, g0, m->n1 + (size_t)g0 * m->K,
                                     m->n0 + (size_t)g0 * m->K, Gn, B, m->K));

@@ -47,3 +47,42 @@ int pg_dense_dgrad_tc(pgmvae_ctx* ctx, cudaStream_t st, const float* dy, int64_t
 int pg_dense_wgrad_tc(pgmvae_ctx* ctx, cudaStream_t st, const float* x, int64_t x_gs, int ldx, const float* dy,
                       int64_t dy_gs, int lddy, float* dw, int64_t dw_gs, int lddw, float* db, int64_t db_gs, int G, int B,
                       int in, int out_dim, int zero_row_base);
+
+// chain kernels (chain_tc.cu): a stack of dense layers per launch, activations resident in TMEM
+#define PG_CHAIN_MAX_STAGES 10
+enum { PG_CHAIN_FWD = 0, PG_CHAIN_ENCODE = 1, PG_CHAIN_BWD = 2 };
+enum { PG_CHAIN_EPI_SELU = 0, PG_CHAIN_EPI_SIGMOID_MSE = 1, PG_CHAIN_EPI_DGRAD = 2 };
+struct PgChainStage {
+    // filled by the caller
+    int K;                 // padded contraction width = columns of the A operand in TMEM (multiple of 8)
+    int pout;              // padded output width (multiple of 8)
+    int k_valid, n_valid;  // logical extents of the weight matrix along K and N (TMA zero-fills the rest)
+    int b_mn;              // 1: W is [K][N] with N contiguous (forward); 0: W is [N][K] with K contiguous (dgrad)
+    int kind;              // PG_CHAIN_EPI_*
+    int add_commit;        // dgrad at the VQ boundary: add cscale * (z - q) before act'
+    const float* w; long long w_gs; int ldw;
+    const float* bias; long long bias_gs;
+    float* outp; long long out_gs; int ldo;              // row written to HBM (activation / gradient), may be null
+    const float* aux; long long aux_gs; int ldaux;       // dgrad: activation of the layer below (for act')
+    // filled by pg_chain_launch
+    int N, ksteps, kblocks, a_col, d_col, bias_off;
+    unsigned kb_bytes;
+};
+struct PgChainArgs {
+    int mode, nst;
+    PgChainStage st[PG_CHAIN_MAX_STAGES];
+    int G, g0, B, V, Vp, D, Dp, K, vq_stage;            // vq_stage < 0: no VQ in this chain
+    const float* a0; long long a0_gs; int lda0, a0_cols; // first operand: rows of width a0_cols (multiple of 8)
+    const float* yf; int ldyf;                           // targets of the MSE stage
+    const uint8_t* y8; int ldy8;                         // encode: raw data for the PLL histogram
+    const float* E; long long e_gs;                      // codebook [G][K][Dp]
+    float* q; float* stq; long long zq_gs; int ldzq;
+    int32_t* idx; long long idx_gs;
+    float* stat_c; float* stat_w;                        // fused EMA statistics [G][K], [G][K][Dp] (nullable)
+    double* acc;                                         // [0] sum sq err, [1] sum abs err, [2] sum (q - z)^2
+    float gscale, cscale;
+    unsigned long long* n1; unsigned long long* n0;      // encode: [G][K] histograms (nullable)
+    const float* z; const float* qv;                     // backward: latent and quantised latent
+};
+int pg_chain_launch(pgmvae_ctx* ctx, cudaStream_t st, const PgChainArgs& a);
+bool pg_chain_supported(const int* pin, const int* pout, int nlayers, int Vp, int Dp, int K, size_t smem_optin);

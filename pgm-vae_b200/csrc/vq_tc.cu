@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(128 + EPI_THREADS, 1)
 vq_assign_tc_kernel(const __grid_constant__ CUtensorMap mapZ, const __grid_constant__ CUtensorMap mapE,
                     const VqTcParams p) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-byte aligned, still a shared-space pointer
     constexpr int KB_ELEMS = F16 ? 64 : 32;           // elements per 128-byte k-block
     const int b_tile_bytes = p.BN * KB_BYTES;
     uint8_t* sA = smem;                                               // [SUB][kblocks][16 KB]

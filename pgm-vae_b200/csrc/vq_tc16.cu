@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(Cfg<SUB>::THREADS, 1)
 vq_assign_f16_kernel(const __grid_constant__ CUtensorMap mapE, const Vq16P p) {
     using C = Cfg<SUB>;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-byte aligned, still a shared-space pointer
     constexpr int B_KB_BYTES = C::BN * KB_BYTES;                       // one k-block of one code tile
     const int stage_bytes = p.kblocks * B_KB_BYTES;
     uint8_t* sB = smem;                                                // [stages][kblocks][BN * 128]
@@ -165,7 +165,7 @@ vq_assign_f16_kernel(const __grid_constant__ CUtensorMap mapE, const Vq16P p) {
         for (int item = blockIdx.x; item < items; item += gridDim.x) {
             const int g = item / p.tiles_m;
             for (int t = 0; t < p.tiles_n; ++t) {
-                tc::mbar_wait_parked(&b_empty[s], ph ^ 1);
+                tc::mbar_wait(&b_empty[s], ph ^ 1);
                 if (tc::elect_one()) {
                     tc::mbar_arrive_expect_tx(&b_full[s], (uint32_t)stage_bytes);
                     for (int kb = 0; kb < p.kblocks; ++kb)
@@ -184,11 +184,11 @@ vq_assign_f16_kernel(const __grid_constant__ CUtensorMap mapE, const Vq16P p) {
         const uint32_t a_sub = (uint32_t)(p.KD >> 1);        // TMEM columns of one sub-tile's z operand
         uint32_t it = 0, item_n = 0, s = 0, ph = 0;
         for (int item = blockIdx.x; item < items; item += gridDim.x, ++item_n) {
-            tc::mbar_wait_parked(a_full, item_n & 1);        // z of this row tile sits in TMEM
+            tc::mbar_wait(a_full, item_n & 1);               // z of this row tile sits in TMEM
             for (int t = 0; t < p.tiles_n; ++t, ++it) {
                 const uint32_t ab = it & 1, aph = (it >> 1) & 1;
-                tc::mbar_wait_parked(&b_full[s], ph);
-                tc::mbar_wait_parked(&acc_empty[ab], aph ^ 1);
+                tc::mbar_wait(&b_full[s], ph);
+                tc::mbar_wait(&acc_empty[ab], aph ^ 1);
                 tc::fence_after_thread_sync();
                 if (tc::elect_one()) {
                     const uint64_t descB = descB0 + (uint64_t)(s * stage_stride);
@@ -274,7 +274,7 @@ vq_assign_f16_kernel(const __grid_constant__ CUtensorMap mapE, const Vq16P p) {
             auto issue = [&](float (&buf)[32]) {
                 const uint32_t git = it + ld_tile, ab = git & 1;
                 if (ld_c == 0) {
-                    tc::mbar_wait_parked(&acc_full[ab], (git >> 1) & 1);
+                    tc::mbar_wait(&acc_full[ab], (git >> 1) & 1);
                     tc::fence_after_thread_sync();
                 }
                 tc::tmem_ld_32x32(acc_addr + ab * SUB * C::BN + ld_c * 32, buf);
