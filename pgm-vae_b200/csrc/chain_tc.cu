@@ -25,6 +25,8 @@
 // the layer-by-layer kernels in dense_tc.cu.  Chains are used when the network is narrow
 // enough for TMEM (every padded width <= 256 and both regions within 512 columns), the codebook
 // fits shared memory and D <= 32; otherwise the per-layer kernels run.
+#include <stdlib.h>
+
 #include <algorithm>
 
 #include "common.cuh"
@@ -85,12 +87,17 @@ __device__ __forceinline__ void load_chunk(const float* src, float (&v)[32], int
 
 // Activations of the tensor-core chains: ex2.approx based (2 ulp); the pre-activations they act on
 // already carry the 2^-11 relative error of the tf32 operands.  The exact-fp32 path (dense_simt.cu)
-// keeps expf.
+// keeps expf, and so does the EXACT instantiation (PGMVAE_CHAIN_EXACT=1), which reproduces the
+// layer-by-layer tensor-core kernels bit for bit up to summation order.
+template <bool EXACT>
 __device__ __forceinline__ float ch_selu(float x) {      // branch-free: 32 independent elements interleave
-    const float e = PG_SELU_SCALE_ALPHA * (__expf(fminf(x, 0.f)) - 1.0f);
+    const float e = PG_SELU_SCALE_ALPHA * ((EXACT ? expf(fminf(x, 0.f)) : __expf(fminf(x, 0.f))) - 1.0f);
     return x < 0.f ? e : PG_SELU_SCALE * x;
 }
-__device__ __forceinline__ float ch_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+template <bool EXACT>
+__device__ __forceinline__ float ch_sigmoid(float x) {
+    return EXACT ? 1.0f / (1.0f + expf(-x)) : __fdividef(1.0f, 1.0f + __expf(-x));
+}
 
 // Exact fp32 arg-min of one row against the codebook in shared memory ([Kp][4*NV4] floats, Kp a
 // multiple of 4, |e|^2 = +inf for the padding codes).  Four codes in flight (independent fmaf chains),
@@ -126,6 +133,7 @@ __device__ __forceinline__ int vq_row_argmin(const float (&v)[32], float zz, con
     return bi;
 }
 
+template <bool EXACT>
 __global__ void __launch_bounds__(CH_THREADS, 2)
 chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ ChainP p) {
     extern __shared__ uint8_t smem_raw[];
@@ -303,7 +311,7 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ Cha
                     if (S.kind == PG_CHAIN_EPI_SELU) {
 #pragma unroll
                         for (int jj = 0; jj < 32; ++jj)
-                            v[jj] = ch_selu(v[jj] + bias[c + jj]);        // columns >= pout are never consumed
+                            v[jj] = ch_selu<EXACT>(v[jj] + bias[c + jj]);        // columns >= pout are never consumed
                         if (valid && orow) store_chunk(orow, v, nv);
                         if (j == p.vq_stage) {
 #pragma unroll
@@ -360,7 +368,7 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ Cha
                         const float live = valid ? 1.0f : 0.f;
 #pragma unroll
                         for (int jj = 0; jj < 32; ++jj) {
-                            const float o = ch_sigmoid(v[jj] + bias[c + jj]);
+                            const float o = ch_sigmoid<EXACT>(v[jj] + bias[c + jj]);
                             const bool on = jj < nv && c + jj < p.V && c + jj != self;    // the net's own variable is masked
                             const float d = on ? o - hv[jj] : 0.f;
                             sq = fmaf(live * d, d, sq);
@@ -484,10 +492,12 @@ int pg_chain_launch(pgmvae_ctx* ctx, cudaStream_t st, const PgChainArgs& a) {
         pgmvae_set_error("chain kernel: configuration does not fit (smem %zu, tmem columns %d)", smem, w0 + w1);
         return PGMVAE_EINVAL;
     }
-    static size_t configured = 0;
-    if (smem > configured) {
-        PG_CUDA(cudaFuncSetAttribute(chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
+    const bool exact = getenv("PGMVAE_CHAIN_EXACT") != nullptr;
+    static size_t configured[2] = {0, 0};
+    if (smem > configured[exact]) {
+        if (exact) PG_CUDA(cudaFuncSetAttribute(chain_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        else PG_CUDA(cudaFuncSetAttribute(chain_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured[exact] = smem;
     }
     const int items = a.G * p.tiles_m;
     const int per_sm = std::max(1, std::min(512 / p.tmem_cols, (int)(ctx->smem_optin / smem)));
@@ -496,7 +506,8 @@ int pg_chain_launch(pgmvae_ctx* ctx, cudaStream_t st, const PgChainArgs& a) {
     grid = (int)pg_cdiv(items, p.items_per_cta);
     PG_KERNEL(ctx, st, a.mode == PG_CHAIN_FWD ? "chain_fwd_tc" : (a.mode == PG_CHAIN_ENCODE ? "chain_encode_tc" : "chain_bwd_tc"),
               bytes, flops);
-    chain_kernel<<<grid, CH_THREADS, smem, st>>>(maps, p);
+    if (exact) chain_kernel<true><<<grid, CH_THREADS, smem, st>>>(maps, p);
+    else chain_kernel<false><<<grid, CH_THREADS, smem, st>>>(maps, p);
     PG_LAUNCHED(ctx);
     return PGMVAE_OK;
 }

@@ -42,6 +42,7 @@ struct DenseTcP {
     float* C2; double* acc; float gscale; int g0;
     const float* z; const float* q; long long zq_gs; int ldzq; float cscale;
     int zero_row_base;
+    float* db; long long db_gs;      // wgrad: bias gradient (column sums of dY) from a ones-row MMA
 };
 
 // one thread moves (up to) 32 consecutive floats of its row; 128-bit accesses when the row is aligned
@@ -76,7 +77,10 @@ __global__ void __launch_bounds__(128) dense_tc_kernel(const __grid_constant__ C
     const int b_stage_bytes = p.BN * 128;
     uint8_t* sA = smem;                                           // [stages][16 KB]
     uint8_t* sB = sA + (size_t)p.stages * A_STAGE_BYTES;          // [stages][BN*128]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sB + (size_t)p.stages * b_stage_bytes);
+    // wgrad: constant A tile whose row 0 is all ones (K-major, one 128-byte row): a second MMA per k-step
+    // then leaves the column sums of dY (the bias gradient) in row 0 of a second accumulator
+    uint8_t* sOnes = sB + (size_t)p.stages * b_stage_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sOnes + (EPI == EPI_WGRAD ? A_STAGE_BYTES : 0));
     uint64_t* full = bars;                       // [MAX_STAGES]
     uint64_t* empty = bars + MAX_STAGES;         // [MAX_STAGES]
     uint64_t* acc_full = bars + 2 * MAX_STAGES;
@@ -99,6 +103,12 @@ __global__ void __launch_bounds__(128) dense_tc_kernel(const __grid_constant__ C
         }
         tc::mbar_init(acc_full, 1);
         tc::fence_barrier_init();
+    }
+    if (EPI == EPI_WGRAD && p.db) {
+        float4* o4 = reinterpret_cast<float4*>(sOnes);
+        for (int i = threadIdx.x; i < A_STAGE_BYTES / 16; i += 128)
+            o4[i] = i < 8 ? make_float4(1.f, 1.f, 1.f, 1.f) : make_float4(0.f, 0.f, 0.f, 0.f);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // visible to the tensor core
     }
     if (warp == 2) {
         tc::tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
@@ -159,6 +169,14 @@ __global__ void __launch_bounds__(128) dense_tc_kernel(const __grid_constant__ C
                     for (int k4 = 0; k4 < 4; ++k4)
                         tc::mma_tf32(tmem_base, dA + (uint64_t)(k4 * a_step), dB + (uint64_t)(k4 * b_step), idesc,
                                      (kb > kb_beg || k4 > 0) ? 1u : 0u);
+                    if (EPI == EPI_WGRAD && p.db && blockIdx.y == 0) {
+                        const uint32_t idesc1 = tc::make_idesc(2, TM, p.BN, 0, p.b_mn);
+                        const uint64_t dOnes = tc::make_smem_desc(tc::smem_u32(sOnes), 16, 1024, 2);
+#pragma unroll
+                        for (int k4 = 0; k4 < 4; ++k4)
+                            tc::mma_tf32(tmem_base + p.BN, dOnes + (uint64_t)(k4 * 2), dB + (uint64_t)(k4 * b_step), idesc1,
+                                         (kb > kb_beg || k4 > 0) ? 1u : 0u);
+                    }
                     tc::mma_commit(&empty[s]);
                     if (kb == kb_end - 1) tc::mma_commit(acc_full);
                 }
@@ -253,6 +271,21 @@ __global__ void __launch_bounds__(128) dense_tc_kernel(const __grid_constant__ C
                 if (j < nv) atomicAdd(dst + j, v[j]);
         }
     }
+    if (EPI == EPI_WGRAD && p.db && nkb > 0 && blockIdx.y == 0 && warp == 0) {      // lane 0 owns TMEM lane 0
+        // row 0 of the second accumulator: sum_b dY[b, n0 .. n0 + BN)
+        for (int c = 0; c < p.BN && n0 + c < p.N; c += 32) {
+            float v[32];
+            tc::tmem_ld_32x32(tmem_base + p.BN + c, v);
+            tc::tmem_ld_wait(v);
+            float* dst = p.db + (long long)g * p.db_gs + n0 + c;
+            const int nv = min(32, p.N - (n0 + c));
+            if (lane == 0) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if (j < nv) atomicAdd(dst + j, v[j]);
+            }
+        }
+    }
     if (EPI == EPI_SIGMOID_MSE) {
         const double dsq = pg_warp_sum_d((double)sq), dab = pg_warp_sum_d((double)ab);
         if (lane == 0) { red[0][warp] = dsq; red[1][warp] = dab; }
@@ -269,37 +302,6 @@ __global__ void __launch_bounds__(128) dense_tc_kernel(const __grid_constant__ C
     }
 }
 
-// column sums of dy: db[g][n] += sum_b dy[g][b][n]   (bias gradient).  One warp reads whole 128-byte row
-// segments; four rows in flight per warp hide the load latency.
-__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ dy, long long dy_gs, int lddy,
-                                                     float* __restrict__ db, long long db_gs, int B, int N,
-                                                     int rows_per_cta) {
-    __shared__ float part[8][33];
-    const int g = blockIdx.z;
-    const int n = blockIdx.x * 32 + (threadIdx.x & 31);
-    const int r0 = blockIdx.y * rows_per_cta, r1 = min(B, r0 + rows_per_cta);
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-    if (n < N) {
-        const float* base = dy + (long long)g * dy_gs + n;
-        int b = r0 + (threadIdx.x >> 5);
-        for (; b + 24 < r1; b += 32) {
-            s0 += base[(long long)b * lddy];
-            s1 += base[(long long)(b + 8) * lddy];
-            s2 += base[(long long)(b + 16) * lddy];
-            s3 += base[(long long)(b + 24) * lddy];
-        }
-        for (; b < r1; b += 8) s0 += base[(long long)b * lddy];
-    }
-    part[threadIdx.x >> 5][threadIdx.x & 31] = (s0 + s1) + (s2 + s3);
-    __syncthreads();
-    if (threadIdx.x < 32 && n < N) {
-        float t = 0.f;
-#pragma unroll
-        for (int w = 0; w < 8; ++w) t += part[w][threadIdx.x];
-        atomicAdd(db + (long long)g * db_gs + n, t);
-    }
-}
-
 inline bool tma_ok(const float* p, int64_t gs, int ld) { return !((uintptr_t)p & 15) && ld % 4 == 0 && gs % 4 == 0; }
 
 int pick_bn(int N) {
@@ -311,11 +313,11 @@ template <int EPI>
 int launch_tc(pgmvae_ctx* ctx, cudaStream_t st, DenseTcP& p, const CUtensorMap& mapA, const CUtensorMap& mapB, int G,
               const char* name, double bytes) {
     p.tmem_cols = 32;
-    while (p.tmem_cols < p.BN) p.tmem_cols <<= 1;
+    while (p.tmem_cols < (EPI == EPI_WGRAD ? 2 : 1) * p.BN) p.tmem_cols <<= 1;
     const size_t stage = (size_t)A_STAGE_BYTES + (size_t)p.BN * 128;
     int kb_cta = p.kb_per_split < p.kblocks ? p.kb_per_split : p.kblocks;
     p.stages = kb_cta < 3 ? (kb_cta < 1 ? 1 : kb_cta) : 3;
-    const size_t smem = 1024 + p.stages * stage + 128;
+    const size_t smem = 1024 + p.stages * stage + (EPI == EPI_WGRAD ? A_STAGE_BYTES : 0) + 128;
     static size_t configured = 0;
     if (smem > configured) {
         PG_CUDA(cudaFuncSetAttribute(dense_tc_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -410,6 +412,7 @@ int pg_dense_wgrad_tc(pgmvae_ctx* ctx, cudaStream_t st, const float* x, int64_t 
     p.kblocks = (int)pg_cdiv(B, KBLK);
     p.a_mn = 1; p.b_mn = 1;
     p.C = dw; p.c_gs = dw_gs; p.ldc = lddw; p.zero_row_base = zero_row_base;
+    p.db = db; p.db_gs = db_gs;
     p.a_shared = x_gs == 0;
     // split the batch so that ~3 CTAs per SM are in flight, at least 8 k-blocks (256 samples) per CTA
     const int64_t tiles = pg_cdiv(out_dim, p.BN) * pg_cdiv(in, TM) * (int64_t)G;
@@ -426,13 +429,7 @@ int pg_dense_wgrad_tc(pgmvae_ctx* ctx, cudaStream_t st, const float* x, int64_t 
     PG_TRY(tc::make_map(&mB, dy, 4, (uint64_t)out_dim, (uint64_t)B, (uint64_t)G, (uint64_t)lddy, (uint64_t)dy_gs, 32, 32, true));
     const double xg = x_gs == 0 ? 1.0 : (double)G;
     PG_TRY(launch_tc<EPI_WGRAD>(ctx, st, p, mA, mB, G, "dense_wgrad_tc",
-                                4.0 * (xg * B * in + (double)G * B * out_dim + (double)G * in * out_dim)));
-    if (db) {
-        int rows = 512;
-        dim3 grid((unsigned)pg_cdiv(out_dim, 32), (unsigned)pg_cdiv(B, rows), (unsigned)G);
-        PG_KERNEL(ctx, st, "dense_bias_grad", 4.0 * ((double)G * B * out_dim + (double)G * out_dim), (double)G * B * out_dim);
-        colsum_kernel<<<grid, 256, 0, st>>>(dy, dy_gs, lddy, db, db_gs, B, out_dim, rows);
-        PG_LAUNCHED(ctx);
-    }
+                                4.0 * (xg * B * in + (double)G * B * out_dim + (double)G * in * out_dim +
+                                       (db ? (double)G * out_dim : 0.0))));
     return PGMVAE_OK;
 }
