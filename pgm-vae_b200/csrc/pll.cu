@@ -8,46 +8,55 @@
 
 namespace {
 
-constexpr int PLL_ROWS = 256;   // rows per tile == threads per CTA
+constexpr int PLL_THREADS = 512;
+constexpr int PLL_TILE = 512;    // rows staged per step
 
-// One CTA owns a tile of VT variables and a contiguous range of rows; its histogram
-// [VT][K][2] lives in shared memory and is flushed once.  y is read through a
-// coalesced [PLL_ROWS][VT] byte tile, idx along its contiguous sample axis.
-__global__ void __launch_bounds__(PLL_ROWS) pll_count_kernel(
+// One CTA owns a tile of VT variables and a contiguous range of at most 32768 rows.  Its histogram
+// lives in shared memory as ONE 32-bit word per (variable, code): n0 in the low half, n1 in the high
+// half, so a sample is a single shared-memory atomic (+1 or +65536) and 32 variables x 512 codes fit
+// 64 KB (three CTAs per SM).  idx is read along its contiguous sample axis (128 bytes per warp
+// request, four requests in flight per thread); y goes through a [PLL_TILE][VT] byte tile.
+__global__ void __launch_bounds__(PLL_THREADS) pll_count_kernel(
     const int32_t* __restrict__ idx, long long idx_gs, const uint8_t* __restrict__ y, int ldy, int g0,
     unsigned long long* __restrict__ n1, unsigned long long* __restrict__ n0, int G, int B, int K, int VT,
     int rows_per_cta) {
-    extern __shared__ __align__(16) unsigned int hist[];              // [VT][K][2]
-    unsigned char* ytile = reinterpret_cast<unsigned char*>(hist + (size_t)VT * K * 2);  // [PLL_ROWS][VT]
-    const int t = threadIdx.x;
+    extern __shared__ __align__(16) unsigned int hist[];              // [VT][K] packed (n1 << 16 | n0)
+    unsigned char* ytile = reinterpret_cast<unsigned char*>(hist + (size_t)VT * K);    // [PLL_TILE][VT]
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const int gv0 = blockIdx.y * VT;
     const int nv = min(VT, G - gv0);
     const int r0 = blockIdx.x * rows_per_cta, r1 = min(B, r0 + rows_per_cta);
-    for (int i = t; i < VT * K * 2; i += PLL_ROWS) hist[i] = 0u;
+    for (int i = t; i < VT * K; i += PLL_THREADS) hist[i] = 0u;
     __syncthreads();
-    for (int rb = r0; rb < r1; rb += PLL_ROWS) {
-        const int nr = min(PLL_ROWS, r1 - rb);
-        for (int i = t; i < nr * nv; i += PLL_ROWS) {
+    for (int rb = r0; rb < r1; rb += PLL_TILE) {
+        const int nr = min(PLL_TILE, r1 - rb);
+        for (int i = t; i < nr * nv; i += PLL_THREADS) {
             const int row = i / nv, c = i - row * nv;
             ytile[row * VT + c] = y[(long long)(rb + row) * ldy + g0 + gv0 + c];
         }
         __syncthreads();
-        if (t < nr) {
-            for (int c = 0; c < nv; ++c) {
-                const int k = idx[(long long)(gv0 + c) * idx_gs + rb + t];
-                const unsigned int one = ytile[t * VT + c] != 0 ? 1u : 0u;
-                atomicAdd(&hist[((size_t)c * K + k) * 2 + one], 1u);
+        for (int c = warp; c < nv; c += PLL_THREADS / 32) {           // one variable per warp at a time
+            const int32_t* ic = idx + (long long)(gv0 + c) * idx_gs + rb;
+            unsigned int* hc = hist + (size_t)c * K;
+            int rr = lane;
+            for (; rr + 96 < nr; rr += 128) {                          // four independent loads in flight
+                const int k0 = ic[rr], k1 = ic[rr + 32], k2 = ic[rr + 64], k3 = ic[rr + 96];
+                atomicAdd(&hc[k0], ytile[rr * VT + c] ? 65536u : 1u);
+                atomicAdd(&hc[k1], ytile[(rr + 32) * VT + c] ? 65536u : 1u);
+                atomicAdd(&hc[k2], ytile[(rr + 64) * VT + c] ? 65536u : 1u);
+                atomicAdd(&hc[k3], ytile[(rr + 96) * VT + c] ? 65536u : 1u);
             }
+            for (; rr < nr; rr += 32) atomicAdd(&hc[ic[rr]], ytile[rr * VT + c] ? 65536u : 1u);
         }
         __syncthreads();
     }
-    for (int i = t; i < nv * K * 2; i += PLL_ROWS) {
+    for (int i = t; i < nv * K; i += PLL_THREADS) {
         const unsigned int h = hist[i];
         if (h) {
-            const int c = i / (2 * K), r = i - c * 2 * K;
-            const int k = r >> 1;
-            unsigned long long* dst = (r & 1) ? n1 : n0;
-            atomicAdd(&dst[(long long)(gv0 + c) * K + k], (unsigned long long)h);
+            const int c = i / K, k = i - c * K;
+            const long long o = (long long)(gv0 + c) * K + k;
+            if (h & 0xffffu) atomicAdd(&n0[o], (unsigned long long)(h & 0xffffu));
+            if (h >> 16) atomicAdd(&n1[o], (unsigned long long)(h >> 16));
         }
     }
 }
@@ -128,22 +137,22 @@ int pgmvae_pll_count(pgmvae_ctx* ctx, void* stream, const int32_t* idx, int64_t 
     PG_CHECK_ARG(ctx && idx && y && n1 && n0);
     PG_CHECK_ARG(K > 0 && G >= 0 && B >= 0);
     if (G == 0 || B == 0) return PGMVAE_OK;
-    const size_t budget = 128 * 1024;
-    int VT = (int)(budget / ((size_t)K * 8 + PLL_ROWS));
+    int VT = (int)((64 * 1024) / ((size_t)K * 4));
     if (VT > 32) VT = 32;
     if (VT > G) VT = G;
     if (VT < 1) {
         pgmvae_set_error("pll_count: K=%d too large for the shared-memory histogram", K);
         return PGMVAE_EINVAL;
     }
-    const size_t smem = (size_t)VT * K * 8 + (size_t)PLL_ROWS * VT;
+    const size_t smem = (size_t)VT * K * 4 + (size_t)PLL_TILE * VT;
     const int vtiles = (int)pg_cdiv(G, VT);
-    // enough row splits to give every SM ~2 CTAs, but keep >= 8 row tiles per CTA to amortise the flush
-    int splits = (int)pg_cdiv(2 * ctx->sm_count, vtiles);
-    const int max_splits = (int)pg_cdiv(B, 8 * PLL_ROWS);
+    // enough row splits to give every SM ~3 CTAs; at most 32768 rows per CTA (16-bit halves of the packed counters)
+    int splits = (int)pg_cdiv(3 * ctx->sm_count, vtiles);
+    const int max_splits = (int)pg_cdiv(B, 4 * PLL_TILE);
     if (splits > max_splits) splits = max_splits;
     if (splits < 1) splits = 1;
-    const int rows_per_cta = pg_round_up((int)pg_cdiv(B, splits), PLL_ROWS);
+    int rows_per_cta = pg_round_up((int)pg_cdiv(B, splits), PLL_TILE);
+    if (rows_per_cta > 32768) rows_per_cta = 32768;
     splits = (int)pg_cdiv(B, rows_per_cta);
     static size_t configured = 0;
     if (smem > 48 * 1024 && smem > configured) {
@@ -152,7 +161,7 @@ int pgmvae_pll_count(pgmvae_ctx* ctx, void* stream, const int32_t* idx, int64_t 
     }
     dim3 grid((unsigned)splits, (unsigned)vtiles);
     PG_KERNEL(ctx, pg_stream(ctx, stream), "pll_count", (double)G * B * 5.0 + 2.0 * G * K * 8.0, (double)G * B);
-    pll_count_kernel<<<grid, PLL_ROWS, smem, pg_stream(ctx, stream)>>>(idx, idx_gs, y, ldy, g0, n1, n0, G, B, K, VT,
+    pll_count_kernel<<<grid, PLL_THREADS, smem, pg_stream(ctx, stream)>>>(idx, idx_gs, y, ldy, g0, n1, n0, G, B, K, VT,
                                                                       rows_per_cta);
     PG_LAUNCHED(ctx);
     return PGMVAE_OK;

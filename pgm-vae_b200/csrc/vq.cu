@@ -5,6 +5,8 @@
 //   ema_apply    TF assign_moving_average x2 + Laplace + normalise  core/quantizer.py:144-152
 // The codebook is held CODE-MAJOR ([K, D] per variable) so that a code row is one
 // contiguous vector for the gather, the scatter and the tensor-core B operand alike.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "ops.cuh"
 
@@ -125,6 +127,59 @@ __global__ void __launch_bounds__(256) vq_quantize_kernel(
 // SMEM=true: CTA-private accumulators in shared memory (K*D floats), flushed once per CTA
 // with one global atomic per touched element; SMEM=false: direct global reductions
 // (codebooks too large for shared memory).  One warp per row, lanes across D.
+__device__ __forceinline__ void red_add_v4(float* addr, float4 v) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                 : "memory");
+}
+
+// Codebooks too large for shared memory (cfg4: 8192 x 64): every row is read once with 128-bit loads
+// (LPR lanes per row, 32 / LPR rows per warp request, eight requests in flight) and added to its code
+// with 128-bit vector reductions resolved in L2 -- one RED per 16 bytes instead of one per float.
+constexpr int SCATTER_UNROLL = 8;       // 128-bit row loads in flight per thread
+
+template <int MODE>
+__global__ void __launch_bounds__(256) scatter_rows_vec_kernel(
+    const float* __restrict__ z, const float* __restrict__ q, long long z_gs, int ldz,
+    const int32_t* __restrict__ idx, long long idx_gs, float* __restrict__ cnt, long long c_gs,
+    float* __restrict__ acc, long long a_gs, int lda, float scale, int B, int D4, int LPR) {
+    const int g = blockIdx.y;
+    const int lane = threadIdx.x & 31;
+    const int sub = lane / LPR, l = lane - sub * LPR;          // row within the warp request, float4 within the row
+    const int rpw = 32 / LPR;                                  // rows per warp request
+    const long long warp_id = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const float* zg = z + (long long)g * z_gs;
+    const float* qg = q ? q + (long long)g * z_gs : nullptr;
+    const int32_t* ig = idx + (long long)g * idx_gs;
+    float* ag = acc + (long long)g * a_gs;
+    float* cg = cnt ? cnt + (long long)g * c_gs : nullptr;
+    for (long long b0 = warp_id * rpw * SCATTER_UNROLL; b0 < B; b0 += nwarps * rpw * SCATTER_UNROLL) {
+        float4 v[SCATTER_UNROLL];
+        int k[SCATTER_UNROLL];
+#pragma unroll
+        for (int u = 0; u < SCATTER_UNROLL; ++u) {
+            const long long b = b0 + u * rpw + sub;
+            k[u] = -1;
+            if (b < B && l < D4) {
+                k[u] = ig[b];
+                v[u] = *reinterpret_cast<const float4*>(zg + b * ldz + 4 * l);
+                if (MODE == 1) {
+                    const float4 qq = *reinterpret_cast<const float4*>(qg + b * ldz + 4 * l);
+                    v[u] = make_float4(scale * (qq.x - v[u].x), scale * (qq.y - v[u].y), scale * (qq.z - v[u].z),
+                                       scale * (qq.w - v[u].w));
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < SCATTER_UNROLL; ++u) {
+            if (k[u] >= 0) {
+                red_add_v4(ag + (long long)k[u] * lda + 4 * l, v[u]);
+                if (MODE == 0 && l == 0) atomicAdd(&cg[k[u]], 1.0f);
+            }
+        }
+    }
+}
+
 template <int MODE, bool SMEM>
 __global__ void __launch_bounds__(256) scatter_rows_kernel(
     const float* __restrict__ z, const float* __restrict__ q, long long z_gs, int ldz,
@@ -173,16 +228,11 @@ __global__ void __launch_bounds__(256) scatter_rows_kernel(
     }
 }
 
-// one CTA per variable
-__global__ void __launch_bounds__(256) ema_apply_kernel(
-    const float* __restrict__ counts, const float* __restrict__ dw, float* __restrict__ biased_c,
-    float* __restrict__ biased_w, float* __restrict__ ema_c, float* __restrict__ ema_w, float* __restrict__ e,
-    int K, int D, int ld, float one_minus, float epsilon, float bias_factor, int zero_debias) {
-    __shared__ float red[8];
-    __shared__ float n_sh;
-    const int g = blockIdx.x;
-    const long long co = (long long)g * K, wo = (long long)g * K * ld;
-    float part = 0.f;
+// EMA update, step 1 (one CTA per variable): the per-code counts
+__global__ void __launch_bounds__(256) ema_counts_kernel(
+    const float* __restrict__ counts, float* __restrict__ biased_c, float* __restrict__ ema_c, int K,
+    float one_minus, float bias_factor, int zero_debias) {
+    const long long co = (long long)blockIdx.x * K;
     for (int k = threadIdx.x; k < K; k += blockDim.x) {
         float u;
         if (zero_debias) {
@@ -191,12 +241,26 @@ __global__ void __launch_bounds__(256) ema_apply_kernel(
             biased_c[co + k] = bc;
             u = bc / bias_factor;
         } else {
-            float c = ema_c[co + k];
+            const float c = ema_c[co + k];
             u = c - (c - counts[co + k]) * one_minus;
         }
         ema_c[co + k] = u;
-        part += u;
     }
+}
+
+// EMA update, step 2 (grid: slices of K*D x variables): n = sum_k ema_c (re-derived per CTA in the same
+// order, so every CTA of a variable sees the identical value), per-code sums, Laplace smoothing and the
+// normalised codebook write-back.  Elements are walked with float4 where the layout allows.
+__global__ void __launch_bounds__(256) ema_apply_kernel(
+    const float* __restrict__ dw, float* __restrict__ biased_w, const float* __restrict__ ema_c,
+    float* __restrict__ ema_w, float* __restrict__ e, int K, int D, int ld, float one_minus, float epsilon,
+    float bias_factor, int zero_debias, int per_cta) {
+    __shared__ float red[8];
+    __shared__ float n_sh;
+    const int g = blockIdx.y;
+    const long long co = (long long)g * K, wo = (long long)g * K * ld;
+    float part = 0.f;
+    for (int k = threadIdx.x; k < K; k += blockDim.x) part += ema_c[co + k];
     part = pg_warp_sum(part);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = part;
     __syncthreads();
@@ -208,7 +272,8 @@ __global__ void __launch_bounds__(256) ema_apply_kernel(
     __syncthreads();
     const float n = n_sh;
     const float denom = n + (float)K * epsilon;
-    for (int i = threadIdx.x; i < K * D; i += blockDim.x) {
+    const int i0 = blockIdx.x * per_cta, i1 = min(K * D, i0 + per_cta);
+    for (int i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
         const int k = i / D, d = i - k * D;
         const long long o = wo + (long long)k * ld + d;
         float u;
@@ -218,7 +283,7 @@ __global__ void __launch_bounds__(256) ema_apply_kernel(
             biased_w[o] = bw;
             u = bw / bias_factor;
         } else {
-            float w = ema_w[o];
+            const float w = ema_w[o];
             u = w - (w - dw[o]) * one_minus;
         }
         ema_w[o] = u;
@@ -274,6 +339,15 @@ static int scatter_launch(pgmvae_ctx* ctx, cudaStream_t st, const float* z, cons
         }
         scatter_rows_kernel<MODE, true><<<grid, 256, smem, st>>>(z, q, z_gs, ldz, idx, idx_gs, cnt, c_gs, acc, a_gs,
                                                                  lda, scale, B, D, K, rows);
+    } else if (D % 4 == 0 && D <= 128 && ldz % 4 == 0 && lda % 4 == 0 && z_gs % 4 == 0 && a_gs % 4 == 0 &&
+               !((uintptr_t)z & 15) && !((uintptr_t)acc & 15) && (!q || !((uintptr_t)q & 15))) {
+        int lpr = 1;
+        while (lpr < D / 4) lpr <<= 1;                       // lanes per row: power of two >= D / 4
+        int per_sm = 8;
+        if (const char* ev = getenv("PGMVAE_SCATTER_CTAS")) per_sm = atoi(ev) > 0 ? atoi(ev) : 8;
+        dim3 vgrid((unsigned)(ctx->sm_count * per_sm), (unsigned)G);
+        scatter_rows_vec_kernel<MODE><<<vgrid, 256, 0, st>>>(z, q, z_gs, ldz, idx, idx_gs, cnt, c_gs, acc, a_gs, lda,
+                                                              scale, B, D / 4, lpr);
     } else {
         scatter_rows_kernel<MODE, false><<<grid, 256, 0, st>>>(z, q, z_gs, ldz, idx, idx_gs, cnt, c_gs, acc, a_gs,
                                                                lda, scale, B, D, K, rows);
@@ -328,8 +402,18 @@ int pgmvae_ema_apply(pgmvae_ctx* ctx, void* stream, const float* counts, const f
     const float one_minus = (float)(1.0 - decay);
     const float bias_factor = 1.0f - powf(1.0f - one_minus, (float)step);
     PG_KERNEL(ctx, pg_stream(ctx, stream), "ema_apply", 4.0 * G * K * D * 5.0 + 4.0 * 4.0 * G * K, 6.0 * G * K * D);
-    ema_apply_kernel<<<G, 256, 0, pg_stream(ctx, stream)>>>(counts, dw, biased_c, biased_w, ema_c, ema_w, e, K, D, ld,
-                                                          one_minus, (float)epsilon, bias_factor, zero_debias);
+    ema_counts_kernel<<<G, 256, 0, pg_stream(ctx, stream)>>>(counts, biased_c, ema_c, K, one_minus, bias_factor,
+                                                           zero_debias);
+    ctx->launches++;
+    // slices of >= 4096 elements; enough CTAs to fill the machine when K * D is large (cfg4: 8192 x 64)
+    int slices = (int)pg_cdiv((int64_t)K * D, 4096);
+    const int want = (int)pg_cdiv(4 * ctx->sm_count, G);
+    if (slices > want) slices = want;
+    if (slices < 1) slices = 1;
+    const int per_cta = (int)pg_cdiv((int64_t)K * D, slices);
+    dim3 grid((unsigned)pg_cdiv((int64_t)K * D, per_cta), (unsigned)G);
+    ema_apply_kernel<<<grid, 256, 0, pg_stream(ctx, stream)>>>(dw, biased_w, ema_c, ema_w, e, K, D, ld, one_minus,
+                                                             (float)epsilon, bias_factor, zero_debias, per_cta);
     PG_LAUNCHED(ctx);
     return PGMVAE_OK;
 }
