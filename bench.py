@@ -15,6 +15,9 @@ Prints ONE JSON line on rank 0.
   cpu_baseline / --impl reference : the CPU restatement of the reference (oracle/, torch-CPU fp32;
              TensorFlow itself is not installable in this image) timed on the host cores
   pll_eval   stage 2 (encoder + VQ assignment + histogram) samples/s, device-resident and e2e
+  vq_assign  BASELINE.json configs[3] shape (D=64, K=8192; 4 Mi vectors unless --vq-n): fused fp16 tcgen05
+             assignment + EMA scatter, useful TFLOP/s against the measured bf16 peak
+  hbm_stages the stand-alone EMA scatter / EMA update / PLL histogram kernels against the measured HBM peak
 """
 import argparse
 import json
@@ -151,6 +154,71 @@ def run_reference(args, wl):
     print(json.dumps(line), flush=True)
 
 
+def measured_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture of this
+    workload (profiles/r1_dram_traffic.json), or None when the kernel was not captured."""
+    p = os.path.join(ROOT, "profiles", "r1_dram_traffic.json")
+    if not os.path.exists(p):
+        return None
+    return json.load(open(p)).get(kernel)
+
+
+def vq_and_hbm_stages(ctx, _ffi, L, n_vq, hbm_peak, tc_peak_bf16):
+    """cfg4-shaped VQ microbench (fused assign + EMA scatter, fp16 operands) and the HBM-bound stages alone."""
+    import ctypes as C
+    rng = np.random.default_rng(0)
+    D, K = 64, 8192
+    e = rng.uniform(-1, 1, (1, K, D)).astype(np.float32) * np.float32(np.sqrt(3.0 / D))
+    z = rng.standard_normal((1, n_vq, D), dtype=np.float32)
+    dz, de = _ffi.DeviceArray.from_numpy(ctx, z), _ffi.DeviceArray.from_numpy(ctx, e)
+    idx = _ffi.DeviceArray(ctx, (1, n_vq), np.int32)
+    cnt, dw = _ffi.DeviceArray(ctx, (1, K)), _ffi.DeviceArray(ctx, (1, K, D))
+
+    def fused():
+        _ffi.check(L.pgmvae_vq_assign_ema(ctx.h, None, dz.ptr, n_vq * D, D, de.ptr, K * D, D, idx.ptr, n_vq, cnt.ptr, K,
+                                          dw.ptr, K * D, D, 1, n_vq, D, K))
+    for _ in range(2):
+        fused()
+    ctx.sync()
+    ctx.timer_start()
+    reps = 3
+    for _ in range(reps):
+        fused()
+    ms = ctx.timer_stop_ms() / reps
+    nres = C.c_int(0)
+    _ffi.check(L.pgmvae_vq_assign_rescored(ctx.h, 1, K, C.byref(nres)))
+    tf = 2.0 * n_vq * D * K / (ms * 1e-3) / 1e12
+    vq = {"workload": f"cfg4 shape: {n_vq} vectors, D=64, K=8192, fp16 tcgen05 assignment + fused EMA scatter",
+          "ms": ms, "vectors_per_s": n_vq / (ms * 1e-3), "useful_tflops": tf, "peak_tflops_bf16": tc_peak_bf16,
+          "frac_of_bf16_peak": tf / tc_peak_bf16, "full_scan_rows": nres.value,
+          "note": "useful flops = 2*D*K per vector; the |e|^2 column adds 25 % MMA work that is not counted"}
+    # stand-alone scatter + update on the same vectors / codes
+    bc, bw = _ffi.DeviceArray(ctx, (1, K)), _ffi.DeviceArray(ctx, (1, K, D))
+    ec, ew = _ffi.DeviceArray(ctx, (1, K)), _ffi.DeviceArray(ctx, (1, K, D))
+    V, K2, B2 = 1556, 512, 32768
+    idx2 = _ffi.DeviceArray.from_numpy(ctx, rng.integers(0, K2, (V, B2)).astype(np.int32))
+    y2 = _ffi.DeviceArray.from_numpy(ctx, (rng.random((B2, V)) < 0.2).astype(np.uint8))
+    n1, n0 = _ffi.DeviceArray(ctx, (V, K2), np.uint64), _ffi.DeviceArray(ctx, (V, K2), np.uint64)
+
+    def stages():
+        _ffi.check(L.pgmvae_ema_stats(ctx.h, None, dz.ptr, n_vq * D, D, idx.ptr, n_vq, cnt.ptr, K, dw.ptr, K * D, D, 1,
+                                      n_vq, D, K))
+        _ffi.check(L.pgmvae_ema_apply(ctx.h, None, cnt.ptr, dw.ptr, bc.ptr, bw.ptr, ec.ptr, ew.ptr, de.ptr, 1, K, D, D,
+                                      0.99, 1e-5, 1, 1))
+        _ffi.check(L.pgmvae_pll_count(ctx.h, None, idx2.ptr, B2, y2.ptr, V, 0, n1.ptr, n0.ptr, V, B2, K2))
+    stages()
+    ctx.sync()
+    ctx.profile_begin()
+    for _ in range(3):
+        stages()
+    hbm = {}
+    for k in ctx.profile_end():
+        gbs = k["bytes"] / max(k["ms"], 1e-9) / 1e6
+        hbm[k["name"]] = {"ms_per_launch": k["ms"] / k["launches"], "algorithmic_GBps": gbs, "frac_of_hbm_peak": gbs / hbm_peak}
+    hbm["shapes"] = {"ema": f"{n_vq} x 64 vectors into 8192 codes", "pll_count": f"{V} variables x {B2} samples, K={K2}"}
+    return vq, hbm
+
+
 # --------------------------------------------------------------------------- our arm
 def run_ours(args, wl):
     V, units, D, K, B, desc = wl
@@ -253,7 +321,7 @@ def run_ours(args, wl):
         "kernel": top["name"], "bound": "tensor" if tensor_bound else "hbm",
         "achieved": tfs if tensor_bound else gbs, "peak": tc_peak if tensor_bound else hbm_peak,
         "unit": "TFLOP/s" if tensor_bound else "GB/s",
-        "frac": (tfs / tc_peak) if tensor_bound else (gbs / hbm_peak), "traffic": None,
+        "frac": (tfs / tc_peak) if tensor_bound else (gbs / hbm_peak), "traffic": measured_traffic(top["name"]),
         "peak_source": peak_src, "avg_launch_ms": avg_ms, "launches_per_step": top["launches"] / psteps,
         "share_of_step": top["ms"] / tot_ms, "algorithmic_bytes_per_launch": top["bytes"] / top["launches"],
         "algorithmic_flops_per_launch": top["flops"] / top["launches"],
@@ -287,6 +355,11 @@ def run_ours(args, wl):
 
     if rank != 0:
         return
+    vq_assign = hbm_stages = None
+    device_bytes = model.device_bytes()
+    if world == 1 and not args.no_microbench:
+        del model, y_dev
+        vq_assign, hbm_stages = vq_and_hbm_stages(ctx, _ffi, L, args.vq_n, hbm_peak, peaks()[1])
     # ---- CPU baseline beside it (rank 0, N == 1 only): bounded sample of the same workload
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
@@ -306,11 +379,11 @@ def run_ours(args, wl):
                    "l2": "per-step working set (activations + gradients, >400 MB at cfg2) exceeds the 126 MB L2; "
                          "8 distinct input batches rotated",
                    "flop_per_sample_train": train_fl, "flop_per_sample_pll": pll_fl,
-                   "achieved_tflops": value * train_fl / 1e12, "device_bytes": model.device_bytes()},
+                   "achieved_tflops": value * train_fl / 1e12, "device_bytes": device_bytes},
         "roofline": roofline, "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": B * V, "d2h_bytes_per_step": 32,
                 "ms_per_step": e2e_ms / args.steps},
-        "gpu_launches": launches, "clocks": clocks, "pll_eval": pll_eval,
+        "gpu_launches": launches, "clocks": clocks, "pll_eval": pll_eval, "vq_assign": vq_assign, "hbm_stages": hbm_stages,
         "loss_after": {"loss": met[0], "mse": met[1], "mae": met[2], "vq_loss": met[3]},
     }
     print(json.dumps(line), flush=True)
@@ -324,6 +397,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-microbench", action="store_true", help="skip the cfg4 VQ and HBM-stage micro-benchmarks")
+    ap.add_argument("--vq-n", type=int, default=1 << 22, help="vectors of the cfg4-shaped VQ micro-benchmark")
     ap.add_argument("--precision", default="tf32", choices=["fp32", "tf32"],
                     help="arithmetic of the GEMM-shaped kernels: tcgen05 tf32 (fp32 accumulate) or exact fp32 CUDA cores")
     args = ap.parse_args()

@@ -25,13 +25,14 @@ namespace {
 constexpr int TM = 128;
 constexpr int KBLK = 32;                          // fp32 elements per k-block (128 bytes)
 constexpr int A_STAGE_BYTES = TM * 128;           // 16 KB
-constexpr int MAX_STAGES = 4;
+constexpr int MAX_STAGES = 8;
 
 enum { EPI_BIAS_ACT = 0, EPI_SIGMOID_MSE = 1, EPI_DGRAD = 2, EPI_WGRAD = 3 };
 
 struct DenseTcP {
     int M, N, K;                     // per-variable problem: C[M,N] = A[M,K] * B[K,N]
     int BN, kblocks, stages, tmem_cols;
+    int a_stage_bytes, apan;         // bytes of one A stage; MN-major A: 32-row panels actually loaded (<= 4)
     int a_mn, b_mn;                  // operand is MN-major (panels of 128 bytes along M / N)
     int a_shared;                    // A is one matrix shared by all variables (the raw data y)
     int vecC;                        // rows of C / aux are 16-byte aligned
@@ -75,8 +76,10 @@ __global__ void __launch_bounds__(128) dense_tc_kernel(const __grid_constant__ C
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-byte aligned, still a shared-space pointer
     const int b_stage_bytes = p.BN * 128;
-    uint8_t* sA = smem;                                           // [stages][16 KB]
-    uint8_t* sB = sA + (size_t)p.stages * A_STAGE_BYTES;          // [stages][BN*128]
+    // [stages][a_stage_bytes]: an MN-major A tile only holds the panels that contain valid rows; the MMA
+    // (M = 128) reads on into the next stage, which only feeds accumulator rows nobody looks at
+    uint8_t* sA = smem;
+    uint8_t* sB = sA + (size_t)p.stages * p.a_stage_bytes + (A_STAGE_BYTES - p.a_stage_bytes);   // [stages][BN*128]
     // wgrad: constant A tile whose row 0 is all ones (K-major, one 128-byte row): a second MMA per k-step
     // then leaves the column sums of dY (the bias gradient) in row 0 of a second accumulator
     uint8_t* sOnes = sB + (size_t)p.stages * b_stage_bytes;
@@ -122,19 +125,19 @@ __global__ void __launch_bounds__(128) dense_tc_kernel(const __grid_constant__ C
     if (nkb > 0) {
         if (warp == 0) {
             // ===================== TMA producer (warp-uniform loop, one elected lane issues) =====================
-            const uint32_t stage_tx = (uint32_t)(A_STAGE_BYTES + b_stage_bytes);
+            const uint32_t stage_tx = (uint32_t)(p.a_stage_bytes + b_stage_bytes);
             uint32_t s = 0, ph = 0;
             const int ga = p.a_shared ? 0 : g;
             for (int kb = kb_beg; kb < kb_end; ++kb) {
                 tc::mbar_wait(&empty[s], ph ^ 1);
                 if (tc::elect_one()) {
                     tc::mbar_arrive_expect_tx(&full[s], stage_tx);
-                    uint8_t* a_dst = sA + (size_t)s * A_STAGE_BYTES;
+                    uint8_t* a_dst = sA + (size_t)s * p.a_stage_bytes;
                     uint8_t* b_dst = sB + (size_t)s * b_stage_bytes;
                     if (!p.a_mn) {
                         tc::tma_load_3d(a_dst, &mapA, &full[s], kb * KBLK, m0, ga);                 // [128 m][32 k]
                     } else {
-                        for (int pn = 0; pn < TM / 32; ++pn)                                        // 4 panels [32 k][32 m]
+                        for (int pn = 0; pn < p.apan; ++pn)                                         // panels [32 k][32 m]
                             tc::tma_load_3d(a_dst + pn * 4096, &mapA, &full[s], m0 + pn * 32, kb * KBLK, ga);
                     }
                     if (!p.b_mn) {
@@ -158,7 +161,7 @@ __global__ void __launch_bounds__(128) dense_tc_kernel(const __grid_constant__ C
             const uint64_t dB0 = p.b_mn ? tc::make_smem_desc(tc::smem_u32(sB), 4096, 512, 1)
                                         : tc::make_smem_desc(tc::smem_u32(sB), 16, 1024, 2);
             const uint32_t a_step = (p.a_mn ? 1024u : 32u) >> 4, b_step = (p.b_mn ? 1024u : 32u) >> 4;
-            const uint32_t a_stage = (uint32_t)A_STAGE_BYTES >> 4, b_stage = (uint32_t)b_stage_bytes >> 4;
+            const uint32_t a_stage = (uint32_t)p.a_stage_bytes >> 4, b_stage = (uint32_t)b_stage_bytes >> 4;
             uint32_t s = 0, ph = 0;
             for (int kb = kb_beg; kb < kb_end; ++kb) {
                 tc::mbar_wait(&full[s], ph);
@@ -314,10 +317,20 @@ int launch_tc(pgmvae_ctx* ctx, cudaStream_t st, DenseTcP& p, const CUtensorMap& 
               const char* name, double bytes) {
     p.tmem_cols = 32;
     while (p.tmem_cols < (EPI == EPI_WGRAD ? 2 : 1) * p.BN) p.tmem_cols <<= 1;
-    const size_t stage = (size_t)A_STAGE_BYTES + (size_t)p.BN * 128;
+    // MN-major A (wgrad) with a single M tile: load only the 32-row panels that hold valid rows
+    p.apan = TM / 32;
+    if (p.a_mn && p.M <= TM) p.apan = (int)pg_cdiv(p.M, 32);
+    p.a_stage_bytes = p.a_mn ? p.apan * 4096 : A_STAGE_BYTES;
+    const size_t stage = (size_t)p.a_stage_bytes + (size_t)p.BN * 128;
     int kb_cta = p.kb_per_split < p.kblocks ? p.kb_per_split : p.kblocks;
-    p.stages = kb_cta < 3 ? (kb_cta < 1 ? 1 : kb_cta) : 3;
-    const size_t smem = 1024 + p.stages * stage + (EPI == EPI_WGRAD ? A_STAGE_BYTES : 0) + 128;
+    if (kb_cta < 1) kb_cta = 1;
+    // wgrad streams long k ranges: as many stages as keep two CTAs per SM (~100 KB each), at most 8
+    int max_stages = EPI == EPI_WGRAD ? (int)((100 * 1024 - 2 * A_STAGE_BYTES) / stage) : 3;
+    if (max_stages > MAX_STAGES) max_stages = MAX_STAGES;
+    if (max_stages < 3) max_stages = 3;
+    p.stages = kb_cta < max_stages ? kb_cta : max_stages;
+    const size_t smem = 1024 + p.stages * stage + (A_STAGE_BYTES - p.a_stage_bytes) +
+                        (EPI == EPI_WGRAD ? A_STAGE_BYTES : 0) + 256;
     static size_t configured = 0;
     if (smem > configured) {
         PG_CUDA(cudaFuncSetAttribute(dense_tc_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -416,7 +429,8 @@ int pg_dense_wgrad_tc(pgmvae_ctx* ctx, cudaStream_t st, const float* x, int64_t 
     p.a_shared = x_gs == 0;
     // split the batch so that ~3 CTAs per SM are in flight, at least 8 k-blocks (256 samples) per CTA
     const int64_t tiles = pg_cdiv(out_dim, p.BN) * pg_cdiv(in, TM) * (int64_t)G;
-    int S = (int)pg_cdiv((int64_t)ctx->sm_count * 3, tiles > 0 ? tiles : 1);
+    // batch splits: fill ONE wave of two CTAs per SM (a partial second wave costs a whole CTA time)
+    int S = (int)(((int64_t)ctx->sm_count * 2) / (tiles > 0 ? tiles : 1));
     const int maxS = (int)pg_cdiv(p.kblocks, 8);
     if (S > maxS) S = maxS;
     if (S < 1) S = 1;
