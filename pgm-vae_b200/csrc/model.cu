@@ -86,6 +86,9 @@ struct pgmvae_model {
     unsigned long long *n1 = nullptr, *n0 = nullptr;
     int64_t device_bytes = 0;
     std::vector<void*> allocs;
+    // data-parallel overlap: all-reduces run on their own stream behind events of the compute stream
+    cudaStream_t comm_stream = nullptr;
+    cudaEvent_t ev_compute = nullptr, ev_comm = nullptr;
 
     float* E() const { return params + e_off; }
     float* dE() const { return grads + e_off; }
@@ -237,6 +240,19 @@ int upload_batch(pgmvae_model* m, const uint8_t* y, int on_device, int B, const 
         *y_dev = m->y_u8;
     }
     return pgmvae_y_to_f32(m->ctx, st, *y_dev, m->V, m->yf, m->Vp, B, m->V);
+}
+
+// all-reduce `buf` on the communication stream once everything issued so far on the compute stream is done
+int overlapped_allreduce(pgmvae_model* m, pgmvae_comm* comm, void* buf, int64_t n, int dtype) {
+    cudaStream_t st = m->ctx->stream;
+    if (!m->comm_stream) {
+        PG_CUDA(cudaStreamCreateWithFlags(&m->comm_stream, cudaStreamNonBlocking));
+        PG_CUDA(cudaEventCreateWithFlags(&m->ev_compute, cudaEventDisableTiming));
+        PG_CUDA(cudaEventCreateWithFlags(&m->ev_comm, cudaEventDisableTiming));
+    }
+    PG_CUDA(cudaEventRecord(m->ev_compute, st));
+    PG_CUDA(cudaStreamWaitEvent(m->comm_stream, m->ev_compute, 0));
+    return pg_comm_allreduce(comm, buf, n, dtype, m->comm_stream);
 }
 
 bool use_chain(const pgmvae_model* m) {
@@ -391,6 +407,9 @@ int pgmvae_model_destroy(pgmvae_model* m) {
     cudaStreamSynchronize(m->ctx->stream);
     for (void* p : m->allocs) cudaFree(p);
     if (m->acc_host) cudaFreeHost(m->acc_host);
+    if (m->comm_stream) cudaStreamDestroy(m->comm_stream);
+    if (m->ev_compute) cudaEventDestroy(m->ev_compute);
+    if (m->ev_comm) cudaEventDestroy(m->ev_comm);
     delete m;
     return PGMVAE_OK;
 }
@@ -521,6 +540,7 @@ int run_step(pgmvae_model* m, const uint8_t* y, int y_on_device, int B, int glob
     const float cscale = (float)(m->cost * 2.0 / n_lat);
 
     const bool chain = use_chain(m) && out_dev == nullptr;
+    bool overlapped = false;
     for (int g0 = 0; g0 < V && chain; g0 += m->Vg) {
         const int Gn = std::min(m->Vg, V - g0);
         const int64_t MB = m->max_batch;
@@ -536,6 +556,18 @@ int run_step(pgmvae_model* m, const uint8_t* y, int y_on_device, int B, int glob
             a.stat_w = stats ? m->stat_w + (size_t)g0 * K * Dp : nullptr;
             a.acc = m->acc; a.gscale = gscale;
             PG_TRY(pg_chain_launch(ctx, st, a));
+        }
+        // single variable group under data parallelism: every exchange is issued as soon as its operand is
+        // final and runs on the communication stream under the kernels that follow
+        const bool overlap = comm != nullptr && Gn == V;
+        if (overlap) {
+            if (stats) {
+                PG_TRY(overlapped_allreduce(m, comm, m->stat_w, (int64_t)V * K * Dp, 0));
+                PG_TRY(pg_comm_allreduce(comm, m->stat_c, (int64_t)V * K, 0, m->comm_stream));
+            }
+            if (!stats) PG_TRY(overlapped_allreduce(m, comm, m->acc, 4, 1));
+            else PG_TRY(pg_comm_allreduce(comm, m->acc, 4, 1, m->comm_stream));
+            overlapped = true;
         }
         if (flags & STEP_FWD_ONLY) continue;
         if (!m->ema)    // q_latent_loss gradient wrt the codebook: 2 (q - z) / (V B D)   (core/quantizer.py:51)
@@ -572,7 +604,11 @@ int run_step(pgmvae_model* m, const uint8_t* y, int y_on_device, int B, int glob
                                       m->grads + L.w_off + (size_t)g0 * L.pin * L.pout, (int64_t)L.pin * L.pout, L.pout,
                                       m->grads + L.b_off + (size_t)g0 * L.pout, L.pout, Gn, B, L.in, L.out,
                                       l == 0 ? g0 : -1));
+            if (overlap)     // kernel and bias gradients of a layer are contiguous: [w_off, b_off + V * pout)
+                PG_TRY(overlapped_allreduce(m, comm, m->grads + L.w_off, (int64_t)(L.b_off + (size_t)V * L.pout - L.w_off), 0));
         }
+        if (overlap && !m->ema)
+            PG_TRY(overlapped_allreduce(m, comm, m->dE(), (int64_t)V * K * Dp, 0));
     }
     for (int g0 = 0; g0 < V && !chain; g0 += m->Vg) {
         const int Gn = std::min(m->Vg, V - g0);
@@ -631,7 +667,11 @@ int run_step(pgmvae_model* m, const uint8_t* y, int y_on_device, int B, int glob
         }
     }
 
-    if (comm) {
+    if (comm && overlapped) {
+        // join: the optimiser / EMA update / metrics wait for the exchanges issued along the way
+        PG_CUDA(cudaEventRecord(m->ev_comm, m->comm_stream));
+        PG_CUDA(cudaStreamWaitEvent(st, m->ev_comm, 0));
+    } else if (comm) {
         if (!(flags & STEP_FWD_ONLY)) PG_TRY(pg_comm_allreduce(comm, m->grads, (int64_t)trainable, 0, st));
         if (m->ema && !(flags & STEP_NO_EMA)) {
             PG_TRY(pg_comm_allreduce(comm, m->stat_w, (int64_t)V * K * Dp, 0, st));
