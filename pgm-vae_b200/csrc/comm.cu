@@ -27,6 +27,8 @@ struct NcclApi {
     int (*CommDestroy)(ncclComm_t) = nullptr;
     int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     const char* (*GetErrorString)(int) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
 };
 
 NcclApi g_nccl;
@@ -51,6 +53,8 @@ int load_nccl() {
     g_nccl.AllReduce =
         (int (*)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t))dlsym(h, "ncclAllReduce");
     g_nccl.GetErrorString = (const char* (*)(int))dlsym(h, "ncclGetErrorString");
+    g_nccl.GroupStart = (int (*)())dlsym(h, "ncclGroupStart");
+    g_nccl.GroupEnd = (int (*)())dlsym(h, "ncclGroupEnd");
     if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.CommDestroy || !g_nccl.AllReduce) {
         pgmvae_set_error("libnccl lacks a required symbol");
         dlclose(h);
@@ -79,6 +83,18 @@ int pg_comm_allreduce(pgmvae_comm* c, void* buf, int64_t n, int dtype, cudaStrea
     const int rc = g_nccl.AllReduce(buf, buf, (size_t)n, dt, NCCL_SUM, c->comm, st);
     if (rc != ncclSuccess_) return nccl_fail("ncclAllReduce", rc);
     return PGMVAE_OK;
+}
+
+// several all-reduces fused into one NCCL launch (no-ops without a communicator / symbols)
+int pg_comm_group_begin(pgmvae_comm* c) {
+    if (!c || c->nranks <= 1 || !g_nccl.GroupStart) return PGMVAE_OK;
+    const int rc = g_nccl.GroupStart();
+    return rc == ncclSuccess_ ? PGMVAE_OK : nccl_fail("ncclGroupStart", rc);
+}
+int pg_comm_group_end(pgmvae_comm* c) {
+    if (!c || c->nranks <= 1 || !g_nccl.GroupEnd) return PGMVAE_OK;
+    const int rc = g_nccl.GroupEnd();
+    return rc == ncclSuccess_ ? PGMVAE_OK : nccl_fail("ncclGroupEnd", rc);
 }
 
 extern "C" {

@@ -26,6 +26,8 @@
 
 struct pgmvae_comm;
 int pg_comm_allreduce(pgmvae_comm* c, void* buf, int64_t n, int dtype, cudaStream_t st);  // comm.cu
+int pg_comm_group_begin(pgmvae_comm* c);
+int pg_comm_group_end(pgmvae_comm* c);
 
 namespace {
 
@@ -560,13 +562,14 @@ int run_step(pgmvae_model* m, const uint8_t* y, int y_on_device, int B, int glob
         // single variable group under data parallelism: every exchange is issued as soon as its operand is
         // final and runs on the communication stream under the kernels that follow
         const bool overlap = comm != nullptr && Gn == V;
-        if (overlap) {
+        if (overlap) {      // EMA statistics + loss accumulators: one fused NCCL launch
+            PG_TRY(pg_comm_group_begin(comm));
+            PG_TRY(overlapped_allreduce(m, comm, m->acc, 4, 1));
             if (stats) {
-                PG_TRY(overlapped_allreduce(m, comm, m->stat_w, (int64_t)V * K * Dp, 0));
+                PG_TRY(pg_comm_allreduce(comm, m->stat_w, (int64_t)V * K * Dp, 0, m->comm_stream));
                 PG_TRY(pg_comm_allreduce(comm, m->stat_c, (int64_t)V * K, 0, m->comm_stream));
             }
-            if (!stats) PG_TRY(overlapped_allreduce(m, comm, m->acc, 4, 1));
-            else PG_TRY(pg_comm_allreduce(comm, m->acc, 4, 1, m->comm_stream));
+            PG_TRY(pg_comm_group_end(comm));
             overlapped = true;
         }
         if (flags & STEP_FWD_ONLY) continue;
@@ -595,6 +598,7 @@ int run_step(pgmvae_model* m, const uint8_t* y, int y_on_device, int B, int glob
             a.z = m->H[4]; a.qv = m->q; a.cscale = cscale;
             PG_TRY(pg_chain_launch(ctx, st, a));
         }
+        size_t bucket_end = m->n_dense;
         for (int l = 9; l >= 0; --l) {
             const Layer& L = m->L[l];
             const float* x = l == 0 ? m->yf : (l == 5 ? m->st : m->H[l - 1]);
@@ -604,8 +608,12 @@ int run_step(pgmvae_model* m, const uint8_t* y, int y_on_device, int B, int glob
                                       m->grads + L.w_off + (size_t)g0 * L.pin * L.pout, (int64_t)L.pin * L.pout, L.pout,
                                       m->grads + L.b_off + (size_t)g0 * L.pout, L.pout, Gn, B, L.in, L.out,
                                       l == 0 ? g0 : -1));
-            if (overlap)     // kernel and bias gradients of a layer are contiguous: [w_off, b_off + V * pout)
-                PG_TRY(overlapped_allreduce(m, comm, m->grads + L.w_off, (int64_t)(L.b_off + (size_t)V * L.pout - L.w_off), 0));
+            // gradients leave in three buckets (layers 9-7, 6-4, 3-0; parameters are laid out in layer order),
+            // each as soon as its last wgrad is issued: few launches, and only the last bucket is exposed
+            if (overlap && (l == 7 || l == 4 || l == 0)) {
+                PG_TRY(overlapped_allreduce(m, comm, m->grads + L.w_off, (int64_t)(bucket_end - L.w_off), 0));
+                bucket_end = L.w_off;
+            }
         }
         if (overlap && !m->ema)
             PG_TRY(overlapped_allreduce(m, comm, m->dE(), (int64_t)V * K * Dp, 0));
