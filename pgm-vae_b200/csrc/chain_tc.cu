@@ -37,7 +37,8 @@ namespace {
 
 constexpr int CH_TM = 128;
 constexpr int CH_RING = 8;              // weight k-block stages: the producer runs ~4 layers ahead of the MMAs
-constexpr int CH_THREADS = 192;
+constexpr int CH_MAXCH = 3;             // independent chains (128-row tiles of one variable) in flight per CTA
+constexpr int CH_THREADS = 64 + 128 * CH_MAXCH;
 
 struct ChainMaps { CUtensorMap m[PG_CHAIN_MAX_STAGES]; };
 
@@ -46,7 +47,7 @@ struct ChainP {
     int nst;
     PgChainStage st[PG_CHAIN_MAX_STAGES];
     int G, g0, B, V, Vp, D, Dp, K, vq_stage;
-    int tiles_m, tmem_cols, nbias, items_per_cta;
+    int tiles_m, tiles_real, tmem_cols, nbias, nch, sub_cols, tab_floats;
     uint32_t stage_bytes;
     // layer-0 operand / targets
     const float* a0; long long a0_gs; int lda0, a0_cols;    // fwd: yf [B][Vp] (shared); bwd: dpre of the top layer
@@ -66,7 +67,21 @@ struct ChainP {
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
-__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }   // the four warps of one chain
+
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {      // non-blocking probe
+    uint32_t done;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(done)
+        : "r"(tc::smem_u32(bar)), "r"(parity)
+        : "memory");
+    return done != 0;
+}
 
 __device__ __forceinline__ void store_chunk(float* dst, const float (&v)[32], int nv) {
 #pragma unroll
@@ -134,36 +149,36 @@ __device__ __forceinline__ int vq_row_argmin(const float (&v)[32], float zz, con
 }
 
 template <bool EXACT>
-__global__ void __launch_bounds__(CH_THREADS, 2)
+__global__ void __launch_bounds__(CH_THREADS, 1)
 chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ ChainP p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-byte aligned, still a shared-space pointer
     uint8_t* sB = smem;                                                          // [CH_RING][stage_bytes]
     uint64_t* bars = reinterpret_cast<uint64_t*>(sB + (size_t)CH_RING * p.stage_bytes);
     uint64_t* b_full = bars;                   // [CH_RING]
-    uint64_t* b_empty = bars + CH_RING;        // [CH_RING]
-    uint64_t* a_ready = bars + 2 * CH_RING;
-    uint64_t* d_full = bars + 2 * CH_RING + 1;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * CH_RING + 2);
-    float* sE = reinterpret_cast<float*>(bars + 2 * CH_RING + 4);                             // [K][Dp]
+    uint64_t* b_empty = bars + CH_RING;        // [CH_RING]   one arrival per chain
+    uint64_t* a_ready = bars + 2 * CH_RING;    // [CH_MAXCH]  one arrival per epilogue warp of the chain
+    uint64_t* d_full = bars + 2 * CH_RING + CH_MAXCH;   // [CH_MAXCH]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * CH_RING + 2 * CH_MAXCH);
+    float* tables = reinterpret_cast<float*>(bars + 2 * CH_RING + 2 * CH_MAXCH + 2);     // per chain: sE | sEE | sHist | sBias
     const int Kp = (p.K + 3) & ~3;                                               // codes padded to a multiple of 4
-    float* sEE = sE + (size_t)Kp * p.Dp;                                         // [Kp]
-    uint32_t* sHist = reinterpret_cast<uint32_t*>(sEE + Kp);                     // [2][K]  (count mode)
-    float* sBias = reinterpret_cast<float*>(sHist + 2 * Kp);                    // biases of all stages, this variable
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int items = p.G * p.tiles_m;
+    const int items = p.G * p.tiles_m;         // item = (variable, group of nch consecutive 128-row tiles)
     // consecutive items per CTA: mostly the same variable, so its codebook and biases stay in shared memory
-    const int item_beg = blockIdx.x * p.items_per_cta, item_end = min(items, item_beg + p.items_per_cta);
+    const int item_beg = (int)((long long)blockIdx.x * items / gridDim.x);
+    const int item_end = (int)((long long)(blockIdx.x + 1) * items / gridDim.x);
 
     if (warp == 0 && lane == 0) {
         for (int j = 0; j < p.nst; ++j) tc::tma_prefetch_desc(&maps.m[j]);
         for (int s = 0; s < CH_RING; ++s) {
             tc::mbar_init(&b_full[s], 1);
-            tc::mbar_init(&b_empty[s], 1);
+            tc::mbar_init(&b_empty[s], p.nch);   // a weight k-block is released once every chain has consumed it
         }
-        tc::mbar_init(a_ready, 4);             // one arrival per epilogue warp
-        tc::mbar_init(d_full, 1);
+        for (int c = 0; c < CH_MAXCH; ++c) {
+            tc::mbar_init(&a_ready[c], 4);       // one arrival per epilogue warp
+            tc::mbar_init(&d_full[c], 1);
+        }
         tc::fence_barrier_init();
     }
     if (warp == 1) {
@@ -200,53 +215,81 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ Cha
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer
+        // ===================== MMA issuer: serves the chains in whatever order their operands become ready.
+        // Every probe is non-blocking (a blocking wait on one chain's weights could starve the chain whose
+        // progress releases that very ring slot); all chains consume the same k-block sequence.
         const uint64_t dB_mn = tc::make_smem_desc(tc::smem_u32(sB), 4096, 512, 1);
         const uint64_t dB_k = tc::make_smem_desc(tc::smem_u32(sB), 16, 1024, 2);
         const uint32_t stage_stride = p.stage_bytes >> 4;
-        uint32_t s = 0, ph = 0, aph = 0;
-        for (int item = item_beg; item < item_end; ++item) {
-            for (int j = 0; j < p.nst; ++j) {
-                const PgChainStage& S = p.st[j];
-                const uint32_t idesc = tc::make_idesc(2, CH_TM, S.N, 0, S.b_mn);
-                const uint64_t dB0 = S.b_mn ? dB_mn : dB_k;
-                const uint32_t bstep = (S.b_mn ? 1024u : 32u) >> 4;
-                tc::mbar_wait(a_ready, aph);                // the A operand of this stage sits in TMEM
-                aph ^= 1;
-                for (int kb = 0; kb < S.kblocks; ++kb) {
-                    tc::mbar_wait(&b_full[s], ph);
-                    tc::fence_after_thread_sync();
-                    if (tc::elect_one()) {
-                        const uint64_t dB = dB0 + (uint64_t)(s * stage_stride);
-                        const int nk = min(4, S.ksteps - kb * 4);
-                        for (int k4 = 0; k4 < nk; ++k4)
-                            tc::mma_tf32_ts(tmem_base + S.d_col, tmem_base + S.a_col + kb * 32 + k4 * 8,
-                                            dB + (uint64_t)(k4 * bstep), idesc, (kb | k4) ? 1u : 0u);
-                        tc::mma_commit(&b_empty[s]);
-                        if (kb == S.kblocks - 1) tc::mma_commit(d_full);
+        int c_item[CH_MAXCH], c_j[CH_MAXCH], c_kb[CH_MAXCH];
+        uint32_t c_seq[CH_MAXCH], c_aph[CH_MAXCH], c_have[CH_MAXCH];
+#pragma unroll
+        for (int c = 0; c < CH_MAXCH; ++c) { c_item[c] = item_beg; c_j[c] = 0; c_kb[c] = 0; c_seq[c] = 0; c_aph[c] = 0; c_have[c] = 0; }
+        int live = item_beg < item_end ? p.nch : 0;
+        while (live > 0) {
+            bool progress = false;
+#pragma unroll
+            for (int c = 0; c < CH_MAXCH; ++c) {
+                if (c >= p.nch || c_item[c] >= item_end) continue;
+                const PgChainStage& S = p.st[c_j[c]];
+                if (!c_have[c]) {                               // the A operand of this stage sits in TMEM?
+                    if (!mbar_test(&a_ready[c], c_aph[c])) continue;
+                    c_aph[c] ^= 1;
+                    c_have[c] = 1;
+                }
+                const uint32_t slot = c_seq[c] % CH_RING, gen = c_seq[c] / CH_RING;
+                if (!mbar_test(&b_full[slot], gen & 1)) continue;
+                progress = true;
+                tc::fence_after_thread_sync();
+                if (tc::elect_one()) {
+                    const uint32_t idesc = tc::make_idesc(2, CH_TM, S.N, 0, S.b_mn);
+                    const uint64_t dB = (S.b_mn ? dB_mn : dB_k) + (uint64_t)(slot * stage_stride);
+                    const uint32_t bstep = (S.b_mn ? 1024u : 32u) >> 4;
+                    const uint32_t tb = tmem_base + c * p.sub_cols;
+                    const int kb = c_kb[c], nk = min(4, S.ksteps - kb * 4);
+                    for (int k4 = 0; k4 < nk; ++k4)
+                        tc::mma_tf32_ts(tb + S.d_col, tb + S.a_col + kb * 32 + k4 * 8, dB + (uint64_t)(k4 * bstep), idesc,
+                                        (kb | k4) ? 1u : 0u);
+                    tc::mma_commit(&b_empty[slot]);
+                    if (kb == S.kblocks - 1) tc::mma_commit(&d_full[c]);
+                }
+                __syncwarp();
+                ++c_seq[c];
+                if (++c_kb[c] == S.kblocks) {
+                    c_kb[c] = 0; c_have[c] = 0;
+                    if (++c_j[c] == p.nst) {
+                        c_j[c] = 0;
+                        if (++c_item[c] >= item_end) --live;
                     }
-                    __syncwarp();
-                    if (++s == CH_RING) { s = 0; ph ^= 1; }
                 }
             }
+            if (!progress) __nanosleep(40);
         }
-    } else {
-        // ===================== epilogue: one sample row per thread
+    } else if (warp < 2 + 4 * p.nch) {
+        // ===================== epilogue: one sample row per thread, four warps per chain
         const int q4 = warp & 3;                              // TMEM lane quarter == warp % 4
+        const int ch = (warp - 2) >> 2;                       // chain of this warp
         const int r = q4 * 32 + lane;
-        const int et = (warp - 2) * 32 + lane;                // 0..127 among the epilogue threads
-        const uint32_t lane_addr = tmem_base + ((uint32_t)(q4 * 32) << 16);
+        const int et = ((warp - 2) & 3) * 32 + lane;          // 0..127 among the threads of the chain
+        const int bar_id = 1 + ch;
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(q4 * 32) << 16) + ch * p.sub_cols;
+        uint64_t* a_rdy = &a_ready[ch];
+        uint64_t* d_ful = &d_full[ch];
+        float* sE = tables + (size_t)ch * p.tab_floats;       // [Kp][Dp]
+        float* sEE = sE + (size_t)Kp * p.Dp;                  // [Kp]
+        uint32_t* sHist = reinterpret_cast<uint32_t*>(sEE + Kp);   // [2][K]  (count mode)
+        float* sBias = reinterpret_cast<float*>(sHist + 2 * Kp);  // biases of all stages, this variable
         uint32_t dph = 0;
         int cur_g = -1;
         double acc_sq = 0.0, acc_ab = 0.0, acc_vq = 0.0;
         for (int item = item_beg; item < item_end; ++item) {
             const int g = item / p.tiles_m, mt = item - g * p.tiles_m;
-            const int row = mt * CH_TM + r;
+            const int row = (mt * p.nch + ch) * CH_TM + r;
             const bool valid = row < p.B;
             const int rowc = valid ? row : 0;
             // ---- codebook of this variable -> shared memory, |e|^2 in the order every fp32 path uses
             if (g != cur_g) {
-                epi_bar();                                    // everyone has left the previous variable's tables
+                epi_bar(bar_id);                                    // everyone has left the previous variable's tables
                 for (int j = 0; j < p.nst; ++j) {
                     const PgChainStage& S = p.st[j];
                     if (S.bias)
@@ -257,7 +300,7 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ Cha
                     for (int i = et * 4; i < p.K * p.Dp; i += 128 * 4)
                         *reinterpret_cast<float4*>(sE + i) = *reinterpret_cast<const float4*>(eg + i);
                     for (int i = p.K * p.Dp + et; i < Kp * p.Dp; i += 128) sE[i] = 0.f;
-                    epi_bar();
+                    epi_bar(bar_id);
                     for (int k = et; k < Kp; k += 128) {
                         float s2 = 0.f;
                         for (int d = 0; d < p.D; ++d) s2 = fmaf(sE[k * p.Dp + d], sE[k * p.Dp + d], s2);
@@ -265,7 +308,7 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ Cha
                         if (p.mode == PG_CHAIN_ENCODE && p.n1 && k < p.K) { sHist[k] = 0; sHist[p.K + k] = 0; }
                     }
                 }
-                epi_bar();
+                epi_bar(bar_id);
                 cur_g = g;
             }
             // ---- operand of the first stage: this thread's row -> TMEM
@@ -286,7 +329,7 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ Cha
                 tc::tmem_st_wait();
                 tc::fence_before_thread_sync();
                 __syncwarp();
-                if (lane == 0) tc::mbar_arrive(a_ready);
+                if (lane == 0) tc::mbar_arrive(a_rdy);
             }
             float sq = 0.f, ab = 0.f, vq = 0.f;
             for (int j = 0; j < p.nst; ++j) {
@@ -297,7 +340,7 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ Cha
                     load_chunk(S.aux + (long long)g * S.aux_gs + (long long)rowc * S.ldaux, hv, min(32, S.pout));
                 else if (S.kind == PG_CHAIN_EPI_SIGMOID_MSE)
                     load_chunk(p.yf + (long long)rowc * p.ldyf, hv, min(32, S.pout));
-                tc::mbar_wait(d_full, dph);
+                tc::mbar_wait(d_ful, dph);
                 dph ^= 1;
                 tc::fence_after_thread_sync();
                 const bool last = j + 1 == p.nst;
@@ -396,13 +439,13 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ Cha
                     tc::tmem_st_wait();
                     tc::fence_before_thread_sync();
                     __syncwarp();
-                    if (lane == 0) tc::mbar_arrive(a_ready);
+                    if (lane == 0) tc::mbar_arrive(a_rdy);
                 }
             }
             acc_sq += (double)sq; acc_ab += (double)ab; acc_vq += (double)vq;
             // ---- PLL histogram of this item -> global counters
             if (p.mode == PG_CHAIN_ENCODE && p.n1) {
-                epi_bar();
+                epi_bar(bar_id);
                 for (int k = et; k < 2 * p.K; k += 128) {
                     const uint32_t c = sHist[k];
                     if (c) {
@@ -412,7 +455,7 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ Cha
                         atomicAdd(dst, (unsigned long long)c);
                     }
                 }
-                epi_bar();
+                epi_bar(bar_id);
             }
         }
         if (p.acc && p.mode == PG_CHAIN_FWD) {
@@ -443,7 +486,6 @@ int pg_chain_launch(pgmvae_ctx* ctx, cudaStream_t st, const PgChainArgs& a) {
     p.G = a.G; p.g0 = a.g0; p.B = a.B; p.V = a.V; p.Vp = a.Vp; p.D = a.D; p.Dp = a.Dp; p.K = a.K;
     p.vq_stage = a.vq_stage;
     if (a.vq_stage < 0) p.K = 0;          // no codebook tables in shared memory
-    p.tiles_m = (int)pg_cdiv(a.B, CH_TM);
     int regw[2] = {a.a0_cols, 0};
     uint32_t stage_bytes = 0;
     double flops = 0.0, bytes = 0.0;
@@ -474,8 +516,13 @@ int pg_chain_launch(pgmvae_ctx* ctx, cudaStream_t st, const PgChainArgs& a) {
         p.st[j].a_col = (j & 1) ? w0 : 0;
         p.st[j].d_col = (j & 1) ? 0 : w0;
     }
+    p.sub_cols = w0 + w1;
+    p.tiles_real = (int)pg_cdiv(a.B, CH_TM);
+    p.nch = std::max(1, std::min({CH_MAXCH, 512 / std::max(1, p.sub_cols), p.tiles_real}));
+    if (const char* ev = getenv("PGMVAE_CHAINS")) p.nch = std::max(1, std::min(p.nch, atoi(ev)));
+    p.tiles_m = (int)pg_cdiv(p.tiles_real, p.nch);
     p.tmem_cols = 32;
-    while (p.tmem_cols < w0 + w1) p.tmem_cols <<= 1;
+    while (p.tmem_cols < p.nch * p.sub_cols) p.tmem_cols <<= 1;
     p.stage_bytes = stage_bytes;
     p.a0 = a.a0; p.a0_gs = a.a0_gs; p.lda0 = a.lda0; p.a0_cols = a.a0_cols;
     p.yf = a.yf; p.ldyf = a.ldyf; p.y8 = a.y8; p.ldy8 = a.ldy8;
@@ -486,8 +533,8 @@ int pg_chain_launch(pgmvae_ctx* ctx, cudaStream_t st, const PgChainArgs& a) {
     if (a.vq_stage >= 0) { flops += 2.0 * a.G * (double)a.B * a.D * a.K; bytes += 4.0 * a.G * (double)a.K * a.D; }
 
     const size_t Kp = (size_t)((a.K + 3) & ~3);
-    const size_t vq_smem = ((a.vq_stage >= 0 ? Kp * a.Dp + 3 * Kp : 0) + p.nbias + 40) * 4;
-    const size_t smem = 1024 + (size_t)CH_RING * stage_bytes + vq_smem + 512;
+    p.tab_floats = (int)(((a.vq_stage >= 0 ? Kp * a.Dp + 3 * Kp : 0) + p.nbias + 40 + 3) & ~(size_t)3);
+    const size_t smem = 1024 + (size_t)CH_RING * stage_bytes + (size_t)p.nch * p.tab_floats * 4 + 512;
     if (smem > ctx->smem_optin || w0 + w1 > 512) {
         pgmvae_set_error("chain kernel: configuration does not fit (smem %zu, tmem columns %d)", smem, w0 + w1);
         return PGMVAE_EINVAL;
@@ -500,14 +547,12 @@ int pg_chain_launch(pgmvae_ctx* ctx, cudaStream_t st, const PgChainArgs& a) {
         configured[exact] = smem;
     }
     const int items = a.G * p.tiles_m;
-    const int per_sm = std::max(1, std::min(512 / p.tmem_cols, (int)(ctx->smem_optin / smem)));
-    int grid = std::min(items, ctx->sm_count * std::min(per_sm, 2));
-    p.items_per_cta = (int)pg_cdiv(items, grid);
-    grid = (int)pg_cdiv(items, p.items_per_cta);
+    const int grid = std::min(items, ctx->sm_count);        // one CTA per SM, nch chains in flight each
     PG_KERNEL(ctx, st, a.mode == PG_CHAIN_FWD ? "chain_fwd_tc" : (a.mode == PG_CHAIN_ENCODE ? "chain_encode_tc" : "chain_bwd_tc"),
               bytes, flops);
-    if (exact) chain_kernel<true><<<grid, CH_THREADS, smem, st>>>(maps, p);
-    else chain_kernel<false><<<grid, CH_THREADS, smem, st>>>(maps, p);
+    const int threads = 64 + 128 * p.nch;
+    if (exact) chain_kernel<true><<<grid, threads, smem, st>>>(maps, p);
+    else chain_kernel<false><<<grid, threads, smem, st>>>(maps, p);
     PG_LAUNCHED(ctx);
     return PGMVAE_OK;
 }
@@ -528,6 +573,6 @@ bool pg_chain_supported(const int* pin, const int* pout, int nlayers, int Vp, in
     if (Dp > 32) return false;
     size_t nbias = 0;
     for (int l = 0; l < nlayers; ++l) nbias += pout[l];
-    const size_t smem = 1024 + CH_RING * stage + ((size_t)(K + 3) * Dp + 3 * (K + 3) + nbias + 40) * 4 + 512;
-    return smem <= smem_optin && smem <= 112 * 1024;
+    const size_t smem = 1024 + CH_RING * stage + CH_MAXCH * ((size_t)(K + 3) * Dp + 3 * (K + 3) + nbias + 44) * 4 + 512;
+    return smem <= smem_optin;
 }

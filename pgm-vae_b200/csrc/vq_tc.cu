@@ -244,7 +244,10 @@ vq_assign_tc_kernel(const __grid_constant__ CUtensorMap mapZ, const __grid_const
             float zz = 0.f;
             for (int d = 0; d < p.D; ++d) zz = fmaf(zr[d], zr[d], zz);
             const float znorm = sqrtf(zz);
-            const float margin = p.margin_scale * znorm * emax + p.margin_abs * (1.0f + znorm + emax);
+            // 2 eps: operand rounding (relative to |z| |e|) + fp32 accumulation / final-sum rounding, which is
+            // relative to the magnitudes involved -- NOT an absolute constant: at initialisation codes and
+            // latents are ~1e-2 and an absolute 2e-5 made every code a candidate (all rows to the full scan)
+            const float margin = p.margin_scale * znorm * emax + p.margin_abs * (znorm + emax) * (znorm + emax);
             float thr = INFINITY, m = INFINITY;
             int ncand = 0;
             tc::mbar_wait(ee_full, item_n & 1);
@@ -478,7 +481,7 @@ int pg_vq_assign_tc(pgmvae_ctx* ctx, cudaStream_t st, int prec, const float* z, 
     p.flag_count = cnt; p.flag_list = list;
     // 2 eps: tf32 truncates (2^-10 per operand), fp16 rounds to nearest (2^-11 per operand); see header
     p.margin_scale = f16 ? 0.00390625f : 0.0078125f;
-    p.margin_abs = 2e-5f;
+    p.margin_abs = 2e-6f;                              // ~32 ulp of the largest term
     p.dbg = getenv("PGMVAE_VQ_DBG") ? atoi(getenv("PGMVAE_VQ_DBG")) : 0;
 
     PG_CUDA(cudaMemsetAsync(emax, 0, 512, st));       // emax and the flag counter

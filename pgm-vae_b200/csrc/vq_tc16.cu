@@ -259,7 +259,10 @@ vq_assign_f16_kernel(const __grid_constant__ CUtensorMap mapE, const Vq16P p) {
             }
             const float znorm = sqrtf(zz);
             // margins in distance units (d = |z|^2 - 2 s); the scores use half of them
-            const float margin_d = p.margin_scale * znorm * emax + p.margin_abs * (1.0f + znorm + emax);
+            // operand rounding (relative to |z| |e|) + fp32 accumulation (relative to the magnitudes) + fp16
+            // subnormals (|x| < 6e-5 carries an absolute error of 2^-25 per element)
+            const float margin_d = p.margin_scale * znorm * emax + p.margin_abs * (znorm + emax) * (znorm + emax) +
+                                   1.0e-6f * (znorm + emax);
             const float margin = 0.5f * margin_d;
             // the fp16 image must be finite and the codebook representable
             // (|z_d| < 65504; -|e|^2/2 must stay above the -60000 of the padding codes)
@@ -517,7 +520,7 @@ int pg_vq_assign_f16(pgmvae_ctx* ctx, cudaStream_t st, const float* z, int64_t z
     p.flag_count = cnt; p.flag_list = list;
     // 2 eps in distance units: fp16 rounds to nearest (2^-11 per operand) -> |d~ - d| <= 2^-9 |z| |e|
     p.margin_scale = 0.00390625f;
-    p.margin_abs = 2e-5f;
+    p.margin_abs = 2e-6f;
 
     PG_CUDA(cudaMemsetAsync(emax, 0, 512, st));       // emax and the flag counter
     PG_KERNEL(ctx, st, "vq_e_prep", (double)G * K * (4.0 * D + 4.0 + 2.0 * p.KD), 2.0 * G * K * D);

@@ -317,3 +317,31 @@ def test_vq_assign_ema_fused_equals_separate(ctx, G, B, D, K, sub, monkeypatch):
     np.testing.assert_array_equal(cnt.numpy(), cnt_ref.numpy())
     assert cnt.numpy().sum() == G * B
     np.testing.assert_allclose(dw.numpy(), dw_ref.numpy(), rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("scale", [1e-2, 1e-3])
+def test_vq_assign_tensor_core_small_magnitudes(ctx, scale):
+    """Initialisation-like magnitudes (latents and codes ~1e-2): the candidate margin is relative to the
+    magnitudes, so the tensor-core paths must neither lose exactness nor send every row to the full scan."""
+    from pgmvae import _ffi
+    G, B, D, K = 4, 2000, 64, 512
+    rng = np.random.default_rng(17)
+    e = (rng.uniform(-1, 1, (G, K, D)) * scale * 0.5).astype(np.float32)
+    z = (rng.standard_normal((G, B, D)) * scale).astype(np.float32)
+    dz, de = _ffi.DeviceArray.from_numpy(ctx, z), _ffi.DeviceArray.from_numpy(ctx, e)
+    L = _ffi.lib()
+    out = {}
+    for prec in (_ffi.PREC_FP32, _ffi.PREC_TF32, _ffi.PREC_BF16):
+        idx = _ffi.DeviceArray(ctx, (G, B), np.int32)
+        ctx.set_precision(prec)
+        try:
+            _ffi.check(L.pgmvae_vq_assign(ctx.h, None, dz.ptr, B * D, D, de.ptr, K * D, D, idx.ptr, B, None, None, G, B, D, K))
+        finally:
+            ctx.set_precision(_ffi.PREC_FP32)
+        n = C.c_int(0)
+        if prec != _ffi.PREC_FP32:
+            _ffi.check(L.pgmvae_vq_assign_rescored(ctx.h, G, K, C.byref(n)))
+            assert n.value <= G * B // 50, (prec, n.value)
+        out[prec] = idx.numpy()
+    np.testing.assert_array_equal(out[_ffi.PREC_TF32], out[_ffi.PREC_FP32])
+    np.testing.assert_array_equal(out[_ffi.PREC_BF16], out[_ffi.PREC_FP32])
