@@ -322,7 +322,11 @@ static int scatter_launch(pgmvae_ctx* ctx, cudaStream_t st, const float* z, cons
                           int lda, float scale, int G, int B, int D, int K) {
     if (G <= 0 || B <= 0) return PGMVAE_OK;
     const size_t smem = ((size_t)K * D + K) * sizeof(float);
-    const bool use_smem = smem <= 160 * 1024;
+    // CTA-private accumulators only while several CTAs fit an SM; beyond that the shared-memory atomics of one
+    // resident CTA are slower (196 GB/s at K = 512, D = 64) than vector reductions in L2
+    const bool vec_ok = D % 4 == 0 && D <= 128 && ldz % 4 == 0 && lda % 4 == 0 && z_gs % 4 == 0 && a_gs % 4 == 0 &&
+                        !((uintptr_t)z & 15) && !((uintptr_t)acc & 15) && (!q || !((uintptr_t)q & 15));
+    const bool use_smem = smem <= (vec_ok ? 32 : 160) * 1024;
     int rows = use_smem ? max(1024, 4 * K) : 2048;
     // keep at least ~2 CTAs per SM in flight when the problem allows it
     while (rows > 256 && pg_cdiv(B, rows) * G < 2 * ctx->sm_count) rows >>= 1;
@@ -339,8 +343,7 @@ static int scatter_launch(pgmvae_ctx* ctx, cudaStream_t st, const float* z, cons
         }
         scatter_rows_kernel<MODE, true><<<grid, 256, smem, st>>>(z, q, z_gs, ldz, idx, idx_gs, cnt, c_gs, acc, a_gs,
                                                                  lda, scale, B, D, K, rows);
-    } else if (D % 4 == 0 && D <= 128 && ldz % 4 == 0 && lda % 4 == 0 && z_gs % 4 == 0 && a_gs % 4 == 0 &&
-               !((uintptr_t)z & 15) && !((uintptr_t)acc & 15) && (!q || !((uintptr_t)q & 15))) {
+    } else if (vec_ok) {
         int lpr = 1;
         while (lpr < D / 4) lpr <<= 1;                       // lanes per row: power of two >= D / 4
         int per_sm = 8;

@@ -152,6 +152,14 @@ class Context:
         self.h = _vp()
         check(lib().pgmvae_ctx_create(int(device), C.byref(self.h)))
         self.device = device
+        # PGMVAE_PRECISION = fp32 | tf32 | bf16 selects the arithmetic of the GEMM-shaped kernels for this process
+        # (default: the library's exact-fp32 CUDA-core path; run.py asks for tf32 unless told otherwise)
+        prec = os.environ.get("PGMVAE_PRECISION", "").lower()
+        if prec:
+            table = {"fp32": PREC_FP32, "tf32": PREC_TF32, "bf16": PREC_BF16, "f16": PREC_BF16}
+            if prec not in table:
+                raise PgmvaeError(f"PGMVAE_PRECISION={prec!r}: expected fp32, tf32 or bf16")
+            self.set_precision(table[prec])
 
     def sync(self):
         check(lib().pgmvae_ctx_sync(self.h))

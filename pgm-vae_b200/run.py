@@ -52,6 +52,9 @@ def main(argv=None):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if world > 1:
         device = int(os.environ.get("LOCAL_RANK", device))
+    # tensor-core arithmetic (tf32 operands, fp32 accumulation; within the 1e-3 parity bar) unless the
+    # environment asks for the exact-fp32 CUDA-core path: PGMVAE_PRECISION=fp32
+    os.environ.setdefault("PGMVAE_PRECISION", "tf32")
     ctx = _ffi.get_context(device)
     comm, rank, world = dist.init_from_env(ctx)
 
