@@ -91,6 +91,10 @@ struct pgmvae_model {
     // data-parallel overlap: all-reduces run on their own stream behind events of the compute stream
     cudaStream_t comm_stream = nullptr;
     cudaEvent_t ev_compute = nullptr, ev_comm = nullptr;
+    // the ten wgrad launches of a step are independent of each other: they are spread over three streams so that
+    // the tail of one overlaps the head of the next
+    cudaStream_t aux_stream[2] = {nullptr, nullptr};
+    cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
 
     float* E() const { return params + e_off; }
     float* dE() const { return grads + e_off; }
@@ -410,6 +414,11 @@ int pgmvae_model_destroy(pgmvae_model* m) {
     for (void* p : m->allocs) cudaFree(p);
     if (m->acc_host) cudaFreeHost(m->acc_host);
     if (m->comm_stream) cudaStreamDestroy(m->comm_stream);
+    for (int i = 0; i < 2; ++i) {
+        if (m->aux_stream[i]) cudaStreamDestroy(m->aux_stream[i]);
+        if (m->ev_join[i]) cudaEventDestroy(m->ev_join[i]);
+    }
+    if (m->ev_fork) cudaEventDestroy(m->ev_fork);
     if (m->ev_compute) cudaEventDestroy(m->ev_compute);
     if (m->ev_comm) cudaEventDestroy(m->ev_comm);
     delete m;
@@ -598,21 +607,38 @@ int run_step(pgmvae_model* m, const uint8_t* y, int y_on_device, int B, int glob
             a.z = m->H[4]; a.qv = m->q; a.cscale = cscale;
             PG_TRY(pg_chain_launch(ctx, st, a));
         }
+        if (!m->aux_stream[0]) {
+            for (int i = 0; i < 2; ++i) {
+                PG_CUDA(cudaStreamCreateWithFlags(&m->aux_stream[i], cudaStreamNonBlocking));
+                PG_CUDA(cudaEventCreateWithFlags(&m->ev_join[i], cudaEventDisableTiming));
+            }
+            PG_CUDA(cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming));
+        }
+        PG_CUDA(cudaEventRecord(m->ev_fork, st));                 // the backward chain has been issued
+        for (int i = 0; i < 2; ++i) PG_CUDA(cudaStreamWaitEvent(m->aux_stream[i], m->ev_fork, 0));
         size_t bucket_end = m->n_dense;
         for (int l = 9; l >= 0; --l) {
             const Layer& L = m->L[l];
             const float* x = l == 0 ? m->yf : (l == 5 ? m->st : m->H[l - 1]);
             const int ldx = l == 0 ? m->Vp : (l == 5 ? Dp : m->L[l - 1].pout);
             const int64_t x_gs = l == 0 ? 0 : MB * ldx;
-            PG_TRY(pgmvae_dense_wgrad(ctx, st, x, x_gs, ldx, m->Gd[l], MB * L.pout, L.pout,
+            // (the per-kernel profiler wants every launch alone on the compute stream)
+            cudaStream_t ws = (ctx->profiling || (9 - l) % 3 == 0) ? st : m->aux_stream[(9 - l) % 3 - 1];
+            PG_TRY(pgmvae_dense_wgrad(ctx, ws, x, x_gs, ldx, m->Gd[l], MB * L.pout, L.pout,
                                       m->grads + L.w_off + (size_t)g0 * L.pin * L.pout, (int64_t)L.pin * L.pout, L.pout,
                                       m->grads + L.b_off + (size_t)g0 * L.pout, L.pout, Gn, B, L.in, L.out,
                                       l == 0 ? g0 : -1));
             // gradients leave in three buckets (layers 9-7, 6-4, 3-0; parameters are laid out in layer order),
             // each as soon as its last wgrad is issued: few launches, and only the last bucket is exposed
-            if (overlap && (l == 7 || l == 4 || l == 0)) {
-                PG_TRY(overlapped_allreduce(m, comm, m->grads + L.w_off, (int64_t)(bucket_end - L.w_off), 0));
-                bucket_end = L.w_off;
+            if (l == 0 || (overlap && (l == 7 || l == 4))) {
+                for (int i = 0; i < 2; ++i) {                     // join the side streams into the compute stream
+                    PG_CUDA(cudaEventRecord(m->ev_join[i], m->aux_stream[i]));
+                    PG_CUDA(cudaStreamWaitEvent(st, m->ev_join[i], 0));
+                }
+                if (overlap) {
+                    PG_TRY(overlapped_allreduce(m, comm, m->grads + L.w_off, (int64_t)(bucket_end - L.w_off), 0));
+                    bucket_end = L.w_off;
+                }
             }
         }
         if (overlap && !m->ema)
