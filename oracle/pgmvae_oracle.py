@@ -368,6 +368,13 @@ class OracleVqVAE:
         prb = self.dist.index_select(0, fts).to(F32)
         return torch.gather(prb, 1, enc_idx)
 
+    def conditional_marginal_log_likelihood(self, x, p1, num_smp, burn_in, verbose=False, uniform=None):
+        """core/model.py:110-148."""
+        rng = np.random.default_rng(0)
+        uni = uniform if uniform is not None else (lambda shape: rng.random(shape, dtype=np.float32))
+        gp = lambda xs, fts: self.get_probability(torch.from_numpy(np.ascontiguousarray(xs)), fts).numpy()
+        return gibbs_cmll(gp, x, p1, num_smp, burn_in, uni, verbose)
+
     # -- helpers for tests -------------------------------------------------- #
     def state_numpy(self) -> Dict[str, np.ndarray]:
         out = {n: t.detach().numpy().copy() for n, t in self.p.items()}
@@ -378,6 +385,41 @@ class OracleVqVAE:
                         "vq.biased_c": st.biased_c.numpy().copy(),
                         "vq.biased_w": st.biased_w.numpy().copy()})
         return out
+
+
+# --------------------------------------------------------------------------- #
+# Gibbs-sampling conditional marginal log-likelihood (core/model.py:110-148)
+# --------------------------------------------------------------------------- #
+def gibbs_cmll(get_probability, x, p1, num_smp, burn_in, uniform, verbose=False):
+    """Block Gibbs sampler of the reference (core/model.py:110-148), framework-free.
+
+    get_probability(xs [F,B,V-1], fts [F]) -> p(y=1) [F,B];  uniform(shape) -> U[0,1) draws (the reference uses
+    tf.random.uniform, whose stream cannot be reproduced without TensorFlow; parity runs inject the draws).
+    Keeps the reference's quirks: the counter starts at i > burn_in * p1 (strict), every block sweeps its own
+    variables with period vol[b], and the last block's denominator is valid * p1 // vol[-1]."""
+    x = np.asarray(x, dtype=np.float32)
+    batch_size, dim = x.shape
+    blocks = int(np.ceil(dim / p1))                                        # :123
+    vol = np.array([p1] * (blocks - 1) + [dim - p1 * (blocks - 1)])        # :124
+    marker = np.arange(blocks) * p1                                        # :126
+    state = np.tile(x[None], (blocks, 1, 1))                               # :127
+    cnt = np.zeros_like(x)                                                 # :128
+    for i in range(num_smp * p1):                                          # :132
+        y = marker + np.mod(i, vol)                                        # :133
+        xs = np.stack([np.delete(state[b], y[b], axis=1) for b in range(blocks)])   # :134-136
+        prb = np.asarray(get_probability(xs, y), dtype=np.float32)         # :137
+        gibbs = (np.asarray(uniform((blocks, batch_size)), dtype=np.float32) < prb).astype(np.float32)   # :138
+        for b in range(blocks):
+            state[b, :, y[b]] = gibbs[b]                                   # :139
+            if i > burn_in * p1:
+                cnt[:, y[b]] += gibbs[b]                                   # :140-141
+        if verbose:
+            print(f"# of samples: {i // p1}, component: {y[0]}")
+    valid = num_smp - burn_in                                              # :146
+    valid_end = np.float32(valid * p1) // np.float32(vol[-1])              # :147
+    den = np.concatenate([np.full(dim - vol[-1], valid, np.float32), np.full(vol[-1], valid_end, np.float32)])
+    cmll = cnt / den[None, :]                                              # :148
+    return float(np.sum(x * np.log(cmll + 1e-5) + (1 - x) * np.log(1 - cmll + 1e-5)) / batch_size)   # :149
 
 
 # --------------------------------------------------------------------------- #

@@ -332,9 +332,14 @@ class VqVAE:
         prb = self.dist[fts].astype(np.float32)
         return np.take_along_axis(prb, enc_idx, axis=1)
 
-    def conditional_marginal_log_likelihood(self, x, p1, num_smp, burn_in, verbose=True):
-        raise NotImplementedError("Gibbs-sampling CMLL (reference core/model.py:110-148) is outside the hot path "
-                                  "(its call is commented out at run.py:74); see SURVEY.md 8(f)")
+    def conditional_marginal_log_likelihood(self, x, p1, num_smp, burn_in, verbose=True, uniform=None):
+        """Conditional marginal log-likelihood by block Gibbs sampling (reference core/model.py:110-148; intended
+        call at run.py:74: ``p1=n_var//10, num_smp=3000, burn_in=150``).  Every sweep step evaluates the selected
+        sub-nets on the device (``get_probability`` -> fts path of every layer + VQ assignment); the sampler state
+        lives on the host.  ``uniform(shape)`` supplies the U[0,1) draws (default: numpy generator seeded by run.py's
+        ``np.random.seed``); the reference's tf.random stream cannot be reproduced without TensorFlow."""
+        uni = uniform if uniform is not None else (lambda shape: np.random.random_sample(shape).astype(np.float32))
+        return _gibbs_cmll(self.get_probability, to_y_float(x), p1, num_smp, burn_in, uni, verbose)
 
     def device_bytes(self) -> int:
         return int(_ffi.lib().pgmvae_model_device_bytes(self._h))
@@ -352,3 +357,40 @@ class VqVAE:
                 _ffi.lib().pgmvae_model_destroy(self._h)
         except Exception:
             pass
+
+
+def to_y_float(x):
+    """[B,V] data as float32 (accepts uint8 / float arrays)."""
+    return np.ascontiguousarray(np.asarray(x), dtype=np.float32)
+
+
+def _gibbs_cmll(get_probability, x, p1, num_smp, burn_in, uniform, verbose=False):
+    """Block Gibbs sampler of the reference (core/model.py:110-148), framework-free.
+
+    get_probability(xs [F,B,V-1], fts [F]) -> p(y=1) [F,B];  uniform(shape) -> U[0,1) draws (the reference uses
+    tf.random.uniform, whose stream cannot be reproduced without TensorFlow; parity runs inject the draws).
+    Keeps the reference's quirks: the counter starts at i > burn_in * p1 (strict), every block sweeps its own
+    variables with period vol[b], and the last block's denominator is valid * p1 // vol[-1]."""
+    x = np.asarray(x, dtype=np.float32)
+    batch_size, dim = x.shape
+    blocks = int(np.ceil(dim / p1))                                        # :123
+    vol = np.array([p1] * (blocks - 1) + [dim - p1 * (blocks - 1)])        # :124
+    marker = np.arange(blocks) * p1                                        # :126
+    state = np.tile(x[None], (blocks, 1, 1))                               # :127
+    cnt = np.zeros_like(x)                                                 # :128
+    for i in range(num_smp * p1):                                          # :132
+        y = marker + np.mod(i, vol)                                        # :133
+        xs = np.stack([np.delete(state[b], y[b], axis=1) for b in range(blocks)])   # :134-136
+        prb = np.asarray(get_probability(xs, y), dtype=np.float32)         # :137
+        gibbs = (np.asarray(uniform((blocks, batch_size)), dtype=np.float32) < prb).astype(np.float32)   # :138
+        for b in range(blocks):
+            state[b, :, y[b]] = gibbs[b]                                   # :139
+            if i > burn_in * p1:
+                cnt[:, y[b]] += gibbs[b]                                   # :140-141
+        if verbose:
+            print(f"# of samples: {i // p1}, component: {y[0]}")
+    valid = num_smp - burn_in                                              # :146
+    valid_end = np.float32(valid * p1) // np.float32(vol[-1])              # :147
+    den = np.concatenate([np.full(dim - vol[-1], valid, np.float32), np.full(vol[-1], valid_end, np.float32)])
+    cmll = cnt / den[None, :]                                              # :148
+    return float(np.sum(x * np.log(cmll + 1e-5) + (1 - x) * np.log(1 - cmll + 1e-5)) / batch_size)   # :149

@@ -189,3 +189,26 @@ def test_run_py_nltcs_end_to_end(ctx, tmp_path):
     vals = {k: float(v) for k, v in (t.split(":") for t in line.split(" ")[1:])}
     for k in ("pll-train", "pll-valid", "pll-test"):
         assert -16 * np.log(2) < vals[k] < -3.0
+
+
+def test_gibbs_cmll_matches_oracle(ctx):
+    """conditional_marginal_log_likelihood (reference core/model.py:110-148) with the same injected uniform draws:
+    the device sub-net path (get_probability) against the oracle."""
+    from core.model import VqVAE
+    units, V, D, K, N = [15, 14, 13, 12], 16, 4, 32, 512
+    params = {k: v.numpy() for k, v in O.init_params(units, V, D, K, seed=3).items()}
+    y = O.synthetic_binary(N, V, seed=4)
+    m = VqVAE(units, V, D, K, cost=0.25, decay=0.99, ema=True, max_batch=N)
+    m.set_weights_from(params)
+    om = O.OracleVqVAE(units, V, D, K, cost=0.25, decay=0.99, ema=True,
+                       params={k: torch.from_numpy(v) for k, v in params.items()})
+    m.dist = m.cpt(y)
+    om.dist = om.cpt(O.make_xs(y), y)
+    xt = y[:24].astype(np.float32)
+    draws = np.random.default_rng(9).random((200, 6, 24), dtype=np.float32)
+    def source():
+        it = iter(draws)
+        return lambda shape: next(it)[:shape[0], :shape[1]]
+    got = m.conditional_marginal_log_likelihood(xt, 3, 10, 2, verbose=False, uniform=source())
+    exp = om.conditional_marginal_log_likelihood(xt, 3, 10, 2, verbose=False, uniform=source())
+    assert np.isfinite(got) and abs(got - exp) <= 2e-2 * abs(exp), (got, exp)

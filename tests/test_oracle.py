@@ -165,3 +165,20 @@ def test_adam_matches_torch_formula():
     alpha = 1e-2 * np.sqrt(1 - 0.999) / (1 - 0.9)
     exp = p0 - alpha * mm / (vv.sqrt() + 1e-7)
     np.testing.assert_allclose(m.p["fd2.kernel"].detach().numpy(), exp.numpy(), rtol=1e-5, atol=1e-7)
+
+
+def test_gibbs_cmll_known_answer():
+    """core/model.py:110-148 on a case small enough to do by hand: dim 3, p1 2 -> blocks [0,1] and [2];
+    6 sweep steps, the counter runs for i > burn_in * p1 = 2; every draw yields 1 -> counts (1, 2, 3) over
+    denominators (2, 2, 4)."""
+    x = np.array([[1, 0, 1]], dtype=np.float32)
+    got = O.gibbs_cmll(lambda xs, fts: np.ones(xs.shape[:2], np.float32), x, 2, 3, 1, lambda sh: np.zeros(sh, np.float32))
+    exp = np.log(0.5 + 1e-5) + np.log(1 - 1.0 + 1e-5) + np.log(0.75 + 1e-5)
+    assert abs(got - exp) < 1e-5
+    # the product's host-side sampler is the same statement
+    import importlib.util, os, sys
+    pkg = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "pgm-vae_b200")
+    sys.path.insert(0, pkg)
+    from core.model import _gibbs_cmll
+    assert _gibbs_cmll(lambda xs, fts: np.ones(xs.shape[:2], np.float32), x, 2, 3, 1,
+                       lambda sh: np.zeros(sh, np.float32)) == got
