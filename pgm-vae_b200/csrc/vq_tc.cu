@@ -10,8 +10,8 @@
 //                              epilogue of code tile t
 //   warp 0 TMA producer | warp 1 MMA issuer (one thread) | warp 2 TMEM allocator |
 //   warps 4-11 epilogue, one sample row per thread (tcgen05.ld 32x32b: lane == row)
-// Operands: kind::tf32 directly on the fp32 data as it lies in HBM, or kind::f16 on an fp16
-// copy made by a conversion pre-pass (half the bytes, twice the MMA rate, 2x tighter bound).
+// Operands: kind::tf32 directly on the fp32 data as it lies in HBM (no copy, no conversion pass).
+// The fp16 flavour lives in vq_tc16.cu (single pass, z operand in tensor memory).
 //
 // Exactness.  Low-precision products only PROPOSE candidates; fp32 decides.  With
 // eps = 2^-8 |z| max|e| (tf32, truncation) or 2^-9 |z| max|e| (fp16, round-to-nearest) bounding
@@ -22,7 +22,6 @@
 // exactly the fp32 arithmetic of the CUDA-core kernel, lowest index on ties, so the indices
 // are those of the fp32 path.  Rows with more candidates than the list holds (many identical
 // dead codes) go to vq_rescore_kernel, an exact full scan.
-#include <cuda_fp16.h>
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -76,18 +75,6 @@ __global__ void enorm_kernel(const float* __restrict__ e, long long e_gs, int ld
     if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<int*>(emax), __float_as_int(m));   // m >= 0
 }
 
-// fp32 -> fp16 copy with the row padded to ld16 halves (zero fill)
-__global__ void to_half_kernel(const float* __restrict__ src, long long src_gs, int lds, __half* __restrict__ dst,
-                               int rows, int D, int ld16, int G) {
-    const long long n = (long long)G * rows * ld16;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        const int c = (int)(i % ld16);
-        const long long t = i / ld16;
-        const int r = (int)(t % rows), g = (int)(t / rows);
-        dst[i] = c < D ? __float2half_rn(src[(long long)g * src_gs + (long long)r * lds + c]) : __half(0.f);
-    }
-}
-
 // minimum of d' = ee - 2 z.e over one 32-column chunk (four independent chains for ILP)
 __device__ __forceinline__ float chunk_min(const float (&v)[32], const float* __restrict__ see) {
     float m0 = INFINITY, m1 = INFINITY, m2 = INFINITY, m3 = INFINITY;
@@ -102,13 +89,12 @@ __device__ __forceinline__ float chunk_min(const float (&v)[32], const float* __
     return fminf(fminf(m0, m1), fminf(m2, m3));
 }
 
-template <bool F16>
 __global__ void __launch_bounds__(128 + EPI_THREADS, 1)
 vq_assign_tc_kernel(const __grid_constant__ CUtensorMap mapZ, const __grid_constant__ CUtensorMap mapE,
                     const VqTcParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-byte aligned, still a shared-space pointer
-    constexpr int KB_ELEMS = F16 ? 64 : 32;           // elements per 128-byte k-block
+    constexpr int KB_ELEMS = 32;                      // fp32 elements per 128-byte k-block
     const int b_tile_bytes = p.BN * KB_BYTES;
     uint8_t* sA = smem;                                               // [SUB][kblocks][16 KB]
     uint8_t* sB = sA + (size_t)SUB * p.kblocks * A_TILE_BYTES;        // [stages][kblocks][BN*128]
@@ -193,7 +179,7 @@ vq_assign_tc_kernel(const __grid_constant__ CUtensorMap mapZ, const __grid_const
         }
     } else if (warp == 1) {
         // ===================== MMA issuer (warp-uniform loop, one elected lane issues) =====================
-        const uint32_t idesc = tc::make_idesc(F16 ? 0 : 2, TM, p.BN, 0, 0);
+        const uint32_t idesc = tc::make_idesc(2, TM, p.BN, 0, 0);
         // Descriptors differ only in the 14-bit start-address field (units of 16 bytes).
         const uint64_t descA0 = tc::make_smem_desc(tc::smem_u32(sA), 16, 1024);
         const uint64_t descB0 = tc::make_smem_desc(tc::smem_u32(sB), 16, 1024);
@@ -216,8 +202,7 @@ vq_assign_tc_kernel(const __grid_constant__ CUtensorMap mapZ, const __grid_const
                         for (int ks = 0; ks < p.ksteps; ++ks) {
                             const uint32_t offA = (uint32_t)((ks >> 2) * A_TILE_BYTES + (ks & 3) * 32) >> 4;
                             const uint32_t offB = (uint32_t)((ks >> 2) * b_tile_bytes + (ks & 3) * 32) >> 4;
-                            if (F16) tc::mma_f16(d_tmem, descA + offA, descB + offB, idesc, ks > 0 ? 1u : 0u);
-                            else tc::mma_tf32(d_tmem, descA + offA, descB + offB, idesc, ks > 0 ? 1u : 0u);
+                            tc::mma_tf32(d_tmem, descA + offA, descB + offB, idesc, ks > 0 ? 1u : 0u);
                         }
                     }
                     tc::mma_commit(&b_empty[s]);      // smem stage free once these MMAs have read it
@@ -426,37 +411,32 @@ static int ensure_scratch(pgmvae_ctx* ctx, size_t bytes) {
 
 bool pg_vq_assign_tc_supported(int prec, int D, int K, int ldz, int lde, const float* z, const float* e, int64_t z_gs,
                                int64_t e_gs) {
+    if (prec != PGMVAE_PREC_TF32) return false;
     if (K < 1 || K > 8192) return false;                  // |e|^2 of one group is staged in shared memory
-    if (prec == PGMVAE_PREC_TF32) {
-        if (D > 64) return false;                         // two 128-byte k-blocks of fp32
-        if (((uintptr_t)z & 15) || ((uintptr_t)e & 15) || ldz % 4 || lde % 4 || z_gs % 4 || e_gs % 4) return false;
-        return true;
-    }
-    return D <= 128;                                      // fp16 copy: any source layout
+    if (D > 64) return false;                             // two 128-byte k-blocks of fp32
+    return !(((uintptr_t)z & 15) || ((uintptr_t)e & 15) || ldz % 4 || lde % 4 || z_gs % 4 || e_gs % 4);
 }
 
-template <bool F16>
 static int launch_vq_tc(pgmvae_ctx* ctx, cudaStream_t st, const CUtensorMap& mapZ, const CUtensorMap& mapE,
                         const VqTcParams& p, size_t smem, int grid) {
     static size_t configured = 0;
     if (smem > configured) {
-        PG_CUDA(cudaFuncSetAttribute(vq_assign_tc_kernel<F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PG_CUDA(cudaFuncSetAttribute(vq_assign_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
-    vq_assign_tc_kernel<F16><<<grid, 128 + EPI_THREADS, smem, st>>>(mapZ, mapE, p);
+    vq_assign_tc_kernel<<<grid, 128 + EPI_THREADS, smem, st>>>(mapZ, mapE, p);
     return PGMVAE_OK;
 }
 
 int pg_vq_assign_tc(pgmvae_ctx* ctx, cudaStream_t st, int prec, const float* z, int64_t z_gs, int ldz, const float* e,
                     int64_t e_gs, int lde, int32_t* idx, int64_t idx_gs, float* best_opt, float* gap_opt, int G, int B,
                     int D, int K) {
+    (void)prec;                                               // tf32 only; the fp16 path is pg_vq_assign_f16
     if (G <= 0 || B <= 0) return PGMVAE_OK;
-    const bool f16 = prec != PGMVAE_PREC_TF32;
-    const int esize = f16 ? 2 : 4;
     VqTcParams p{};
     p.G = G; p.B = B; p.D = D; p.K = K;
-    p.ksteps = (int)pg_cdiv((int64_t)D * esize, 32);          // one MMA consumes 32 bytes of K
-    p.kblocks = (int)pg_cdiv((int64_t)D * esize, KB_BYTES);
+    p.ksteps = (int)pg_cdiv((int64_t)D * 4, 32);              // one MMA consumes 32 bytes of K
+    p.kblocks = (int)pg_cdiv((int64_t)D * 4, KB_BYTES);
     p.BN = 128;
     if (K < p.BN) p.BN = pg_round_up(K, 32);                  // UMMA N % 16 == 0; the epilogue reads 32-column chunks
     p.tmem_cols = 32;
@@ -464,11 +444,8 @@ int pg_vq_assign_tc(pgmvae_ctx* ctx, cudaStream_t st, int prec, const float* z, 
     p.tiles_m = (int)pg_cdiv(B, TMR);
     p.tiles_n = (int)pg_cdiv(K, p.BN);
     p.Kpad = p.tiles_n * p.BN;
-    const int ld16 = pg_round_up(D, 8);
     const size_t off_ee = 0, off_emax = align256((size_t)G * p.Kpad * 4), off_cnt = off_emax + 256,
-                 off_list = off_cnt + 256, off_e16 = align256(off_list + (size_t)G * B * sizeof(int2)),
-                 off_z16 = align256(off_e16 + (f16 ? (size_t)G * K * ld16 * 2 : 0)),
-                 total = off_z16 + (f16 ? (size_t)G * B * ld16 * 2 : 0);
+                 off_list = off_cnt + 256, total = align256(off_list + (size_t)G * B * sizeof(int2));
     PG_TRY(ensure_scratch(ctx, total));
     ctx->vq_cnt_off = off_cnt;
     uint8_t* sc = (uint8_t*)ctx->scratch;
@@ -479,8 +456,8 @@ int pg_vq_assign_tc(pgmvae_ctx* ctx, cudaStream_t st, int prec, const float* z, 
     p.z = z; p.z_gs = z_gs; p.ldz = ldz; p.e = e; p.e_gs = e_gs; p.lde = lde; p.ee = ee; p.emax = emax;
     p.idx = idx; p.idx_gs = idx_gs; p.best = best_opt; p.gap = gap_opt;
     p.flag_count = cnt; p.flag_list = list;
-    // 2 eps: tf32 truncates (2^-10 per operand), fp16 rounds to nearest (2^-11 per operand); see header
-    p.margin_scale = f16 ? 0.00390625f : 0.0078125f;
+    // 2 eps: tf32 operands are read by truncation (2^-10 per operand); see header
+    p.margin_scale = 0.0078125f;
     p.margin_abs = 2e-6f;                              // ~32 ulp of the largest term
     p.dbg = getenv("PGMVAE_VQ_DBG") ? atoi(getenv("PGMVAE_VQ_DBG")) : 0;
 
@@ -490,22 +467,9 @@ int pg_vq_assign_tc(pgmvae_ctx* ctx, cudaStream_t st, int prec, const float* z, 
     PG_LAUNCHED(ctx);
 
     CUtensorMap mapZ, mapE;
-    if (f16) {
-        __half* e16 = (__half*)(sc + off_e16);
-        __half* z16 = (__half*)(sc + off_z16);
-        PG_KERNEL(ctx, st, "vq_to_half", 6.0 * ((double)G * B * D + (double)G * K * D), 0.0);
-        to_half_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(e, e_gs, lde, e16, K, D, ld16, G);
-        to_half_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(z, z_gs, ldz, z16, B, D, ld16, G);
-        ctx->launches++;
-        PG_LAUNCHED(ctx);
-        PG_TRY(tc::make_map(&mapZ, z16, 2, (uint64_t)D, (uint64_t)B, (uint64_t)G, (uint64_t)ld16, (uint64_t)B * ld16, 64, TM));
-        PG_TRY(tc::make_map(&mapE, e16, 2, (uint64_t)D, (uint64_t)K, (uint64_t)G, (uint64_t)ld16, (uint64_t)K * ld16, 64,
-                            (uint32_t)p.BN));
-    } else {
-        PG_TRY(tc::make_map(&mapZ, z, 4, (uint64_t)D, (uint64_t)B, (uint64_t)G, (uint64_t)ldz, (uint64_t)z_gs, 32, TM));
-        PG_TRY(tc::make_map(&mapE, e, 4, (uint64_t)D, (uint64_t)K, (uint64_t)G, (uint64_t)lde, (uint64_t)e_gs, 32,
-                            (uint32_t)p.BN));
-    }
+    PG_TRY(tc::make_map(&mapZ, z, 4, (uint64_t)D, (uint64_t)B, (uint64_t)G, (uint64_t)ldz, (uint64_t)z_gs, 32, TM));
+    PG_TRY(tc::make_map(&mapE, e, 4, (uint64_t)D, (uint64_t)K, (uint64_t)G, (uint64_t)lde, (uint64_t)e_gs, 32,
+                        (uint32_t)p.BN));
     // smem: A [SUB][kblocks] | B ring | ee | candidates | barriers
     const size_t fixed = 1024 + (size_t)SUB * p.kblocks * A_TILE_BYTES + (size_t)p.Kpad * 4 +
                          (size_t)TMR * CAND_CAP * 4 + 256;
@@ -519,10 +483,9 @@ int pg_vq_assign_tc(pgmvae_ctx* ctx, cudaStream_t st, int prec, const float* z, 
     }
     const int items = G * p.tiles_m;
     const int grid = items < ctx->sm_count ? items : ctx->sm_count;
-    PG_KERNEL(ctx, st, f16 ? "vq_assign_tc_f16" : "vq_assign_tc_tf32",
-              4.0 * ((double)G * B * D + (double)G * K * D + (double)G * B), 2.0 * G * B * (double)D * K);
-    if (f16) PG_TRY(launch_vq_tc<true>(ctx, st, mapZ, mapE, p, smem, grid));
-    else PG_TRY(launch_vq_tc<false>(ctx, st, mapZ, mapE, p, smem, grid));
+    PG_KERNEL(ctx, st, "vq_assign_tc_tf32", 4.0 * ((double)G * B * D + (double)G * K * D + (double)G * B),
+              2.0 * G * B * (double)D * K);
+    PG_TRY(launch_vq_tc(ctx, st, mapZ, mapE, p, smem, grid));
     PG_LAUNCHED(ctx);
 
     PG_KERNEL(ctx, st, "vq_rescore_fp32", 0.0, 0.0);
