@@ -169,7 +169,8 @@ def test_dgrad_wgrad_operators_tensor_core_vs_fp32(ctx, G, B, fin, fout):
 
 
 @pytest.mark.parametrize("V,units,D,K,B,ema", [(16, [15, 14, 13, 12], 4, 32, 256, True), (69, [50, 40, 30, 20], 16, 128, 1000, True),
-                                               (69, [50, 40, 30, 20], 16, 128, 515, False), (9, [70, 33, 9, 20], 8, 50, 77, True)])
+                                               (69, [50, 40, 30, 20], 16, 128, 515, False), (9, [70, 33, 9, 20], 8, 50, 77, True),
+                                               (5, [6, 5, 4, 3], 3, 7, 1, True), (4, [120, 9, 64, 8], 30, 33, 385, False)])
 @pytest.mark.parametrize("exact", [True, False])
 def test_chain_kernels_equal_layer_by_layer_kernels(ctx, monkeypatch, V, units, D, K, B, ema, exact):
     """The TMEM-resident chain kernels (forward, backward, encode + histogram) against the layer-by-layer
