@@ -43,7 +43,7 @@ constexpr int A_COLS = 128;                   // TMEM columns reserved for the z
 
 template <int SUB>
 struct Cfg {
-    static constexpr int BN = SUB == 2 ? 96 : 64;          // codes per tile: 128 + 2*SUB*BN == 512 columns
+    static constexpr int BN = 64;                          // codes per tile: 128 + 2*SUB*BN <= 512 columns; two chunks
     static constexpr int NCH = BN / 32;                    // 32-column chunks per tile
     static constexpr int TMR = TM * SUB;                   // rows per CTA row tile
     static constexpr int EPI_WARPS = 4 * SUB;
@@ -270,28 +270,8 @@ vq_assign_f16_kernel(const __grid_constant__ CUtensorMap mapE, const Vq16P p) {
             float runmax = -INFINITY, thr = -INFINITY, evmax = -INFINITY;
             int cnt = 0;
 
-            const int nchunks = p.tiles_n * C::NCH;
+            static_assert(C::NCH == 2, "the epilogue pipeline below is written for two 32-column chunks per tile");
             const uint32_t acc_addr = lane_addr + A_COLS + sub * C::BN;
-            int ld_tile = 0, ld_c = 0;                           // next chunk to load
-            int rt_c = 0;  uint32_t rt_it = it;                  // next chunk to retire
-            auto issue = [&](float (&buf)[32]) {
-                const uint32_t git = it + ld_tile, ab = git & 1;
-                if (ld_c == 0) {
-                    tc::mbar_wait(&acc_full[ab], (git >> 1) & 1);
-                    tc::fence_after_thread_sync();
-                }
-                tc::tmem_ld_32x32(acc_addr + ab * SUB * C::BN + ld_c * 32, buf);
-                if (++ld_c == C::NCH) { ld_c = 0; ++ld_tile; }
-            };
-            auto retire = [&]() {                                // after wait::ld: the chunk is in registers
-                if (++rt_c == C::NCH) {
-                    rt_c = 0;
-                    tc::fence_before_thread_sync();
-                    __syncwarp();
-                    if (lane == 0) tc::mbar_arrive(&acc_empty[rt_it & 1]);
-                    ++rt_it;
-                }
-            };
             auto consume = [&](const float (&v)[32], int n) {
                 // maxima of the four 8-code groups and of the chunk: 18 instructions for 32 scores
                 float gm[4];
@@ -324,19 +304,33 @@ vq_assign_f16_kernel(const __grid_constant__ CUtensorMap mapE, const Vq16P p) {
                     }
                 }
             };
+            // Straight-line pipeline over (tile, chunk): the load of the next chunk -- also across tile boundaries --
+            // is in flight while the current one is reduced; an accumulator buffer goes back to the MMA warp as
+            // soon as its second chunk sits in registers.  (A first version drove this with generic
+            // issue/retire counters: ~40 of its ~128 instructions per chunk were loop bookkeeping.)
             float va[32], vb[32];
-            issue(va);
-            for (int n = 0; n < nchunks; n += 2) {
+            {
+                const uint32_t ab = it & 1;
+                tc::mbar_wait(&acc_full[ab], (it >> 1) & 1);
+                tc::fence_after_thread_sync();
+                tc::tmem_ld_32x32(acc_addr + ab * SUB * C::BN, va);
+            }
+            for (int t = 0; t < p.tiles_n; ++t) {
+                const uint32_t git = it + t, ab = git & 1;
                 tc::tmem_ld_wait(va);
-                retire();
-                if (n + 1 < nchunks) issue(vb);
-                consume(va, n);
-                if (n + 1 < nchunks) {
-                    tc::tmem_ld_wait(vb);
-                    retire();
-                    if (n + 2 < nchunks) issue(va);
-                    consume(vb, n + 1);
+                tc::tmem_ld_32x32(acc_addr + ab * SUB * C::BN + 32, vb);
+                consume(va, 2 * t);
+                tc::tmem_ld_wait(vb);
+                tc::fence_before_thread_sync();
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(&acc_empty[ab]);          // both chunks of this buffer are in registers
+                if (t + 1 < p.tiles_n) {
+                    const uint32_t nb = (git + 1) & 1;
+                    tc::mbar_wait(&acc_full[nb], ((git + 1) >> 1) & 1);
+                    tc::fence_after_thread_sync();
+                    tc::tmem_ld_32x32(acc_addr + nb * SUB * C::BN, va);
                 }
+                consume(vb, 2 * t + 1);
             }
             it += p.tiles_n;
 
