@@ -16,6 +16,8 @@
 // persistent tile loop.  Out-of-bounds rows / columns / k are zero-filled by TMA, so ragged
 // batches and the awkward layer widths (15, 14, 13, 50, 1555 ...) need no host-side padding
 // beyond 16-byte row strides.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "ops.cuh"
 #include "tc_common.cuh"
@@ -325,7 +327,11 @@ int launch_tc(pgmvae_ctx* ctx, cudaStream_t st, DenseTcP& p, const CUtensorMap& 
     int kb_cta = p.kb_per_split < p.kblocks ? p.kb_per_split : p.kblocks;
     if (kb_cta < 1) kb_cta = 1;
     // wgrad streams long k ranges: as many stages as keep two CTAs per SM (~100 KB each), at most 8
-    int max_stages = EPI == EPI_WGRAD ? (int)((100 * 1024 - 2 * A_STAGE_BYTES) / stage) : 3;
+    // (PGMVAE_WGRAD_SMEM_KB: under data parallelism a smaller budget leaves shared memory on every SM for the
+    //  NCCL CTAs that run beside the wgrad kernels)
+    int budget_kb = 100;
+    if (const char* ev = getenv("PGMVAE_WGRAD_SMEM_KB")) budget_kb = atoi(ev) >= 48 ? atoi(ev) : 100;
+    int max_stages = EPI == EPI_WGRAD ? (int)((budget_kb * 1024 - 2 * A_STAGE_BYTES) / stage) : 3;
     if (max_stages > MAX_STAGES) max_stages = MAX_STAGES;
     if (max_stages < 3) max_stages = 3;
     p.stages = kb_cta < max_stages ? kb_cta : max_stages;
