@@ -261,6 +261,15 @@ int pgmvae_model_get_tensor(pgmvae_model* m, const char* name, float* host, int6
 int pgmvae_model_set_ema_steps(pgmvae_model* m, int step_c, int step_w);
 int pgmvae_model_set_adam_step(pgmvae_model* m, int64_t t);
 
+/* Peer-to-peer gradient exchange (single node, data parallel; new work like pgmvae_comm_*): instead of NCCL
+ * all-reduces followed by Adam, ONE kernel per rank reads the gradient buffers of all ranks over NVLink, sums
+ * them in rank order and applies the Adam update (the replicas stay bit-identical).
+ * export: writes 2 x 64 bytes (CUDA IPC handles of this rank's gradient buffer and flag block); the host
+ * exchanges them (any side channel) and passes all of them, in rank order, to import.  Optional: without it
+ * pgmvae_model_train_step reduces the gradients through the communicator.                                  */
+int pgmvae_model_p2p_export(pgmvae_model* m, void* handles_out128);
+int pgmvae_model_p2p_import(pgmvae_model* m, int rank, int nranks, const void* all_handles);
+
 /* One training step on a batch y [B,V] uint8 (host or device pointer).
  * global_B is the batch size over all data-parallel ranks (== B without DP); comm may be NULL.
  * flags: bit0 = skip the optimiser/EMA update (gradients only).

@@ -109,6 +109,26 @@ class VqVAE:
         _ffi.check(_ffi.lib().pgmvae_model_create(self.ctx.h, units, self.nvar, self.dim, self.k, self.cost, self.decay,
                                                   self.epsilon, int(self.ema), max_batch, C.byref(h)))
         self._h, self.max_batch = h, max_batch
+        self._setup_p2p()
+
+    def _setup_p2p(self):
+        """Data parallel on one node: map every rank's gradient buffer into every other rank (CUDA IPC) so that the
+        library can fuse the gradient exchange with Adam (pgmvae_model_p2p_*).  Collective: every rank creates its
+        model at the same point.  torch.distributed (gloo) only carries the 128 handle bytes.  PGMVAE_P2P=0 keeps
+        the NCCL all-reduces."""
+        comm = self.comm
+        if comm is None or getattr(comm, "h", None) is None or comm.nranks < 2 or comm.nranks > 8:
+            return
+        if os.environ.get("PGMVAE_P2P", "1") == "0":
+            return
+        import torch.distributed as dist
+        buf = C.create_string_buffer(128)
+        _ffi.check(_ffi.lib().pgmvae_model_p2p_export(self._h, buf))
+        handles = [None] * comm.nranks
+        dist.all_gather_object(handles, buf.raw)
+        blob = C.create_string_buffer(b"".join(handles), 128 * comm.nranks)
+        _ffi.check(_ffi.lib().pgmvae_model_p2p_import(self._h, comm.rank, comm.nranks, blob))
+        dist.barrier()
 
     def _ensure_capacity(self, batch: int):
         """The workspace is sized for max_batch samples; grow it (state is carried over)."""

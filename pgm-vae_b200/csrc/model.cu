@@ -60,6 +60,88 @@ __global__ void init_uniform_kernel(float* __restrict__ dst, long long n, int ro
     dst[i] = val;
 }
 
+// ---- peer-to-peer sum + Adam ------------------------------------------------------------------
+struct P2pArgs {
+    float* const* peer_grads; int* const* peer_flags; int* my_flags;
+    int rank, R, step;
+    long long n;
+    float *p, *m, *v;
+    float alpha, omb1, omb2, eps;
+    unsigned int* counter; int* err;
+};
+
+__device__ __forceinline__ int ld_volatile_i32(const int* p) { return *reinterpret_cast<const volatile int*>(p); }
+
+// One launch per rank and step: (1) tell every peer that this rank's gradients are complete, (2) wait for theirs,
+// (3) g = sum over ranks in rank order (identical on every rank, so the replicas stay bit-identical), read straight
+// from the peers' HBM over NVLink, and the Keras-form Adam update on it, (4) tell every peer that their buffers have
+// been read.  Waits are bounded: a dead peer raises *err instead of hanging the GPU.
+__global__ void __launch_bounds__(256) p2p_sum_adam_kernel(const P2pArgs a) {
+    __shared__ int ok;
+    if (blockIdx.x == 0 && threadIdx.x < a.R) {
+        __threadfence_system();
+        *reinterpret_cast<volatile int*>(a.peer_flags[threadIdx.x] + a.rank) = a.step;          // ready[rank] at peer
+    }
+    if (threadIdx.x == 0) {
+        int good = 1;
+        for (int q = 0; q < a.R && good; ++q) {
+            long long spins = 0;
+            while (ld_volatile_i32(a.my_flags + q) < a.step) {
+                if (++spins > 20000000ll) { good = 0; break; }
+                __nanosleep(100);
+            }
+        }
+        __threadfence_system();
+        ok = good;
+    }
+    __syncthreads();
+    if (!ok) {
+        if (threadIdx.x == 0) *reinterpret_cast<volatile int*>(a.err) = 1;
+        return;
+    }
+    const long long n4 = a.n >> 2;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        float4 gg = reinterpret_cast<const float4*>(a.peer_grads[0])[i];
+        for (int q = 1; q < a.R; ++q) {
+            const float4 t = reinterpret_cast<const float4*>(a.peer_grads[q])[i];
+            gg.x += t.x; gg.y += t.y; gg.z += t.z; gg.w += t.w;
+        }
+        float4 pp = reinterpret_cast<float4*>(a.p)[i];
+        float4 mm = reinterpret_cast<float4*>(a.m)[i];
+        float4 vv = reinterpret_cast<float4*>(a.v)[i];
+#define PG_ADAM1(c)                                          \
+        mm.c += (gg.c - mm.c) * a.omb1;                      \
+        vv.c += (gg.c * gg.c - vv.c) * a.omb2;               \
+        pp.c -= (mm.c * a.alpha) / (sqrtf(vv.c) + a.eps);
+        PG_ADAM1(x) PG_ADAM1(y) PG_ADAM1(z) PG_ADAM1(w)
+#undef PG_ADAM1
+        reinterpret_cast<float4*>(a.p)[i] = pp;
+        reinterpret_cast<float4*>(a.m)[i] = mm;
+        reinterpret_cast<float4*>(a.v)[i] = vv;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        if (atomicAdd(a.counter, 1u) == gridDim.x - 1) {           // last block: every read of the peers is done
+            *a.counter = 0u;
+            for (int q = 0; q < a.R; ++q)
+                *reinterpret_cast<volatile int*>(a.peer_flags[q] + a.R + a.rank) = a.step;      // done[rank] at peer
+        }
+    }
+}
+
+// before this rank overwrites its gradient buffer: every peer has finished reading the previous step's gradients
+__global__ void p2p_wait_done_kernel(const int* my_flags, int R, int step, int* err) {
+    if ((int)threadIdx.x < R) {
+        long long spins = 0;
+        while (ld_volatile_i32(my_flags + R + threadIdx.x) < step) {
+            if (++spins > 20000000ll) { *reinterpret_cast<volatile int*>(err) = 1; break; }
+            __nanosleep(100);
+        }
+    }
+}
+
 }  // namespace
 
 struct pgmvae_model {
@@ -93,6 +175,16 @@ struct pgmvae_model {
     cudaEvent_t ev_compute = nullptr, ev_comm = nullptr;
     // the ten wgrad launches of a step are independent of each other: they are spread over three streams so that
     // the tail of one overlaps the head of the next
+    // peer-to-peer gradient exchange fused with Adam (single node, NVLink): every rank reads the gradient buffers
+    // of all ranks directly and applies the identical update -- no NCCL launch on the critical path
+    bool p2p = false;
+    int p2p_rank = 0, p2p_n = 1, p2p_step = 0;
+    float** peer_grads = nullptr;      // device array [R] of gradient buffers (own + IPC-mapped peers)
+    int** peer_flags = nullptr;        // device array [R] of flag blocks: ready[R] | done[R]
+    int* p2p_flags = nullptr;          // this rank's flag block (peers write into it)
+    unsigned int* p2p_counter = nullptr;
+    int* p2p_err = nullptr;            // pinned host word: a peer barrier timed out
+    std::vector<void*> ipc_opened;
     cudaStream_t aux_stream[2] = {nullptr, nullptr};
     cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
 
@@ -413,6 +505,8 @@ int pgmvae_model_destroy(pgmvae_model* m) {
     cudaStreamSynchronize(m->ctx->stream);
     for (void* p : m->allocs) cudaFree(p);
     if (m->acc_host) cudaFreeHost(m->acc_host);
+    for (void* q : m->ipc_opened) cudaIpcCloseMemHandle(q);
+    if (m->p2p_err) cudaFreeHost(m->p2p_err);
     if (m->comm_stream) cudaStreamDestroy(m->comm_stream);
     for (int i = 0; i < 2; ++i) {
         if (m->aux_stream[i]) cudaStreamDestroy(m->aux_stream[i]);
@@ -508,6 +602,49 @@ int pgmvae_model_get_tensor(pgmvae_model* m, const char* name, float* host, int6
     return PGMVAE_OK;
 }
 
+/* handles_out: 2 x 64 bytes (cudaIpcMemHandle_t of the gradient buffer and of this rank's flag block) */
+int pgmvae_model_p2p_export(pgmvae_model* m, void* handles_out) {
+    PG_CHECK_ARG(m && handles_out);
+    PG_CUDA(cudaSetDevice(m->ctx->device));
+    if (!m->p2p_flags) {
+        PG_TRY(dev_alloc(m, (void**)&m->p2p_flags, 256));
+        PG_TRY(dev_alloc(m, (void**)&m->p2p_counter, 256));
+        PG_CUDA(cudaMallocHost((void**)&m->p2p_err, sizeof(int)));
+        *m->p2p_err = 0;
+        PG_CUDA(cudaStreamSynchronize(m->ctx->stream));
+    }
+    cudaIpcMemHandle_t h[2];
+    PG_CUDA(cudaIpcGetMemHandle(&h[0], m->grads));
+    PG_CUDA(cudaIpcGetMemHandle(&h[1], m->p2p_flags));
+    memcpy(handles_out, h, sizeof(h));
+    return PGMVAE_OK;
+}
+
+/* all_handles: nranks x 128 bytes in rank order (what every rank exported); at most 8 ranks on one node */
+int pgmvae_model_p2p_import(pgmvae_model* m, int rank, int nranks, const void* all_handles) {
+    PG_CHECK_ARG(m && all_handles && nranks >= 2 && nranks <= 8 && rank >= 0 && rank < nranks && m->p2p_flags);
+    PG_CUDA(cudaSetDevice(m->ctx->device));
+    float* g[8]; int* f[8];
+    for (int q = 0; q < nranks; ++q) {
+        if (q == rank) { g[q] = m->grads; f[q] = m->p2p_flags; continue; }
+        cudaIpcMemHandle_t h[2];
+        memcpy(h, (const char*)all_handles + (size_t)q * sizeof(h), sizeof(h));
+        void *pg = nullptr, *pf = nullptr;
+        PG_CUDA(cudaIpcOpenMemHandle(&pg, h[0], cudaIpcMemLazyEnablePeerAccess));
+        m->ipc_opened.push_back(pg);
+        PG_CUDA(cudaIpcOpenMemHandle(&pf, h[1], cudaIpcMemLazyEnablePeerAccess));
+        m->ipc_opened.push_back(pf);
+        g[q] = (float*)pg; f[q] = (int*)pf;
+    }
+    PG_TRY(dev_alloc(m, (void**)&m->peer_grads, 8 * sizeof(float*)));
+    PG_TRY(dev_alloc(m, (void**)&m->peer_flags, 8 * sizeof(int*)));
+    PG_CUDA(cudaMemcpyAsync(m->peer_grads, g, nranks * sizeof(float*), cudaMemcpyHostToDevice, m->ctx->stream));
+    PG_CUDA(cudaMemcpyAsync(m->peer_flags, f, nranks * sizeof(int*), cudaMemcpyHostToDevice, m->ctx->stream));
+    PG_CUDA(cudaStreamSynchronize(m->ctx->stream));
+    m->p2p_rank = rank; m->p2p_n = nranks; m->p2p_step = 0; m->p2p = true;
+    return PGMVAE_OK;
+}
+
 int pgmvae_model_set_ema_steps(pgmvae_model* m, int step_c, int step_w) {
     PG_CHECK_ARG(m && step_c >= 0 && step_w >= 0);
     m->step_c = step_c; m->step_w = step_w;
@@ -538,6 +675,10 @@ int run_step(pgmvae_model* m, const uint8_t* y, int y_on_device, int B, int glob
     PG_TRY(upload_batch(m, y, y_on_device, B, &y_dev));
 
     const size_t trainable = m->ema ? m->n_dense : m->n_params;
+    if (m->p2p && m->p2p_step > 0) {
+        p2p_wait_done_kernel<<<1, 32, 0, st>>>(m->p2p_flags, m->p2p_n, m->p2p_step, m->p2p_err);
+        PG_LAUNCHED(ctx);
+    }
     PG_CUDA(cudaMemsetAsync(m->grads, 0, trainable * 4, st));
     PG_CUDA(cudaMemsetAsync(m->acc, 0, 4 * sizeof(double), st));
     if (m->ema) {
@@ -551,7 +692,7 @@ int run_step(pgmvae_model* m, const uint8_t* y, int y_on_device, int B, int glob
     const float cscale = (float)(m->cost * 2.0 / n_lat);
 
     const bool chain = use_chain(m) && out_dev == nullptr;
-    bool overlapped = false;
+    bool overlapped = false, use_p2p = false;
     for (int g0 = 0; g0 < V && chain; g0 += m->Vg) {
         const int Gn = std::min(m->Vg, V - g0);
         const int64_t MB = m->max_batch;
@@ -571,6 +712,7 @@ int run_step(pgmvae_model* m, const uint8_t* y, int y_on_device, int B, int glob
         // single variable group under data parallelism: every exchange is issued as soon as its operand is
         // final and runs on the communication stream under the kernels that follow
         const bool overlap = comm != nullptr && Gn == V;
+        use_p2p = overlap && m->p2p && !(flags & (STEP_NO_UPDATE | STEP_FWD_ONLY));
         if (overlap) {      // EMA statistics + loss accumulators: one fused NCCL launch
             PG_TRY(pg_comm_group_begin(comm));
             PG_TRY(overlapped_allreduce(m, comm, m->acc, 4, 1));
@@ -635,13 +777,13 @@ int run_step(pgmvae_model* m, const uint8_t* y, int y_on_device, int B, int glob
                     PG_CUDA(cudaEventRecord(m->ev_join[i], m->aux_stream[i]));
                     PG_CUDA(cudaStreamWaitEvent(st, m->ev_join[i], 0));
                 }
-                if (overlap) {
+                if (overlap && !use_p2p) {
                     PG_TRY(overlapped_allreduce(m, comm, m->grads + L.w_off, (int64_t)(bucket_end - L.w_off), 0));
                     bucket_end = L.w_off;
                 }
             }
         }
-        if (overlap && !m->ema)
+        if (overlap && !m->ema && !use_p2p)
             PG_TRY(overlapped_allreduce(m, comm, m->dE(), (int64_t)V * K * Dp, 0));
     }
     for (int g0 = 0; g0 < V && !chain; g0 += m->Vg) {
@@ -718,8 +860,22 @@ int run_step(pgmvae_model* m, const uint8_t* y, int y_on_device, int B, int glob
         m->adam_t += 1;
         const double b1 = 0.9, b2 = 0.999;
         const float alpha = (float)((double)lr * sqrt(1.0 - pow(b2, (double)m->adam_t)) / (1.0 - pow(b1, (double)m->adam_t)));
-        PG_TRY(pgmvae_adam_step(ctx, st, m->params, m->grads, m->adam_m, m->adam_v, (int64_t)trainable, alpha, b1, b2,
-                                1e-7));
+        if (use_p2p) {
+            P2pArgs a{};
+            a.peer_grads = m->peer_grads; a.peer_flags = m->peer_flags; a.my_flags = m->p2p_flags;
+            a.rank = m->p2p_rank; a.R = m->p2p_n; a.step = ++m->p2p_step;
+            a.n = (long long)trainable; a.p = m->params; a.m = m->adam_m; a.v = m->adam_v;
+            a.alpha = alpha; a.omb1 = (float)(1.0 - b1); a.omb2 = (float)(1.0 - b2); a.eps = 1e-7f;
+            a.counter = m->p2p_counter; a.err = m->p2p_err;
+            int blocks = (int)std::min<int64_t>(pg_cdiv((int64_t)trainable, 256 * 4 * 2), (int64_t)ctx->sm_count * 4);
+            if (blocks < 1) blocks = 1;
+            PG_KERNEL(ctx, st, "p2p_sum_adam", 4.0 * trainable * (m->p2p_n + 6.0), (10.0 + m->p2p_n) * trainable);
+            p2p_sum_adam_kernel<<<blocks, 256, 0, st>>>(a);
+            PG_LAUNCHED(ctx);
+        } else {
+            PG_TRY(pgmvae_adam_step(ctx, st, m->params, m->grads, m->adam_m, m->adam_v, (int64_t)trainable, alpha, b1, b2,
+                                    1e-7));
+        }
     }
     if (!(flags & STEP_NO_UPDATE)) {
         if (m->ema && !(flags & STEP_NO_EMA)) {
@@ -731,6 +887,10 @@ int run_step(pgmvae_model* m, const uint8_t* y, int y_on_device, int B, int glob
     if (metrics4) {
         PG_CUDA(cudaMemcpyAsync(m->acc_host, m->acc, 4 * sizeof(double), cudaMemcpyDeviceToHost, st));
         PG_CUDA(cudaStreamSynchronize(st));
+        if (m->p2p_err && *m->p2p_err) {
+            pgmvae_set_error("peer-to-peer gradient exchange: a rank did not reach the barrier (timed out)");
+            return PGMVAE_ENCCL;
+        }
         const double mse = m->acc_host[0] / n_out, mae = m->acc_host[1] / n_out;
         const double e_latent = m->acc_host[2] / n_lat;
         const double vq = m->ema ? m->cost * e_latent : (1.0 + m->cost) * e_latent;
