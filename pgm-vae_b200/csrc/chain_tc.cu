@@ -83,19 +83,28 @@ __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {     
     return done != 0;
 }
 
+// One thread moves (up to) 32 consecutive floats of its row with 256-bit accesses: every row starts on a 32-byte
+// boundary (row strides are multiples of 8 floats), so a store fills whole 32-byte sectors -- half the memory
+// instructions and half the L1 wavefronts of 128-bit accesses (the rows of a warp lie in 32 different lines).
 __device__ __forceinline__ void store_chunk(float* dst, const float (&v)[32], int nv) {
 #pragma unroll
-    for (int j = 0; j < 32; j += 4)
-        if (j < nv) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    for (int j = 0; j < 32; j += 8)
+        if (j < nv)
+            asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst + j), "f"(v[j]), "f"(v[j + 1]),
+                         "f"(v[j + 2]), "f"(v[j + 3]), "f"(v[j + 4]), "f"(v[j + 5]), "f"(v[j + 6]), "f"(v[j + 7])
+                         : "memory");
 }
 __device__ __forceinline__ void load_chunk(const float* src, float (&v)[32], int nv) {
 #pragma unroll
-    for (int j = 0; j < 32; j += 4) {
+    for (int j = 0; j < 32; j += 8) {
         if (j < nv) {
-            const float4 t = *reinterpret_cast<const float4*>(src + j);
-            v[j] = t.x; v[j + 1] = t.y; v[j + 2] = t.z; v[j + 3] = t.w;
+            asm volatile("ld.global.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                         : "=f"(v[j]), "=f"(v[j + 1]), "=f"(v[j + 2]), "=f"(v[j + 3]), "=f"(v[j + 4]), "=f"(v[j + 5]),
+                           "=f"(v[j + 6]), "=f"(v[j + 7])
+                         : "l"(src + j));
         } else {
-            v[j] = v[j + 1] = v[j + 2] = v[j + 3] = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[j + i] = 0.f;
         }
     }
 }
@@ -104,14 +113,29 @@ __device__ __forceinline__ void load_chunk(const float* src, float (&v)[32], int
 // already carry the 2^-11 relative error of the tf32 operands.  The exact-fp32 path (dense_simt.cu)
 // keeps expf, and so does the EXACT instantiation (PGMVAE_CHAIN_EXACT=1), which reproduces the
 // layer-by-layer tensor-core kernels bit for bit up to summation order.
+__device__ __forceinline__ float ex2_ftz(float x) {       // bare MUFU.EX2: no denormal rescue around it
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rcp_ftz(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 template <bool EXACT>
 __device__ __forceinline__ float ch_selu(float x) {      // branch-free: 32 independent elements interleave
-    const float e = PG_SELU_SCALE_ALPHA * ((EXACT ? expf(fminf(x, 0.f)) : __expf(fminf(x, 0.f))) - 1.0f);
-    return x < 0.f ? e : PG_SELU_SCALE * x;
+    if (EXACT) {
+        const float e = PG_SELU_SCALE_ALPHA * (expf(fminf(x, 0.f)) - 1.0f);
+        return x < 0.f ? e : PG_SELU_SCALE * x;
+    }
+    // scale * max(x, 0) + scale_alpha * (e^min(x, 0) - 1): the second term is exactly 0 for x >= 0
+    const float neg = fmaf(PG_SELU_SCALE_ALPHA, ex2_ftz(fminf(x, 0.f) * 1.4426950408889634f), -PG_SELU_SCALE_ALPHA);
+    return fmaf(PG_SELU_SCALE, fmaxf(x, 0.f), neg);
 }
 template <bool EXACT>
 __device__ __forceinline__ float ch_sigmoid(float x) {
-    return EXACT ? 1.0f / (1.0f + expf(-x)) : __fdividef(1.0f, 1.0f + __expf(-x));
+    return EXACT ? 1.0f / (1.0f + expf(-x)) : rcp_ftz(1.0f + ex2_ftz(x * -1.4426950408889634f));
 }
 
 // Exact fp32 arg-min of one row against the codebook in shared memory ([Kp][4*NV4] floats, Kp a
@@ -148,8 +172,62 @@ __device__ __forceinline__ int vq_row_argmin(const float (&v)[32], float zz, con
     return bi;
 }
 
-template <bool EXACT>
-__global__ void __launch_bounds__(CH_THREADS, 1)
+// The VQ step on one row held in registers (v[0 .. 4*NV4) = the padded latent; the rest of v is cleared):
+// assignment, then either the PLL histogram (encode) or q = E[idx], the straight-through output st = z + (q - z)
+// left in v, the commitment / codebook loss and the EMA statistics (core/quantizer.py:134-156).
+template <int MODE, int NV4>
+__device__ __forceinline__ void vq_stage(float (&v)[32], const ChainP& p, const float* __restrict__ sE,
+                                         const float* __restrict__ sEE, uint32_t* sHist, int Kp, int g, int row, int rowc,
+                                         bool valid, float& vq) {
+    constexpr int DP = 4 * NV4;
+#pragma unroll
+    for (int d = DP; d < 32; ++d) v[d] = 0.f;
+    float zz = 0.f;
+#pragma unroll
+    for (int d = 0; d < DP; ++d)
+        if (d < p.D) zz = fmaf(v[d], v[d], zz);
+    const int bi = vq_row_argmin<NV4>(v, zz, sE, sEE, Kp);
+    if (valid && p.idx) p.idx[(long long)g * p.idx_gs + rowc] = bi;
+    if (MODE == PG_CHAIN_ENCODE) {
+        if (valid && p.n1) {
+            const int bit = p.y8[(long long)row * p.ldy8 + p.g0 + g] != 0;
+            atomicAdd(&sHist[(bit ? 0 : p.K) + bi], 1u);
+        }
+        return;
+    }
+    const float* er = sE + bi * DP;
+    float qv[DP];
+#pragma unroll
+    for (int d = 0; d < DP; d += 4) {
+        const float4 t = *reinterpret_cast<const float4*>(er + d);
+        qv[d] = t.x; qv[d + 1] = t.y; qv[d + 2] = t.z; qv[d + 3] = t.w;
+    }
+    const long long zo = (long long)g * p.zq_gs + (long long)rowc * p.ldzq;
+    if (valid) {
+#pragma unroll
+        for (int d = 0; d < DP; d += 8)
+            asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p.q + zo + d), "f"(qv[d]),
+                         "f"(qv[d + 1]), "f"(qv[d + 2]), "f"(qv[d + 3]), "f"(qv[d + 4]), "f"(qv[d + 5]), "f"(qv[d + 6]),
+                         "f"(qv[d + 7])
+                         : "memory");
+        if (p.stat_w) {
+            float* dw = p.stat_w + ((long long)g * p.K + bi) * DP;
+#pragma unroll
+            for (int d = 0; d < DP; d += 4) red_add_v4(dw + d, v[d], v[d + 1], v[d + 2], v[d + 3]);
+            atomicAdd(p.stat_c + (long long)g * p.K + bi, 1.0f);
+        }
+    }
+#pragma unroll
+    for (int d = 0; d < DP; ++d) {
+        const float diff = qv[d] - v[d];
+        if (valid && d < p.D) vq = fmaf(diff, diff, vq);
+        v[d] = v[d] + diff;
+    }
+    if (valid) store_chunk(p.stq + zo, v, DP);
+}
+
+template <bool EXACT, int MODE>
+__global__ void __launch_bounds__(CH_THREADS, 1)    // 14 warps are allocated as 16: 128 registers per thread
 chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ ChainP p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-byte aligned, still a shared-space pointer
@@ -305,7 +383,7 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ Cha
                         float s2 = 0.f;
                         for (int d = 0; d < p.D; ++d) s2 = fmaf(sE[k * p.Dp + d], sE[k * p.Dp + d], s2);
                         sEE[k] = k < p.K ? s2 : INFINITY;
-                        if (p.mode == PG_CHAIN_ENCODE && p.n1 && k < p.K) { sHist[k] = 0; sHist[p.K + k] = 0; }
+                        if (MODE == PG_CHAIN_ENCODE && p.n1 && k < p.K) { sHist[k] = 0; sHist[p.K + k] = 0; }
                     }
                 }
                 epi_bar(bar_id);
@@ -315,16 +393,12 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ Cha
             {
                 const float* ar = p.a0 + (long long)g * p.a0_gs + (long long)rowc * p.lda0;
                 const uint32_t a_addr = lane_addr + p.st[0].a_col;
-                for (int c = 0; c < p.a0_cols; c += 8) {
-                    float4 x0 = make_float4(0.f, 0.f, 0.f, 0.f), x1 = x0;
-                    if (valid) {
-                        x0 = *reinterpret_cast<const float4*>(ar + c);
-                        x1 = *reinterpret_cast<const float4*>(ar + c + 4);
-                    }
-                    const uint32_t u[8] = {__float_as_uint(x0.x), __float_as_uint(x0.y), __float_as_uint(x0.z),
-                                           __float_as_uint(x0.w), __float_as_uint(x1.x), __float_as_uint(x1.y),
-                                           __float_as_uint(x1.z), __float_as_uint(x1.w)};
-                    tc::tmem_st_32x8(a_addr + c, u);
+                for (int c = 0; c < p.a0_cols; c += 64) {     // sixteen 16-byte loads in flight per thread
+                    float t0[32], t1[32];
+                    load_chunk(ar + c, t0, valid ? min(32, p.a0_cols - c) : 0);
+                    load_chunk(ar + c + 32, t1, valid ? min(32, p.a0_cols - c - 32) : 0);
+                    tc::tmem_st_32x32(a_addr + c, t0);        // the region is a multiple of 32 columns wide
+                    if (c + 32 < p.a0_cols) tc::tmem_st_32x32(a_addr + c + 32, t1);
                 }
                 tc::tmem_st_wait();
                 tc::fence_before_thread_sync();
@@ -334,103 +408,119 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ Cha
             float sq = 0.f, ab = 0.f, vq = 0.f;
             for (int j = 0; j < p.nst; ++j) {
                 const PgChainStage& S = p.st[j];
-                // operands that come from HBM are requested before waiting for the MMAs of this stage
+                // operands that come from HBM are requested before waiting for the MMAs of this stage, and the next
+                // chunk's before the current chunk is processed
                 float hv[32];
-                if (S.kind == PG_CHAIN_EPI_DGRAD)
-                    load_chunk(S.aux + (long long)g * S.aux_gs + (long long)rowc * S.ldaux, hv, min(32, S.pout));
-                else if (S.kind == PG_CHAIN_EPI_SIGMOID_MSE)
-                    load_chunk(p.yf + (long long)rowc * p.ldyf, hv, min(32, S.pout));
+                const float* hsrc = nullptr;
+                if (MODE == PG_CHAIN_BWD) hsrc = S.aux + (long long)g * S.aux_gs + (long long)rowc * S.ldaux;
+                else if (MODE == PG_CHAIN_FWD && S.kind == PG_CHAIN_EPI_SIGMOID_MSE) hsrc = p.yf + (long long)rowc * p.ldyf;
+                if (hsrc) load_chunk(hsrc, hv, min(32, S.pout));
+                if (MODE == PG_CHAIN_BWD && S.add_commit) {          // commitment gradient (single chunk: Dp <= 32)
+                    float zv[32], qv[32];
+                    const long long zo = (long long)g * p.zq_gs + (long long)rowc * p.ldzq;
+                    load_chunk(p.z + zo, zv, min(32, S.pout));
+                    load_chunk(p.qv + zo, qv, min(32, S.pout));
+#pragma unroll
+                    for (int jj = 0; jj < 32; ++jj) {
+                        hv[jj] = pg_dselu_from_out(hv[jj]);           // hv = 0 beyond pout
+                        zv[jj] -= qv[jj];
+                    }
+                    tc::mbar_wait(d_ful, dph);
+                    dph ^= 1;
+                    tc::fence_after_thread_sync();
+                    float v[32];
+                    tc::tmem_ld_32x32(lane_addr + S.d_col, v);
+                    tc::tmem_ld_wait(v);
+#pragma unroll
+                    for (int jj = 0; jj < 32; ++jj) v[jj] = fmaf(p.cscale, zv[jj], v[jj]) * hv[jj];
+                    if (valid && S.outp)
+                        store_chunk(S.outp + (long long)g * S.out_gs + (long long)rowc * S.ldo, v, min(32, S.pout));
+                    if (j + 1 != p.nst) {
+                        tc::tmem_st_32x32(lane_addr + S.d_col, v);
+                        tc::tmem_st_wait();
+                        tc::fence_before_thread_sync();
+                        __syncwarp();
+                        if (lane == 0) tc::mbar_arrive(a_rdy);
+                    }
+                    continue;
+                }
+                if (MODE == PG_CHAIN_BWD) {     // dX = (dY W^T) * act'(h): two chunks per round, both requested up front
+                    float h1[32];
+                    load_chunk(hsrc + 32, h1, min(32, S.pout - 32));
+                    tc::mbar_wait(d_ful, dph);
+                    dph ^= 1;
+                    tc::fence_after_thread_sync();
+                    float* orow = S.outp ? S.outp + (long long)g * S.out_gs + (long long)rowc * S.ldo : nullptr;
+                    const bool wr = valid && orow != nullptr, fwd_st = j + 1 != p.nst;
+                    for (int c = 0; c < S.pout; c += 64) {
+                        if (c > 0) {
+                            load_chunk(hsrc + c, hv, min(32, S.pout - c));
+                            load_chunk(hsrc + c + 32, h1, min(32, S.pout - c - 32));
+                        }
+                        float v[32];
+                        tc::tmem_ld_32x32(lane_addr + S.d_col + c, v);
+                        tc::tmem_ld_wait(v);
+#pragma unroll
+                        for (int jj = 0; jj < 32; ++jj) v[jj] *= pg_dselu_from_out(hv[jj]);   // hv = 0 beyond pout
+                        if (wr) store_chunk(orow + c, v, min(32, S.pout - c));
+                        if (fwd_st) tc::tmem_st_32x32(lane_addr + S.d_col + c, v);
+                        if (c + 32 < S.pout) {
+                            tc::tmem_ld_32x32(lane_addr + S.d_col + c + 32, v);
+                            tc::tmem_ld_wait(v);
+#pragma unroll
+                            for (int jj = 0; jj < 32; ++jj) v[jj] *= pg_dselu_from_out(h1[jj]);
+                            if (wr) store_chunk(orow + c + 32, v, min(32, S.pout - c - 32));
+                            if (fwd_st) tc::tmem_st_32x32(lane_addr + S.d_col + c + 32, v);
+                        }
+                    }
+                    if (fwd_st) {
+                        tc::tmem_st_wait();
+                        tc::fence_before_thread_sync();
+                        __syncwarp();
+                        if (lane == 0) tc::mbar_arrive(a_rdy);
+                    }
+                    continue;
+                }
                 tc::mbar_wait(d_ful, dph);
                 dph ^= 1;
                 tc::fence_after_thread_sync();
                 const bool last = j + 1 == p.nst;
                 const float* bias = sBias + S.bias_off;       // this variable's biases (shared memory)
                 for (int c = 0; c < S.pout; c += 32) {
+                    const int nv = min(32, S.pout - c);
                     float v[32];
                     tc::tmem_ld_32x32(lane_addr + S.d_col + c, v);
                     tc::tmem_ld_wait(v);
-                    const int nv = min(32, S.pout - c);
                     float* orow = S.outp ? S.outp + (long long)g * S.out_gs + (long long)rowc * S.ldo + c : nullptr;
-                    if (S.kind == PG_CHAIN_EPI_SELU) {
+                    if (MODE != PG_CHAIN_BWD && S.kind == PG_CHAIN_EPI_SELU) {
 #pragma unroll
                         for (int jj = 0; jj < 32; ++jj)
                             v[jj] = ch_selu<EXACT>(v[jj] + bias[c + jj]);        // columns >= pout are never consumed
                         if (valid && orow) store_chunk(orow, v, nv);
                         if (j == p.vq_stage) {
-#pragma unroll
-                            for (int d = 0; d < 32; ++d)
-                                if (d >= p.Dp) v[d] = 0.f;
-                            // ---- VQ on this row (Dp <= 32: the whole latent sits in v[0..Dp))
-                            float zz = 0.f;
-#pragma unroll
-                            for (int d = 0; d < 32; ++d)
-                                if (d < p.D) zz = fmaf(v[d], v[d], zz);
-                            int bi;
-                            switch (p.Dp >> 2) {
-                                case 2: bi = vq_row_argmin<2>(v, zz, sE, sEE, Kp); break;
-                                case 4: bi = vq_row_argmin<4>(v, zz, sE, sEE, Kp); break;
-                                case 6: bi = vq_row_argmin<6>(v, zz, sE, sEE, Kp); break;
-                                default: bi = vq_row_argmin<8>(v, zz, sE, sEE, Kp); break;
-                            }
-                            const long long io = (long long)g * p.idx_gs + rowc;
-                            if (valid && p.idx) p.idx[io] = bi;
-                            if (p.mode == PG_CHAIN_ENCODE) {
-                                if (valid && p.n1) {
-                                    const int bit = p.y8[(long long)row * p.ldy8 + p.g0 + g] != 0;
-                                    atomicAdd(&sHist[(bit ? 0 : p.K) + bi], 1u);
-                                }
-                            } else {
-                                // q = E[idx]; straight-through st = z + (q - z); commitment / codebook loss
-                                const float* er = sE + bi * p.Dp;
-                                float qv[32];
-#pragma unroll
-                                for (int d = 0; d < 32; ++d) qv[d] = d < p.Dp ? er[d] : 0.f;
-                                const long long zo = (long long)g * p.zq_gs + (long long)rowc * p.ldzq;
-                                if (valid) {
-                                    store_chunk(p.q + zo, qv, p.Dp);
-                                    if (p.stat_w) {
-                                        float* dw = p.stat_w + ((long long)g * p.K + bi) * p.Dp;
-#pragma unroll
-                                        for (int d = 0; d < 32; d += 4)
-                                            if (d < p.Dp) red_add_v4(dw + d, v[d], v[d + 1], v[d + 2], v[d + 3]);
-                                        atomicAdd(p.stat_c + (long long)g * p.K + bi, 1.0f);
-                                    }
-                                }
-#pragma unroll
-                                for (int d = 0; d < 32; ++d) {
-                                    const float diff = qv[d] - v[d];
-                                    if (valid && d < p.D) vq = fmaf(diff, diff, vq);
-                                    v[d] = v[d] + diff;
-                                }
-                                if (valid) store_chunk(p.stq + zo, v, p.Dp);
+                            switch (p.Dp >> 3) {      // padded latent width: a multiple of 8, at most 32
+                                case 1: vq_stage<MODE, 2>(v, p, sE, sEE, sHist, Kp, g, row, rowc, valid, vq); break;
+                                case 2: vq_stage<MODE, 4>(v, p, sE, sEE, sHist, Kp, g, row, rowc, valid, vq); break;
+                                case 3: vq_stage<MODE, 6>(v, p, sE, sEE, sHist, Kp, g, row, rowc, valid, vq); break;
+                                default: vq_stage<MODE, 8>(v, p, sE, sEE, sHist, Kp, g, row, rowc, valid, vq); break;
                             }
                         }
-                    } else if (S.kind == PG_CHAIN_EPI_SIGMOID_MSE) {
-                        if (c > 0) load_chunk(p.yf + (long long)rowc * p.ldyf + c, hv, nv);
-                        const int self = p.g0 + g;
-                        const float live = valid ? 1.0f : 0.f;
+                    } else if (MODE == PG_CHAIN_FWD && S.kind == PG_CHAIN_EPI_SIGMOID_MSE) {
+                        if (c > 0) load_chunk(hsrc + c, hv, nv);
+                        // columns that count: inside the data, not the net's own variable, row inside the batch
+                        const int self = p.g0 + g - c;
+                        uint32_t on = nv >= 32 ? 0xffffffffu : ((1u << nv) - 1u);
+                        if (p.V - c < 32) on &= p.V - c > 0 ? ((1u << (p.V - c)) - 1u) : 0u;
+                        if (self >= 0 && self < 32) on &= ~(1u << self);
+                        if (!valid) on = 0u;
 #pragma unroll
                         for (int jj = 0; jj < 32; ++jj) {
                             const float o = ch_sigmoid<EXACT>(v[jj] + bias[c + jj]);
-                            const bool on = jj < nv && c + jj < p.V && c + jj != self;    // the net's own variable is masked
-                            const float d = on ? o - hv[jj] : 0.f;
-                            sq = fmaf(live * d, d, sq);
-                            ab += live * fabsf(d);
-                            v[jj] = p.gscale * d * o * (1.0f - o);
+                            const float d = (on & (1u << jj)) ? o - hv[jj] : 0.f;
+                            sq = fmaf(d, d, sq);
+                            ab += fabsf(d);
+                            v[jj] = (p.gscale * d) * fmaf(-o, o, o);
                         }
-                        if (valid && orow) store_chunk(orow, v, nv);
-                    } else {   // PG_CHAIN_EPI_DGRAD: dX = (dY W^T [+ commitment gradient]) * act'(h)
-                        if (S.add_commit) {
-                            float zv[32], qv[32];
-                            const long long zo = (long long)g * p.zq_gs + (long long)rowc * p.ldzq + c;
-                            load_chunk(p.z + zo, zv, nv);
-                            load_chunk(p.qv + zo, qv, nv);
-#pragma unroll
-                            for (int jj = 0; jj < 32; ++jj) v[jj] = fmaf(p.cscale, zv[jj] - qv[jj], v[jj]);
-                        }
-                        if (c > 0) load_chunk(S.aux + (long long)g * S.aux_gs + (long long)rowc * S.ldaux + c, hv, nv);
-#pragma unroll
-                        for (int jj = 0; jj < 32; ++jj) v[jj] *= pg_dselu_from_out(hv[jj]);   // hv = 0 beyond nv
                         if (valid && orow) store_chunk(orow, v, nv);
                     }
                     if (!last) tc::tmem_st_32x32(lane_addr + S.d_col + c, v);
@@ -444,7 +534,7 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ Cha
             }
             acc_sq += (double)sq; acc_ab += (double)ab; acc_vq += (double)vq;
             // ---- PLL histogram of this item -> global counters
-            if (p.mode == PG_CHAIN_ENCODE && p.n1) {
+            if (MODE == PG_CHAIN_ENCODE && p.n1) {
                 epi_bar(bar_id);
                 for (int k = et; k < 2 * p.K; k += 128) {
                     const uint32_t c = sHist[k];
@@ -458,7 +548,7 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ Cha
                 epi_bar(bar_id);
             }
         }
-        if (p.acc && p.mode == PG_CHAIN_FWD) {
+        if (p.acc && MODE == PG_CHAIN_FWD) {
             acc_sq = pg_warp_sum_d(acc_sq); acc_ab = pg_warp_sum_d(acc_ab); acc_vq = pg_warp_sum_d(acc_vq);
             if (lane == 0) {
                 atomicAdd(p.acc + 0, acc_sq);
@@ -532,6 +622,17 @@ int pg_chain_launch(pgmvae_ctx* ctx, cudaStream_t st, const PgChainArgs& a) {
     bytes += 4.0 * (a.a0_gs ? (double)a.G : 1.0) * a.B * a.a0_cols;
     if (a.vq_stage >= 0) { flops += 2.0 * a.G * (double)a.B * a.D * a.K; bytes += 4.0 * a.G * (double)a.K * a.D; }
 
+    {   // rows move with 256-bit accesses: 32-byte aligned bases, row strides multiples of 8 floats
+        auto ok = [](const void* q, long long gs, int ld) { return !q || (!((uintptr_t)q & 31) && gs % 8 == 0 && ld % 8 == 0); };
+        bool al = ok(a.a0, a.a0_gs, a.lda0) && ok(a.yf, 0, a.ldyf) && ok(a.q, a.zq_gs, a.ldzq) && ok(a.stq, a.zq_gs, a.ldzq) &&
+                  ok(a.z, a.zq_gs, a.ldzq) && ok(a.qv, a.zq_gs, a.ldzq);
+        for (int j = 0; j < a.nst; ++j)
+            al = al && ok(a.st[j].outp, a.st[j].out_gs, a.st[j].ldo) && ok(a.st[j].aux, a.st[j].aux_gs, a.st[j].ldaux);
+        if (!al) {
+            pgmvae_set_error("chain kernel: activation rows must be 32-byte aligned");
+            return PGMVAE_EINVAL;
+        }
+    }
     const size_t Kp = (size_t)((a.K + 3) & ~3);
     p.tab_floats = (int)(((a.vq_stage >= 0 ? Kp * a.Dp + 3 * Kp : 0) + p.nbias + 40 + 3) & ~(size_t)3);
     const size_t smem = 1024 + (size_t)CH_RING * stage_bytes + (size_t)p.nch * p.tab_floats * 4 + 512;
@@ -540,19 +641,23 @@ int pg_chain_launch(pgmvae_ctx* ctx, cudaStream_t st, const PgChainArgs& a) {
         return PGMVAE_EINVAL;
     }
     const bool exact = getenv("PGMVAE_CHAIN_EXACT") != nullptr;
-    static size_t configured[2] = {0, 0};
-    if (smem > configured[exact]) {
-        if (exact) PG_CUDA(cudaFuncSetAttribute(chain_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        else PG_CUDA(cudaFuncSetAttribute(chain_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured[exact] = smem;
+    using KernelT = void (*)(const ChainMaps, const ChainP);
+    static const KernelT kernels[2][3] = {
+        {chain_kernel<false, PG_CHAIN_FWD>, chain_kernel<false, PG_CHAIN_ENCODE>, chain_kernel<false, PG_CHAIN_BWD>},
+        {chain_kernel<true, PG_CHAIN_FWD>, chain_kernel<true, PG_CHAIN_ENCODE>, chain_kernel<true, PG_CHAIN_BWD>}};
+    if (a.mode < 0 || a.mode > 2) return PGMVAE_EINVAL;
+    const KernelT kern = kernels[exact][a.mode];
+    static size_t configured[2][3] = {{0, 0, 0}, {0, 0, 0}};
+    if (smem > configured[exact][a.mode]) {
+        PG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured[exact][a.mode] = smem;
     }
     const int items = a.G * p.tiles_m;
     const int grid = std::min(items, ctx->sm_count);        // one CTA per SM, nch chains in flight each
     PG_KERNEL(ctx, st, a.mode == PG_CHAIN_FWD ? "chain_fwd_tc" : (a.mode == PG_CHAIN_ENCODE ? "chain_encode_tc" : "chain_bwd_tc"),
               bytes, flops);
     const int threads = 64 + 128 * p.nch;
-    if (exact) chain_kernel<true><<<grid, threads, smem, st>>>(maps, p);
-    else chain_kernel<false><<<grid, threads, smem, st>>>(maps, p);
+    kern<<<grid, threads, smem, st>>>(maps, p);
     PG_LAUNCHED(ctx);
     return PGMVAE_OK;
 }

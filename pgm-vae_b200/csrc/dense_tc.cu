@@ -18,6 +18,8 @@
 // beyond 16-byte row strides.
 #include <stdlib.h>
 
+#include <algorithm>
+
 #include "common.cuh"
 #include "ops.cuh"
 #include "tc_common.cuh"
@@ -72,9 +74,10 @@ __device__ __forceinline__ void load_row(const float* src, float (&v)[32], int n
     }
 }
 
+// The CTA program: (bx, by, bz) = (N tile, M tile, variable x batch split) of the problem p.
 template <int EPI>
-__global__ void __launch_bounds__(128) dense_tc_kernel(const __grid_constant__ CUtensorMap mapA,
-                                                       const __grid_constant__ CUtensorMap mapB, const DenseTcP p) {
+__device__ __forceinline__ void dense_tc_body(const CUtensorMap& mapA, const CUtensorMap& mapB, const DenseTcP& p,
+                                              const int bx, const int by, const int bz) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-byte aligned, still a shared-space pointer
     const int b_stage_bytes = p.BN * 128;
@@ -93,8 +96,8 @@ __global__ void __launch_bounds__(128) dense_tc_kernel(const __grid_constant__ C
     __shared__ double red[2][4];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int g = blockIdx.z / p.S, split = blockIdx.z - g * p.S;
-    const int m0 = blockIdx.y * TM, n0 = blockIdx.x * p.BN;
+    const int g = bz / p.S, split = bz - g * p.S;
+    const int m0 = by * TM, n0 = bx * p.BN;
     const int kb_beg = split * p.kb_per_split;
     const int kb_end = min(p.kblocks, kb_beg + p.kb_per_split);
     const int nkb = kb_end - kb_beg;
@@ -174,7 +177,7 @@ __global__ void __launch_bounds__(128) dense_tc_kernel(const __grid_constant__ C
                     for (int k4 = 0; k4 < 4; ++k4)
                         tc::mma_tf32(tmem_base, dA + (uint64_t)(k4 * a_step), dB + (uint64_t)(k4 * b_step), idesc,
                                      (kb > kb_beg || k4 > 0) ? 1u : 0u);
-                    if (EPI == EPI_WGRAD && p.db && blockIdx.y == 0) {
+                    if (EPI == EPI_WGRAD && p.db && by == 0) {
                         const uint32_t idesc1 = tc::make_idesc(2, TM, p.BN, 0, p.b_mn);
                         const uint64_t dOnes = tc::make_smem_desc(tc::smem_u32(sOnes), 16, 1024, 2);
 #pragma unroll
@@ -276,7 +279,7 @@ __global__ void __launch_bounds__(128) dense_tc_kernel(const __grid_constant__ C
                 if (j < nv) atomicAdd(dst + j, v[j]);
         }
     }
-    if (EPI == EPI_WGRAD && p.db && nkb > 0 && blockIdx.y == 0 && warp == 0) {      // lane 0 owns TMEM lane 0
+    if (EPI == EPI_WGRAD && p.db && nkb > 0 && by == 0 && warp == 0) {      // lane 0 owns TMEM lane 0
         // row 0 of the second accumulator: sum_b dY[b, n0 .. n0 + BN)
         for (int c = 0; c < p.BN && n0 + c < p.N; c += 32) {
             float v[32];
@@ -307,6 +310,34 @@ __global__ void __launch_bounds__(128) dense_tc_kernel(const __grid_constant__ C
     }
 }
 
+template <int EPI>
+__global__ void __launch_bounds__(128) dense_tc_kernel(const __grid_constant__ CUtensorMap mapA,
+                                                       const __grid_constant__ CUtensorMap mapB,
+                                                       const __grid_constant__ DenseTcP p) {
+    dense_tc_body<EPI>(mapA, mapB, p, (int)blockIdx.x, (int)blockIdx.y, (int)blockIdx.z);
+}
+
+// All weight-gradient GEMMs of a training step in ONE launch: ten launches of ~25 us each spend a third of their
+// time ramping up and draining (each is a single wave of CTAs); one launch of all their CTAs streams through.
+// CTAs are numbered problem by problem, the longest-running problems first.
+constexpr int WG_MAX = 10;
+struct WgradMultiP {
+    CUtensorMap mA[WG_MAX], mB[WG_MAX];
+    DenseTcP p[WG_MAX];
+    int start[WG_MAX + 1];           // first CTA of every problem
+    int nx[WG_MAX], ny[WG_MAX];      // grid extents of every problem (z = the rest)
+    int n;
+};
+__global__ void __launch_bounds__(128) wgrad_multi_kernel(const __grid_constant__ WgradMultiP P) {
+    int l = 0;
+    while (l + 1 < P.n && (int)blockIdx.x >= P.start[l + 1]) ++l;
+    int r = (int)blockIdx.x - P.start[l];
+    const int bx = r % P.nx[l];
+    r /= P.nx[l];
+    const int by = r % P.ny[l];
+    dense_tc_body<EPI_WGRAD>(P.mA[l], P.mB[l], P.p[l], bx, by, r / P.ny[l]);
+}
+
 inline bool tma_ok(const float* p, int64_t gs, int ld) { return !((uintptr_t)p & 15) && ld % 4 == 0 && gs % 4 == 0; }
 
 int pick_bn(int N) {
@@ -314,9 +345,9 @@ int pick_bn(int N) {
     return bn > 128 ? 128 : bn;
 }
 
+// stage geometry of one problem; returns the dynamic shared memory its CTAs need
 template <int EPI>
-int launch_tc(pgmvae_ctx* ctx, cudaStream_t st, DenseTcP& p, const CUtensorMap& mapA, const CUtensorMap& mapB, int G,
-              const char* name, double bytes) {
+size_t configure_tc(DenseTcP& p) {
     p.tmem_cols = 32;
     while (p.tmem_cols < (EPI == EPI_WGRAD ? 2 : 1) * p.BN) p.tmem_cols <<= 1;
     // MN-major A (wgrad) with a single M tile: load only the 32-row panels that hold valid rows
@@ -335,8 +366,13 @@ int launch_tc(pgmvae_ctx* ctx, cudaStream_t st, DenseTcP& p, const CUtensorMap& 
     if (max_stages > MAX_STAGES) max_stages = MAX_STAGES;
     if (max_stages < 3) max_stages = 3;
     p.stages = kb_cta < max_stages ? kb_cta : max_stages;
-    const size_t smem = 1024 + p.stages * stage + (A_STAGE_BYTES - p.a_stage_bytes) +
-                        (EPI == EPI_WGRAD ? A_STAGE_BYTES : 0) + 256;
+    return 1024 + p.stages * stage + (A_STAGE_BYTES - p.a_stage_bytes) + (EPI == EPI_WGRAD ? A_STAGE_BYTES : 0) + 256;
+}
+
+template <int EPI>
+int launch_tc(pgmvae_ctx* ctx, cudaStream_t st, DenseTcP& p, const CUtensorMap& mapA, const CUtensorMap& mapB, int G,
+              const char* name, double bytes) {
+    const size_t smem = configure_tc<EPI>(p);
     static size_t configured = 0;
     if (smem > configured) {
         PG_CUDA(cudaFuncSetAttribute(dense_tc_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -422,34 +458,107 @@ int pg_dense_dgrad_tc(pgmvae_ctx* ctx, cudaStream_t st, const float* dy, int64_t
                                        (double)G * B * in * (h_in ? 2 : 1) + (z ? 2.0 * G * B * in : 0.0)));
 }
 
-int pg_dense_wgrad_tc(pgmvae_ctx* ctx, cudaStream_t st, const float* x, int64_t x_gs, int ldx, const float* dy,
-                      int64_t dy_gs, int lddy, float* dw, int64_t dw_gs, int lddw, float* db, int64_t db_gs, int G, int B,
-                      int in, int out_dim, int zero_row_base) {
-    if (G <= 0 || B <= 0) return PGMVAE_OK;
-    DenseTcP p{};
+namespace {
+// problem description + tensor maps of one weight-gradient GEMM; S = batch splits (0: fill one wave of two CTAs per SM)
+int setup_wgrad(pgmvae_ctx* ctx, const float* x, int64_t x_gs, int ldx, const float* dy, int64_t dy_gs, int lddy,
+                float* dw, int64_t dw_gs, int lddw, float* db, int64_t db_gs, int G, int B, int in, int out_dim,
+                int zero_row_base, int64_t ctas_target, DenseTcP& p, CUtensorMap& mA, CUtensorMap& mB, double& bytes) {
+    p = DenseTcP{};
     p.M = in; p.N = out_dim; p.K = B; p.BN = pick_bn(out_dim);
     p.kblocks = (int)pg_cdiv(B, KBLK);
     p.a_mn = 1; p.b_mn = 1;
     p.C = dw; p.c_gs = dw_gs; p.ldc = lddw; p.zero_row_base = zero_row_base;
     p.db = db; p.db_gs = db_gs;
     p.a_shared = x_gs == 0;
-    // split the batch so that ~3 CTAs per SM are in flight, at least 8 k-blocks (256 samples) per CTA
+    // batch splits: at least 8 k-blocks (256 samples) per CTA
     const int64_t tiles = pg_cdiv(out_dim, p.BN) * pg_cdiv(in, TM) * (int64_t)G;
-    // batch splits: fill ONE wave of two CTAs per SM (a partial second wave costs a whole CTA time)
-    int S = (int)(((int64_t)ctx->sm_count * 2) / (tiles > 0 ? tiles : 1));
+    int S = (int)(ctas_target / (tiles > 0 ? tiles : 1));
     const int maxS = (int)pg_cdiv(p.kblocks, 8);
     if (S > maxS) S = maxS;
     if (S < 1) S = 1;
     while ((int64_t)G * S > 65535 && S > 1) --S;
     p.kb_per_split = (int)pg_cdiv(p.kblocks, S);
     p.S = (int)pg_cdiv(p.kblocks, p.kb_per_split);
-    CUtensorMap mA, mB;
     // x[B][in] read as rows k = b, contiguous m = in; boxes of [32 b][32 m]
     PG_TRY(tc::make_map(&mA, x, 4, (uint64_t)in, (uint64_t)B, (uint64_t)G, (uint64_t)ldx, (uint64_t)x_gs, 32, 32, true));
     PG_TRY(tc::make_map(&mB, dy, 4, (uint64_t)out_dim, (uint64_t)B, (uint64_t)G, (uint64_t)lddy, (uint64_t)dy_gs, 32, 32, true));
     const double xg = x_gs == 0 ? 1.0 : (double)G;
-    PG_TRY(launch_tc<EPI_WGRAD>(ctx, st, p, mA, mB, G, "dense_wgrad_tc",
-                                4.0 * (xg * B * in + (double)G * B * out_dim + (double)G * in * out_dim +
-                                       (db ? (double)G * out_dim : 0.0))));
+    bytes = 4.0 * (xg * B * in + (double)G * B * out_dim + (double)G * in * out_dim + (db ? (double)G * out_dim : 0.0));
+    return PGMVAE_OK;
+}
+}  // namespace
+
+int pg_dense_wgrad_tc(pgmvae_ctx* ctx, cudaStream_t st, const float* x, int64_t x_gs, int ldx, const float* dy,
+                      int64_t dy_gs, int lddy, float* dw, int64_t dw_gs, int lddw, float* db, int64_t db_gs, int G, int B,
+                      int in, int out_dim, int zero_row_base) {
+    if (G <= 0 || B <= 0) return PGMVAE_OK;
+    DenseTcP p;
+    CUtensorMap mA, mB;
+    double bytes;
+    // fill ONE wave of two CTAs per SM (a partial second wave costs a whole CTA time)
+    PG_TRY(setup_wgrad(ctx, x, x_gs, ldx, dy, dy_gs, lddy, dw, dw_gs, lddw, db, db_gs, G, B, in, out_dim, zero_row_base,
+                       (int64_t)ctx->sm_count * 2, p, mA, mB, bytes));
+    PG_TRY(launch_tc<EPI_WGRAD>(ctx, st, p, mA, mB, G, "dense_wgrad_tc", bytes));
+    return PGMVAE_OK;
+}
+
+bool pg_dense_wgrad_multi_supported(const PgWgradProblem* pr, int n) {
+    if (n < 1 || n > WG_MAX) return false;
+    for (int i = 0; i < n; ++i)
+        if (!tma_ok(pr[i].x, pr[i].x_gs, pr[i].ldx) || !tma_ok(pr[i].dy, pr[i].dy_gs, pr[i].lddy)) return false;
+    return true;
+}
+
+int pg_dense_wgrad_multi_tc(pgmvae_ctx* ctx, cudaStream_t st, const PgWgradProblem* pr, int n) {
+    if (n < 1 || n > WG_MAX) {
+        pgmvae_set_error("wgrad (multi): %d problems (1..%d)", n, WG_MAX);
+        return PGMVAE_EINVAL;
+    }
+    static WgradMultiP P;                 // 4.7 KB of kernel parameters (one host thread per context)
+    double bytes = 0.0, flops = 0.0, cost[WG_MAX];
+    size_t smem = 0;
+    int order[WG_MAX], Gs[WG_MAX], cnt = 0;
+    DenseTcP tp[WG_MAX];
+    CUtensorMap tA[WG_MAX], tB[WG_MAX];
+    for (int i = 0; i < n; ++i) {
+        const PgWgradProblem& q = pr[i];
+        if (q.G <= 0 || q.B <= 0) continue;
+        double b;
+        PG_TRY(setup_wgrad(ctx, q.x, q.x_gs, q.ldx, q.dy, q.dy_gs, q.lddy, q.dw, q.dw_gs, q.lddw, q.db, q.db_gs, q.G, q.B,
+                           q.in, q.out, q.zero_row_base, (int64_t)ctx->sm_count * 2, tp[cnt], tA[cnt], tB[cnt], b));
+        smem = std::max(smem, configure_tc<EPI_WGRAD>(tp[cnt]));
+        bytes += b;
+        flops += 2.0 * q.G * (double)q.B * q.in * q.out;
+        cost[cnt] = (double)tp[cnt].kb_per_split * (tp[cnt].a_stage_bytes + tp[cnt].BN * 128);   // bytes one CTA streams
+        order[cnt] = cnt;
+        Gs[cnt] = q.G;
+        ++cnt;
+    }
+    if (cnt == 0) return PGMVAE_OK;
+    for (int i = 1; i < cnt; ++i)                     // longest CTAs first
+        for (int j = i; j > 0 && cost[order[j]] > cost[order[j - 1]]; --j) std::swap(order[j], order[j - 1]);
+    int64_t total = 0;
+    for (int i = 0; i < cnt; ++i) {
+        const int o = order[i];
+        P.p[i] = tp[o]; P.mA[i] = tA[o]; P.mB[i] = tB[o];
+        P.nx[i] = (int)pg_cdiv(tp[o].N, tp[o].BN);
+        P.ny[i] = (int)pg_cdiv(tp[o].M, TM);
+        P.start[i] = (int)total;
+        total += (int64_t)P.nx[i] * P.ny[i] * tp[o].S * Gs[o];
+    }
+    P.start[cnt] = (int)total;
+    P.n = cnt;
+    if (total > 0x7fffffff) {
+        pgmvae_set_error("wgrad (multi): grid too large");
+        return PGMVAE_EINVAL;
+    }
+    static size_t configured = 0;
+    if (smem > configured) {
+        PG_CUDA(cudaFuncSetAttribute(wgrad_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    PG_KERNEL(ctx, st, "dense_wgrad_multi_tc", bytes, flops);
+    wgrad_multi_kernel<<<(unsigned)total, 128, smem, st>>>(P);
+    PG_LAUNCHED(ctx);
     return PGMVAE_OK;
 }

@@ -749,6 +749,27 @@ int run_step(pgmvae_model* m, const uint8_t* y, int y_on_device, int B, int glob
             a.z = m->H[4]; a.qv = m->q; a.cscale = cscale;
             PG_TRY(pg_chain_launch(ctx, st, a));
         }
+        // weight gradients.  Without NCCL buckets to feed (single GPU, or the peer-to-peer exchange that reads the
+        // whole gradient buffer at once) all ten GEMMs go out as ONE launch.
+        {
+            PgWgradProblem pr[10];
+            for (int l = 9; l >= 0; --l) {
+                const Layer& L = m->L[l];
+                PgWgradProblem& q = pr[9 - l];
+                q.x = l == 0 ? m->yf : (l == 5 ? m->st : m->H[l - 1]);
+                q.ldx = l == 0 ? m->Vp : (l == 5 ? Dp : m->L[l - 1].pout);
+                q.x_gs = l == 0 ? 0 : MB * q.ldx;
+                q.dy = m->Gd[l]; q.dy_gs = MB * L.pout; q.lddy = L.pout;
+                q.dw = m->grads + L.w_off + (size_t)g0 * L.pin * L.pout; q.dw_gs = (int64_t)L.pin * L.pout; q.lddw = L.pout;
+                q.db = m->grads + L.b_off + (size_t)g0 * L.pout; q.db_gs = L.pout;
+                q.G = Gn; q.B = B; q.in = L.in; q.out = L.out; q.zero_row_base = l == 0 ? g0 : -1;
+            }
+            const bool per_layer = getenv("PGMVAE_WGRAD_PER_LAYER") != nullptr;
+            if (!per_layer && !(overlap && !use_p2p) && pg_dense_wgrad_multi_supported(pr, 10)) {
+                PG_TRY(pg_dense_wgrad_multi_tc(ctx, st, pr, 10));
+                continue;
+            }
+        }
         if (!m->aux_stream[0]) {
             for (int i = 0; i < 2; ++i) {
                 PG_CUDA(cudaStreamCreateWithFlags(&m->aux_stream[i], cudaStreamNonBlocking));

@@ -48,6 +48,17 @@ int pg_dense_wgrad_tc(pgmvae_ctx* ctx, cudaStream_t st, const float* x, int64_t 
                       int64_t dy_gs, int lddy, float* dw, int64_t dw_gs, int lddw, float* db, int64_t db_gs, int G, int B,
                       int in, int out_dim, int zero_row_base);
 
+// every weight-gradient GEMM of a step in one launch (dense_tc.cu)
+struct PgWgradProblem {
+    const float* x; int64_t x_gs; int ldx;          // layer input  [G][B][in]  (x_gs = 0: shared by all variables)
+    const float* dy; int64_t dy_gs; int lddy;       // d(loss)/d(pre-activation) [G][B][out]
+    float* dw; int64_t dw_gs; int lddw;             // += x^T dy   [G][in][out]
+    float* db; int64_t db_gs;                       // += column sums of dy [G][out]
+    int G, B, in, out, zero_row_base;
+};
+bool pg_dense_wgrad_multi_supported(const PgWgradProblem* pr, int n);
+int pg_dense_wgrad_multi_tc(pgmvae_ctx* ctx, cudaStream_t st, const PgWgradProblem* pr, int n);
+
 // chain kernels (chain_tc.cu): a stack of dense layers per launch, activations resident in TMEM
 #define PG_CHAIN_MAX_STAGES 10
 enum { PG_CHAIN_FWD = 0, PG_CHAIN_ENCODE = 1, PG_CHAIN_BWD = 2 };

@@ -1,8 +1,9 @@
+# GPU parity tests + the quick bench (per-kernel times)
 set -x
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "rc=$?" >> gpurun_out/pytest_gpu.log
 tail -6 gpurun_out/pytest_gpu.log
-timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/bench_quick.json 2> gpurun_out/bench_quick.err
+timeout 300 python bench.py --steps 30 --warmup 5 --no-cpu-baseline --no-microbench > gpurun_out/bench_quick.json 2> gpurun_out/bench_quick.err
 tail -3 gpurun_out/bench_quick.err
 python - <<'PY'
 import json
