@@ -69,20 +69,6 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
 }
 __device__ __forceinline__ void epi_bar(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }   // the four warps of one chain
 
-__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {      // non-blocking probe
-    uint32_t done;
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t"
-        "}\n"
-        : "=r"(done)
-        : "r"(tc::smem_u32(bar)), "r"(parity)
-        : "memory");
-    return done != 0;
-}
-
 // One thread moves (up to) 32 consecutive floats of its row with 256-bit accesses: every row starts on a 32-byte
 // boundary (row strides are multiples of 8 floats), so a store fills whole 32-byte sectors -- half the memory
 // instructions and half the L1 wavefronts of 128-bit accesses (the rows of a warp lie in 32 different lines).
@@ -254,7 +240,7 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ Cha
             tc::mbar_init(&b_empty[s], p.nch);   // a weight k-block is released once every chain has consumed it
         }
         for (int c = 0; c < CH_MAXCH; ++c) {
-            tc::mbar_init(&a_ready[c], 4);       // one arrival per epilogue warp
+            tc::mbar_init(&a_ready[c], 4);       // (unused: the chain's warps meet at a named barrier instead)
             tc::mbar_init(&d_full[c], 1);
         }
         tc::fence_barrier_init();
@@ -292,58 +278,7 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ Cha
                 }
             }
         }
-    } else if (warp == 1) {
-        // ===================== MMA issuer: serves the chains in whatever order their operands become ready.
-        // Every probe is non-blocking (a blocking wait on one chain's weights could starve the chain whose
-        // progress releases that very ring slot); all chains consume the same k-block sequence.
-        const uint64_t dB_mn = tc::make_smem_desc(tc::smem_u32(sB), 4096, 512, 1);
-        const uint64_t dB_k = tc::make_smem_desc(tc::smem_u32(sB), 16, 1024, 2);
-        const uint32_t stage_stride = p.stage_bytes >> 4;
-        int c_item[CH_MAXCH], c_j[CH_MAXCH], c_kb[CH_MAXCH];
-        uint32_t c_seq[CH_MAXCH], c_aph[CH_MAXCH], c_have[CH_MAXCH];
-#pragma unroll
-        for (int c = 0; c < CH_MAXCH; ++c) { c_item[c] = item_beg; c_j[c] = 0; c_kb[c] = 0; c_seq[c] = 0; c_aph[c] = 0; c_have[c] = 0; }
-        int live = item_beg < item_end ? p.nch : 0;
-        while (live > 0) {
-            bool progress = false;
-#pragma unroll
-            for (int c = 0; c < CH_MAXCH; ++c) {
-                if (c >= p.nch || c_item[c] >= item_end) continue;
-                const PgChainStage& S = p.st[c_j[c]];
-                if (!c_have[c]) {                               // the A operand of this stage sits in TMEM?
-                    if (!mbar_test(&a_ready[c], c_aph[c])) continue;
-                    c_aph[c] ^= 1;
-                    c_have[c] = 1;
-                }
-                const uint32_t slot = c_seq[c] % CH_RING, gen = c_seq[c] / CH_RING;
-                if (!mbar_test(&b_full[slot], gen & 1)) continue;
-                progress = true;
-                tc::fence_after_thread_sync();
-                if (tc::elect_one()) {
-                    const uint32_t idesc = tc::make_idesc(2, CH_TM, S.N, 0, S.b_mn);
-                    const uint64_t dB = (S.b_mn ? dB_mn : dB_k) + (uint64_t)(slot * stage_stride);
-                    const uint32_t bstep = (S.b_mn ? 1024u : 32u) >> 4;
-                    const uint32_t tb = tmem_base + c * p.sub_cols;
-                    const int kb = c_kb[c], nk = min(4, S.ksteps - kb * 4);
-                    for (int k4 = 0; k4 < nk; ++k4)
-                        tc::mma_tf32_ts(tb + S.d_col, tb + S.a_col + kb * 32 + k4 * 8, dB + (uint64_t)(k4 * bstep), idesc,
-                                        (kb | k4) ? 1u : 0u);
-                    tc::mma_commit(&b_empty[slot]);
-                    if (kb == S.kblocks - 1) tc::mma_commit(&d_full[c]);
-                }
-                __syncwarp();
-                ++c_seq[c];
-                if (++c_kb[c] == S.kblocks) {
-                    c_kb[c] = 0; c_have[c] = 0;
-                    if (++c_j[c] == p.nst) {
-                        c_j[c] = 0;
-                        if (++c_item[c] >= item_end) --live;
-                    }
-                }
-            }
-            if (!progress) __nanosleep(40);
-        }
-    } else if (warp < 2 + 4 * p.nch) {
+    } else if (warp >= 2 && warp < 2 + 4 * p.nch) {      // (warp 1 only owns the TMEM allocation)
         // ===================== epilogue: one sample row per thread, four warps per chain
         const int q4 = warp & 3;                              // TMEM lane quarter == warp % 4
         const int ch = (warp - 2) >> 2;                       // chain of this warp
@@ -351,7 +286,6 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ Cha
         const int et = ((warp - 2) & 3) * 32 + lane;          // 0..127 among the threads of the chain
         const int bar_id = 1 + ch;
         const uint32_t lane_addr = tmem_base + ((uint32_t)(q4 * 32) << 16) + ch * p.sub_cols;
-        uint64_t* a_rdy = &a_ready[ch];
         uint64_t* d_ful = &d_full[ch];
         float* sE = tables + (size_t)ch * p.tab_floats;       // [Kp][Dp]
         float* sEE = sE + (size_t)Kp * p.Dp;                  // [Kp]
@@ -359,6 +293,42 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ Cha
         float* sBias = reinterpret_cast<float*>(sHist + 2 * Kp);  // biases of all stages, this variable
         uint32_t dph = 0;
         int cur_g = -1;
+        // MMA issue.  There is no separate issuer warp: once the four warps of a chain have left the operand of a
+        // stage in TMEM they meet at the chain's named barrier and the chain's first warp issues that stage's
+        // tcgen05.mma itself (one elected lane) -- no polling warp that competes for issue slots, no mbarrier
+        // round trip between the last tcgen05.st and the first MMA.  All chains consume the same k-block
+        // sequence of the weight ring; a slot is released when every chain's MMAs have read it.
+        const bool issuer = ((warp - 2) & 3) == 0;
+        const uint64_t dB_mn = tc::make_smem_desc(tc::smem_u32(sB), 4096, 512, 1);
+        const uint64_t dB_k = tc::make_smem_desc(tc::smem_u32(sB), 16, 1024, 2);
+        const uint32_t stage_stride = p.stage_bytes >> 4;
+        uint32_t wseq = 0;                                    // k-blocks consumed by this chain so far
+        auto issue_stage = [&](int j) {
+            tc::tmem_st_wait();
+            tc::fence_before_thread_sync();
+            epi_bar(bar_id);                                  // the operand rows of all 128 threads are in TMEM
+            if (!issuer) return;
+            tc::fence_after_thread_sync();
+            const PgChainStage& S = p.st[j];
+            const uint32_t idesc = tc::make_idesc(2, CH_TM, S.N, 0, S.b_mn);
+            const uint32_t bstep = (S.b_mn ? 1024u : 32u) >> 4;
+            const uint32_t tb = tmem_base + ch * p.sub_cols;
+            for (int kb = 0; kb < S.kblocks; ++kb, ++wseq) {
+                const uint32_t slot = wseq % CH_RING, gen = wseq / CH_RING;
+                tc::mbar_wait(&b_full[slot], gen & 1);
+                tc::fence_after_thread_sync();
+                if (tc::elect_one()) {
+                    const uint64_t dB = (S.b_mn ? dB_mn : dB_k) + (uint64_t)(slot * stage_stride);
+                    const int nk = min(4, S.ksteps - kb * 4);
+                    for (int k4 = 0; k4 < nk; ++k4)
+                        tc::mma_tf32_ts(tb + S.d_col, tb + S.a_col + kb * 32 + k4 * 8, dB + (uint64_t)(k4 * bstep), idesc,
+                                        (kb | k4) ? 1u : 0u);
+                    tc::mma_commit(&b_empty[slot]);
+                    if (kb == S.kblocks - 1) tc::mma_commit(d_ful);
+                }
+                __syncwarp();
+            }
+        };
         double acc_sq = 0.0, acc_ab = 0.0, acc_vq = 0.0;
         for (int item = item_beg; item < item_end; ++item) {
             const int g = item / p.tiles_m, mt = item - g * p.tiles_m;
@@ -400,10 +370,7 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ Cha
                     tc::tmem_st_32x32(a_addr + c, t0);        // the region is a multiple of 32 columns wide
                     if (c + 32 < p.a0_cols) tc::tmem_st_32x32(a_addr + c + 32, t1);
                 }
-                tc::tmem_st_wait();
-                tc::fence_before_thread_sync();
-                __syncwarp();
-                if (lane == 0) tc::mbar_arrive(a_rdy);
+                issue_stage(0);
             }
             float sq = 0.f, ab = 0.f, vq = 0.f;
             for (int j = 0; j < p.nst; ++j) {
@@ -437,10 +404,7 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ Cha
                         store_chunk(S.outp + (long long)g * S.out_gs + (long long)rowc * S.ldo, v, min(32, S.pout));
                     if (j + 1 != p.nst) {
                         tc::tmem_st_32x32(lane_addr + S.d_col, v);
-                        tc::tmem_st_wait();
-                        tc::fence_before_thread_sync();
-                        __syncwarp();
-                        if (lane == 0) tc::mbar_arrive(a_rdy);
+                        issue_stage(j + 1);
                     }
                     continue;
                 }
@@ -473,12 +437,7 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ Cha
                             if (fwd_st) tc::tmem_st_32x32(lane_addr + S.d_col + c + 32, v);
                         }
                     }
-                    if (fwd_st) {
-                        tc::tmem_st_wait();
-                        tc::fence_before_thread_sync();
-                        __syncwarp();
-                        if (lane == 0) tc::mbar_arrive(a_rdy);
-                    }
+                    if (fwd_st) issue_stage(j + 1);
                     continue;
                 }
                 tc::mbar_wait(d_ful, dph);
@@ -525,12 +484,7 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ Cha
                     }
                     if (!last) tc::tmem_st_32x32(lane_addr + S.d_col + c, v);
                 }
-                if (!last) {
-                    tc::tmem_st_wait();
-                    tc::fence_before_thread_sync();
-                    __syncwarp();
-                    if (lane == 0) tc::mbar_arrive(a_rdy);
-                }
+                if (!last) issue_stage(j + 1);
             }
             acc_sq += (double)sq; acc_ab += (double)ab; acc_vq += (double)vq;
             // ---- PLL histogram of this item -> global counters
