@@ -69,6 +69,16 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
 }
 __device__ __forceinline__ void epi_bar(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }   // the four warps of one chain
 
+// Asks for the 128-byte lines that hold [ptr, ptr + bytes) (bytes <= 384, a multiple of 32) to be brought into
+// L2: the backward chain requests the rows it will read two stages ahead, so its register loads are L2 hits.
+__device__ __forceinline__ void l2_prefetch(const float* ptr, int bytes) {
+    const char* c = reinterpret_cast<const char*>(ptr);
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(c));
+    if (bytes > 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(c + 128));
+    if (bytes > 256) asm volatile("prefetch.global.L2 [%0];" ::"l"(c + 256));
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(c + bytes - 32));     // the row's last sector may start a new line
+}
+
 // One thread moves (up to) 32 consecutive floats of its row with 256-bit accesses: every row starts on a 32-byte
 // boundary (row strides are multiples of 8 floats), so a store fills whole 32-byte sectors -- half the memory
 // instructions and half the L1 wavefronts of 128-bit accesses (the rows of a warp lie in 32 different lines).
@@ -373,8 +383,21 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ Cha
                 issue_stage(0);
             }
             float sq = 0.f, ab = 0.f, vq = 0.f;
+            auto prefetch_stage = [&](int jn) {        // backward: the rows stage jn reads from HBM -> L2
+                if (MODE != PG_CHAIN_BWD || jn >= p.nst || !valid) return;
+                const PgChainStage& N = p.st[jn];
+                l2_prefetch(N.aux + (long long)g * N.aux_gs + (long long)rowc * N.ldaux, N.pout * 4);
+                if (N.add_commit) {
+                    const long long zo = (long long)g * p.zq_gs + (long long)rowc * p.ldzq;
+                    l2_prefetch(p.z + zo, N.pout * 4);
+                    l2_prefetch(p.qv + zo, N.pout * 4);
+                }
+            };
+            prefetch_stage(0);
+            prefetch_stage(1);
             for (int j = 0; j < p.nst; ++j) {
                 const PgChainStage& S = p.st[j];
+                prefetch_stage(j + 2);
                 // operands that come from HBM are requested before waiting for the MMAs of this stage, and the next
                 // chunk's before the current chunk is processed
                 float hv[32];
