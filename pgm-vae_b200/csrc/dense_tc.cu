@@ -274,9 +274,24 @@ __device__ __forceinline__ void dense_tc_body(const CUtensorMap& mapA, const CUt
         } else {  // EPI_WGRAD: rows are weight rows (input features), reduced over the batch splits
             if (p.zero_row_base >= 0 && row == p.zero_row_base + g) continue;
             float* dst = p.C + off;
+            if (p.vecC) {                       // 16-byte aligned rows: four partial sums per reduction
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-                if (j < nv) atomicAdd(dst + j, v[j]);
+                for (int j = 0; j < 32; j += 4) {
+                    if (j + 4 <= nv) {
+                        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "f"(v[j]), "f"(v[j + 1]),
+                                     "f"(v[j + 2]), "f"(v[j + 3])
+                                     : "memory");
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                            if (j + i < nv) atomicAdd(dst + j + i, v[j + i]);
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if (j < nv) atomicAdd(dst + j, v[j]);
+            }
         }
     }
     if (EPI == EPI_WGRAD && p.db && nkb > 0 && by == 0 && warp == 0) {      // lane 0 owns TMEM lane 0
@@ -470,6 +485,7 @@ int setup_wgrad(pgmvae_ctx* ctx, const float* x, int64_t x_gs, int ldx, const fl
     p.C = dw; p.c_gs = dw_gs; p.ldc = lddw; p.zero_row_base = zero_row_base;
     p.db = db; p.db_gs = db_gs;
     p.a_shared = x_gs == 0;
+    p.vecC = tma_ok(dw, dw_gs, lddw);
     // batch splits: at least 8 k-blocks (256 samples) per CTA
     const int64_t tiles = pg_cdiv(out_dim, p.BN) * pg_cdiv(in, TM) * (int64_t)G;
     int S = (int)(ctas_target / (tiles > 0 ? tiles : 1));
