@@ -402,10 +402,13 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ Cha
                 // chunk's before the current chunk is processed
                 float hv[32];
                 const float* hsrc = nullptr;
-                if (MODE == PG_CHAIN_BWD) hsrc = S.aux + (long long)g * S.aux_gs + (long long)rowc * S.ldaux;
-                else if (MODE == PG_CHAIN_FWD && S.kind == PG_CHAIN_EPI_SIGMOID_MSE) hsrc = p.yf + (long long)rowc * p.ldyf;
+                // TRAIN = the forward stages followed by the dgrad stages of the same rows in one pass
+                const bool dgrad = MODE == PG_CHAIN_BWD || (MODE == PG_CHAIN_TRAIN && S.kind == PG_CHAIN_EPI_DGRAD);
+                constexpr bool HAS_LOSS = MODE == PG_CHAIN_FWD || MODE == PG_CHAIN_TRAIN;
+                if (dgrad) hsrc = S.aux + (long long)g * S.aux_gs + (long long)rowc * S.ldaux;
+                else if (HAS_LOSS && S.kind == PG_CHAIN_EPI_SIGMOID_MSE) hsrc = p.yf + (long long)rowc * p.ldyf;
                 if (hsrc) load_chunk(hsrc, hv, min(32, S.pout));
-                if (MODE == PG_CHAIN_BWD && S.add_commit) {          // commitment gradient (single chunk: Dp <= 32)
+                if (dgrad && S.add_commit) {          // commitment gradient (single chunk: Dp <= 32)
                     float zv[32], qv[32];
                     const long long zo = (long long)g * p.zq_gs + (long long)rowc * p.ldzq;
                     load_chunk(p.z + zo, zv, min(32, S.pout));
@@ -431,7 +434,7 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ Cha
                     }
                     continue;
                 }
-                if (MODE == PG_CHAIN_BWD) {     // dX = (dY W^T) * act'(h): two chunks per round, both requested up front
+                if (dgrad) {     // dX = (dY W^T) * act'(h): two chunks per round, both requested up front
                     float h1[32];
                     load_chunk(hsrc + 32, h1, min(32, S.pout - 32));
                     tc::mbar_wait(d_ful, dph);
@@ -487,7 +490,7 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ Cha
                                 default: vq_stage<MODE, 8>(v, p, sE, sEE, sHist, Kp, g, row, rowc, valid, vq); break;
                             }
                         }
-                    } else if (MODE == PG_CHAIN_FWD && S.kind == PG_CHAIN_EPI_SIGMOID_MSE) {
+                    } else if (HAS_LOSS && S.kind == PG_CHAIN_EPI_SIGMOID_MSE) {
                         if (c > 0) load_chunk(hsrc + c, hv, nv);
                         // columns that count: inside the data, not the net's own variable, row inside the batch
                         const int self = p.g0 + g - c;
@@ -525,7 +528,7 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ Cha
                 epi_bar(bar_id);
             }
         }
-        if (p.acc && MODE == PG_CHAIN_FWD) {
+        if (p.acc && (MODE == PG_CHAIN_FWD || MODE == PG_CHAIN_TRAIN)) {
             acc_sq = pg_warp_sum_d(acc_sq); acc_ab = pg_warp_sum_d(acc_ab); acc_vq = pg_warp_sum_d(acc_vq);
             if (lane == 0) {
                 atomicAdd(p.acc + 0, acc_sq);
@@ -576,7 +579,7 @@ int pg_chain_launch(pgmvae_ctx* ctx, cudaStream_t st, const PgChainArgs& a) {
                                 (uint64_t)S.ldw, (uint64_t)S.w_gs, 32, (uint32_t)S.N));
         flops += 2.0 * a.G * (double)a.B * S.k_valid * S.n_valid;
         bytes += 4.0 * a.G * ((double)S.k_valid * S.n_valid + (S.outp ? (double)a.B * S.n_valid : 0.0) +
-                              (S.aux ? (double)a.B * S.n_valid : 0.0));
+                              (S.aux && a.mode == PG_CHAIN_BWD ? (double)a.B * S.n_valid : 0.0));
     }
     const int w0 = pg_round_up(regw[0], 32), w1 = pg_round_up(regw[1], 32);
     for (int j = 0; j < a.nst; ++j) {
@@ -619,20 +622,22 @@ int pg_chain_launch(pgmvae_ctx* ctx, cudaStream_t st, const PgChainArgs& a) {
     }
     const bool exact = getenv("PGMVAE_CHAIN_EXACT") != nullptr;
     using KernelT = void (*)(const ChainMaps, const ChainP);
-    static const KernelT kernels[2][3] = {
-        {chain_kernel<false, PG_CHAIN_FWD>, chain_kernel<false, PG_CHAIN_ENCODE>, chain_kernel<false, PG_CHAIN_BWD>},
-        {chain_kernel<true, PG_CHAIN_FWD>, chain_kernel<true, PG_CHAIN_ENCODE>, chain_kernel<true, PG_CHAIN_BWD>}};
-    if (a.mode < 0 || a.mode > 2) return PGMVAE_EINVAL;
+    static const KernelT kernels[2][4] = {
+        {chain_kernel<false, PG_CHAIN_FWD>, chain_kernel<false, PG_CHAIN_ENCODE>, chain_kernel<false, PG_CHAIN_BWD>,
+         chain_kernel<false, PG_CHAIN_TRAIN>},
+        {chain_kernel<true, PG_CHAIN_FWD>, chain_kernel<true, PG_CHAIN_ENCODE>, chain_kernel<true, PG_CHAIN_BWD>,
+         chain_kernel<true, PG_CHAIN_TRAIN>}};
+    if (a.mode < 0 || a.mode > 3) return PGMVAE_EINVAL;
     const KernelT kern = kernels[exact][a.mode];
-    static size_t configured[2][3] = {{0, 0, 0}, {0, 0, 0}};
+    static size_t configured[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
     if (smem > configured[exact][a.mode]) {
         PG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured[exact][a.mode] = smem;
     }
     const int items = a.G * p.tiles_m;
     const int grid = std::min(items, ctx->sm_count);        // one CTA per SM, nch chains in flight each
-    PG_KERNEL(ctx, st, a.mode == PG_CHAIN_FWD ? "chain_fwd_tc" : (a.mode == PG_CHAIN_ENCODE ? "chain_encode_tc" : "chain_bwd_tc"),
-              bytes, flops);
+    static const char* const names[4] = {"chain_fwd_tc", "chain_encode_tc", "chain_bwd_tc", "chain_train_tc"};
+    PG_KERNEL(ctx, st, names[a.mode], bytes, flops);
     const int threads = 64 + 128 * p.nch;
     kern<<<grid, threads, smem, st>>>(maps, p);
     PG_LAUNCHED(ctx);

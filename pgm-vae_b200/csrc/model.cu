@@ -381,6 +381,24 @@ void chain_common(const pgmvae_model* m, int g0, int Gn, int B, PgChainArgs& a) 
     a.idx = m->idx; a.idx_gs = B;
 }
 
+// the dgrad stages fd9 .. fd1 appended at a.st[j0 ...]
+void chain_bwd_stages(const pgmvae_model* m, int g0, int j0, PgChainArgs& a) {
+    const int64_t MB = m->max_batch;
+    for (int j = 0; j < 9; ++j) {
+        const int l = 9 - j;
+        const Layer& L = m->L[l];
+        const Layer& P = m->L[l - 1];
+        PgChainStage& S = a.st[j0 + j];
+        S = PgChainStage{};
+        S.K = L.pout; S.pout = L.pin; S.k_valid = L.out; S.n_valid = L.in; S.b_mn = 0;
+        S.kind = PG_CHAIN_EPI_DGRAD; S.add_commit = l == 5;
+        S.w = m->params + L.w_off + (size_t)g0 * L.pin * L.pout; S.w_gs = (int64_t)L.pin * L.pout; S.ldw = L.pout;
+        S.outp = m->Gd[l - 1]; S.out_gs = MB * P.pout; S.ldo = P.pout;
+        S.aux = m->H[l - 1]; S.aux_gs = MB * P.pout; S.ldaux = P.pout;
+    }
+    a.nst = j0 + 9;
+}
+
 // encoder + assignment (+ PLL histogram when n1/n0 are given) in one launch
 int chain_encode(pgmvae_model* m, int g0, int Gn, int B, const uint8_t* y_dev, unsigned long long* n1,
                  unsigned long long* n0) {
@@ -697,10 +715,17 @@ int run_step(pgmvae_model* m, const uint8_t* y, int y_on_device, int B, int glob
         const int Gn = std::min(m->Vg, V - g0);
         const int64_t MB = m->max_batch;
         const bool stats = m->ema && !(flags & STEP_NO_EMA);
+        const bool fused = !(flags & STEP_FWD_ONLY) && getenv("PGMVAE_CHAIN_SPLIT") == nullptr;
         {   // forward chain: fd0..fd4, VQ (+ EMA statistics), fd5..fd9, loss and d(loss)/d(pre-activation)
             PgChainArgs a{};
             a.mode = PG_CHAIN_FWD;
             chain_fwd_stages(m, g0, 0, 10, a);
+            if (fused) {        // forward and dgrad of the same rows in one pass (nothing global lies between them:
+                                // the loss scale is a constant, the EMA statistics only feed the codebook update)
+                a.mode = PG_CHAIN_TRAIN;
+                chain_bwd_stages(m, g0, 10, a);
+                a.z = m->H[4]; a.qv = m->q; a.cscale = cscale;
+            }
             chain_common(m, g0, Gn, B, a);
             a.vq_stage = 4;
             a.a0 = m->yf; a.a0_gs = 0; a.lda0 = m->Vp; a.a0_cols = m->Vp;
@@ -727,22 +752,10 @@ int run_step(pgmvae_model* m, const uint8_t* y, int y_on_device, int B, int glob
         if (!m->ema)    // q_latent_loss gradient wrt the codebook: 2 (q - z) / (V B D)   (core/quantizer.py:51)
             PG_TRY(pgmvae_vq_codebook_grad(ctx, st, m->H[4], m->q, MB * Dp, Dp, m->idx, B, m->dE() + (size_t)g0 * K * Dp,
                                            (int64_t)K * Dp, Dp, (float)(2.0 / n_lat), Gn, B, D, K));
-        {   // backward chain: dgrad of fd9 .. fd1
+        if (!fused) {   // backward chain: dgrad of fd9 .. fd1
             PgChainArgs a{};
             a.mode = PG_CHAIN_BWD;
-            a.nst = 9;
-            for (int j = 0; j < 9; ++j) {
-                const int l = 9 - j;
-                const Layer& L = m->L[l];
-                const Layer& P = m->L[l - 1];
-                PgChainStage& S = a.st[j];
-                S = PgChainStage{};
-                S.K = L.pout; S.pout = L.pin; S.k_valid = L.out; S.n_valid = L.in; S.b_mn = 0;
-                S.kind = PG_CHAIN_EPI_DGRAD; S.add_commit = l == 5;
-                S.w = m->params + L.w_off + (size_t)g0 * L.pin * L.pout; S.w_gs = (int64_t)L.pin * L.pout; S.ldw = L.pout;
-                S.outp = m->Gd[l - 1]; S.out_gs = MB * P.pout; S.ldo = P.pout;
-                S.aux = m->H[l - 1]; S.aux_gs = MB * P.pout; S.ldaux = P.pout;
-            }
+            chain_bwd_stages(m, g0, 0, a);
             chain_common(m, g0, Gn, B, a);
             a.vq_stage = -1;
             a.a0 = m->Gd[9]; a.a0_gs = MB * m->L[9].pout; a.lda0 = m->L[9].pout; a.a0_cols = m->L[9].pout;

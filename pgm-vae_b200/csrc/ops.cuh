@@ -60,8 +60,8 @@ bool pg_dense_wgrad_multi_supported(const PgWgradProblem* pr, int n);
 int pg_dense_wgrad_multi_tc(pgmvae_ctx* ctx, cudaStream_t st, const PgWgradProblem* pr, int n);
 
 // chain kernels (chain_tc.cu): a stack of dense layers per launch, activations resident in TMEM
-#define PG_CHAIN_MAX_STAGES 10
-enum { PG_CHAIN_FWD = 0, PG_CHAIN_ENCODE = 1, PG_CHAIN_BWD = 2 };
+#define PG_CHAIN_MAX_STAGES 20
+enum { PG_CHAIN_FWD = 0, PG_CHAIN_ENCODE = 1, PG_CHAIN_BWD = 2, PG_CHAIN_TRAIN = 3 };   // TRAIN = FWD stages followed by BWD stages
 enum { PG_CHAIN_EPI_SELU = 0, PG_CHAIN_EPI_SIGMOID_MSE = 1, PG_CHAIN_EPI_DGRAD = 2 };
 struct PgChainStage {
     // filled by the caller
