@@ -114,12 +114,13 @@ class VqVAE:
     def _setup_p2p(self):
         """Data parallel on one node: map every rank's gradient buffer into every other rank (CUDA IPC) so that the
         library can fuse the gradient exchange with Adam (pgmvae_model_p2p_*).  Collective: every rank creates its
-        model at the same point.  torch.distributed (gloo) only carries the 128 handle bytes.  PGMVAE_P2P=0 keeps
-        the NCCL all-reduces."""
+        model at the same point.  torch.distributed (gloo) only carries the 128 handle bytes.  Opt-in (PGMVAE_P2P=1): measured on
+        8 B200 the NCCL all-reduce of the gradient buffer (0.77 ms per cfg2 step) beats every rank reading all eight
+        buffers (0.80 ms); at 2 GPUs the two tie."""
         comm = self.comm
         if comm is None or getattr(comm, "h", None) is None or comm.nranks < 2 or comm.nranks > 8:
             return
-        if os.environ.get("PGMVAE_P2P", "1") == "0":
+        if os.environ.get("PGMVAE_P2P", "0") != "1":      # opt-in: NCCL (in-switch reduction) wins at 8 GPUs
             return
         import torch.distributed as dist
         buf = C.create_string_buffer(128)

@@ -172,7 +172,7 @@ struct pgmvae_model {
     std::vector<void*> allocs;
     // data-parallel overlap: all-reduces run on their own stream behind events of the compute stream
     cudaStream_t comm_stream = nullptr;
-    cudaEvent_t ev_compute = nullptr, ev_comm = nullptr;
+    cudaEvent_t ev_compute = nullptr, ev_comm = nullptr, ev_stats = nullptr;
     // the ten wgrad launches of a step are independent of each other: they are spread over three streams so that
     // the tail of one overlaps the head of the next
     // peer-to-peer gradient exchange fused with Adam (single node, NVLink): every rank reads the gradient buffers
@@ -344,9 +344,14 @@ int upload_batch(pgmvae_model* m, const uint8_t* y, int on_device, int B, const 
 int overlapped_allreduce(pgmvae_model* m, pgmvae_comm* comm, void* buf, int64_t n, int dtype) {
     cudaStream_t st = m->ctx->stream;
     if (!m->comm_stream) {
-        PG_CUDA(cudaStreamCreateWithFlags(&m->comm_stream, cudaStreamNonBlocking));
+        // highest priority: the exchange kernels take the first SM slots that free up instead of queueing behind
+        // the thousands of CTAs of the weight-gradient launch that was issued before them
+        int prio_lo = 0, prio_hi = 0;
+        PG_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        PG_CUDA(cudaStreamCreateWithPriority(&m->comm_stream, cudaStreamNonBlocking, prio_hi));
         PG_CUDA(cudaEventCreateWithFlags(&m->ev_compute, cudaEventDisableTiming));
         PG_CUDA(cudaEventCreateWithFlags(&m->ev_comm, cudaEventDisableTiming));
+        PG_CUDA(cudaEventCreateWithFlags(&m->ev_stats, cudaEventDisableTiming));
     }
     PG_CUDA(cudaEventRecord(m->ev_compute, st));
     PG_CUDA(cudaStreamWaitEvent(m->comm_stream, m->ev_compute, 0));
@@ -533,6 +538,7 @@ int pgmvae_model_destroy(pgmvae_model* m) {
     if (m->ev_fork) cudaEventDestroy(m->ev_fork);
     if (m->ev_compute) cudaEventDestroy(m->ev_compute);
     if (m->ev_comm) cudaEventDestroy(m->ev_comm);
+    if (m->ev_stats) cudaEventDestroy(m->ev_stats);
     delete m;
     return PGMVAE_OK;
 }
@@ -746,6 +752,7 @@ int run_step(pgmvae_model* m, const uint8_t* y, int y_on_device, int B, int glob
                 PG_TRY(pg_comm_allreduce(comm, m->stat_c, (int64_t)V * K, 0, m->comm_stream));
             }
             PG_TRY(pg_comm_group_end(comm));
+            PG_CUDA(cudaEventRecord(m->ev_stats, m->comm_stream));
             overlapped = true;
         }
         if (flags & STEP_FWD_ONLY) continue;
@@ -777,9 +784,14 @@ int run_step(pgmvae_model* m, const uint8_t* y, int y_on_device, int B, int glob
                 q.db = m->grads + L.b_off + (size_t)g0 * L.pout; q.db_gs = L.pout;
                 q.G = Gn; q.B = B; q.in = L.in; q.out = L.out; q.zero_row_base = l == 0 ? g0 : -1;
             }
+            // Data parallel through NCCL: one launch + ONE all-reduce of the whole gradient buffer behind it (a few MB:
+            // latency-bound, ~the cost of the exposed last bucket) beats ten launches feeding three overlapped
+            // buckets; PGMVAE_DP_BUCKETS=1 keeps the bucketed schedule (large models: bandwidth-bound exchange).
             const bool per_layer = getenv("PGMVAE_WGRAD_PER_LAYER") != nullptr;
-            if (!per_layer && !(overlap && !use_p2p) && pg_dense_wgrad_multi_supported(pr, 10)) {
+            const bool buckets = overlap && !use_p2p && getenv("PGMVAE_DP_BUCKETS") != nullptr;
+            if (!per_layer && !buckets && pg_dense_wgrad_multi_supported(pr, 10)) {
                 PG_TRY(pg_dense_wgrad_multi_tc(ctx, st, pr, 10));
+                if (overlap && !use_p2p) PG_TRY(overlapped_allreduce(m, comm, m->grads, (int64_t)trainable, 0));
                 continue;
             }
         }
@@ -877,8 +889,17 @@ int run_step(pgmvae_model* m, const uint8_t* y, int y_on_device, int B, int glob
         }
     }
 
+    auto ema_update = [&]() -> int {
+        if ((flags & STEP_NO_UPDATE) || !m->ema || (flags & STEP_NO_EMA)) return PGMVAE_OK;
+        m->step_c += 1; m->step_w += 1;
+        return pgmvae_ema_apply(ctx, st, m->stat_c, m->stat_w, m->biased_c, m->biased_w, m->ema_c, m->ema_w, m->E(), V, K,
+                                Dp, Dp, m->decay, m->epsilon, m->step_c, 1);
+    };
     if (comm && overlapped) {
-        // join: the optimiser / EMA update / metrics wait for the exchanges issued along the way
+        // join: the statistics were exchanged long ago, so the codebook update runs while the gradient exchange is
+        // still in flight; the optimiser waits for that one
+        PG_CUDA(cudaStreamWaitEvent(st, m->ev_stats, 0));
+        PG_TRY(ema_update());
         PG_CUDA(cudaEventRecord(m->ev_comm, m->comm_stream));
         PG_CUDA(cudaStreamWaitEvent(st, m->ev_comm, 0));
     } else if (comm) {
@@ -911,13 +932,7 @@ int run_step(pgmvae_model* m, const uint8_t* y, int y_on_device, int B, int glob
                                     1e-7));
         }
     }
-    if (!(flags & STEP_NO_UPDATE)) {
-        if (m->ema && !(flags & STEP_NO_EMA)) {
-            m->step_c += 1; m->step_w += 1;
-            PG_TRY(pgmvae_ema_apply(ctx, st, m->stat_c, m->stat_w, m->biased_c, m->biased_w, m->ema_c, m->ema_w, m->E(),
-                                    V, K, Dp, Dp, m->decay, m->epsilon, m->step_c, 1));
-        }
-    }
+    if (!(comm && overlapped)) PG_TRY(ema_update());
     if (metrics4) {
         PG_CUDA(cudaMemcpyAsync(m->acc_host, m->acc, 4 * sizeof(double), cudaMemcpyDeviceToHost, st));
         PG_CUDA(cudaStreamSynchronize(st));
