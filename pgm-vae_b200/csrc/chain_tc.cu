@@ -47,7 +47,7 @@ struct ChainP {
     int nst;
     PgChainStage st[PG_CHAIN_MAX_STAGES];
     int G, g0, B, V, Vp, D, Dp, K, vq_stage;
-    int tiles_m, tiles_real, tmem_cols, nbias, nch, sub_cols, tab_floats;
+    int tiles_m, tiles_real, tmem_cols, nbias, nch, sub_cols, tab_floats, tail_ok;
     uint32_t stage_bytes;
     // layer-0 operand / targets
     const float* a0; long long a0_gs; int lda0, a0_cols;    // fwd: yf [B][Vp] (shared); bwd: dpre of the top layer
@@ -239,9 +239,27 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ Cha
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int items = p.G * p.tiles_m;         // item = (variable, group of nch consecutive 128-row tiles)
-    // consecutive items per CTA: mostly the same variable, so its codebook and biases stay in shared memory
-    const int item_beg = (int)((long long)blockIdx.x * items / gridDim.x);
-    const int item_end = (int)((long long)(blockIdx.x + 1) * items / gridDim.x);
+    // Consecutive items per CTA: mostly the same variable, so its codebook and biases stay in shared memory.
+    // items = q * grid + rem: when the rem left-over items are few they are not handed out whole (which makes the
+    // kernel as long as q + 1 items on a few CTAs while the others idle) but as single tiles, one per CTA, that run
+    // in chain 0 alone at the end (a lone chain has the SM to itself and takes about half the time of a full item).
+    int item_beg, item_end, tail_item = -1, tail_sel = 0;
+    {
+        const int grid = (int)gridDim.x, q = items / grid, rem = items - q * grid, b = (int)blockIdx.x;
+        if (p.tail_ok && p.nch > 1 && q > 0 && rem > 0 && rem * p.nch <= grid) {
+            item_beg = b * q;
+            item_end = item_beg + q;
+            if (b < rem * p.nch) {
+                tail_item = q * grid + b / p.nch;
+                tail_sel = b % p.nch;
+                if ((tail_item % p.tiles_m) * p.nch + tail_sel >= p.tiles_real) tail_item = -1;     // padding tile
+            }
+        } else {
+            item_beg = (int)((long long)b * items / grid);
+            item_end = (int)((long long)(b + 1) * items / grid);
+        }
+    }
+    const int n_main = item_end - item_beg, n_slots = n_main + (tail_item >= 0 ? 1 : 0);
 
     if (warp == 0 && lane == 0) {
         for (int j = 0; j < p.nst; ++j) tc::tma_prefetch_desc(&maps.m[j]);
@@ -267,7 +285,8 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ Cha
     if (warp == 0) {
         // ===================== TMA producer: weight k-blocks of every stage of every item
         uint32_t s = 0, ph = 0;
-        for (int item = item_beg; item < item_end; ++item) {
+        for (int sl = 0; sl < n_slots; ++sl) {
+            const int item = sl < n_main ? item_beg + sl : tail_item;
             const int g = item / p.tiles_m;
             for (int j = 0; j < p.nst; ++j) {
                 const PgChainStage& S = p.st[j];
@@ -340,9 +359,24 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ Cha
             }
         };
         double acc_sq = 0.0, acc_ab = 0.0, acc_vq = 0.0;
-        for (int item = item_beg; item < item_end; ++item) {
+        for (int sl = 0; sl < n_slots; ++sl) {
+            const bool tail = sl >= n_main;
+            const int item = tail ? tail_item : item_beg + sl;
+            if (tail && ch != 0) {
+                // this chain sits the single-tile item out; its issuer still hands every weight k-block back
+                if (issuer) {
+                    for (int j = 0; j < p.nst; ++j)
+                        for (int kb = 0; kb < p.st[j].kblocks; ++kb, ++wseq) {
+                            const uint32_t slot = wseq % CH_RING, gen = wseq / CH_RING;
+                            tc::mbar_wait(&b_full[slot], gen & 1);
+                            if (lane == 0) tc::mbar_arrive(&b_empty[slot]);
+                            __syncwarp();
+                        }
+                }
+                continue;
+            }
             const int g = item / p.tiles_m, mt = item - g * p.tiles_m;
-            const int row = (mt * p.nch + ch) * CH_TM + r;
+            const int row = (mt * p.nch + (tail ? tail_sel : ch)) * CH_TM + r;
             const bool valid = row < p.B;
             const int rowc = valid ? row : 0;
             // ---- codebook of this variable -> shared memory, |e|^2 in the order every fp32 path uses
@@ -591,6 +625,7 @@ int pg_chain_launch(pgmvae_ctx* ctx, cudaStream_t st, const PgChainArgs& a) {
     p.nch = std::max(1, std::min({CH_MAXCH, 512 / std::max(1, p.sub_cols), p.tiles_real}));
     if (const char* ev = getenv("PGMVAE_CHAINS")) p.nch = std::max(1, std::min(p.nch, atoi(ev)));
     p.tiles_m = (int)pg_cdiv(p.tiles_real, p.nch);
+    p.tail_ok = getenv("PGMVAE_CHAIN_NO_TAIL") == nullptr;
     p.tmem_cols = 32;
     while (p.tmem_cols < p.nch * p.sub_cols) p.tmem_cols <<= 1;
     p.stage_bytes = stage_bytes;
