@@ -127,26 +127,30 @@ vq_assign_f16_kernel(const __grid_constant__ CUtensorMap mapE, const Vq16P p) {
     uint8_t* sB = smem;                                                // [stages][kblocks][BN * 128]
     float2* ring = reinterpret_cast<float2*>(sB + (size_t)p.stages * stage_bytes);   // [RING][TMR]
     uint64_t* bars = reinterpret_cast<uint64_t*>(ring + RING * C::TMR);
-    uint64_t* a_full = bars + 0;
-    uint64_t* acc_full = bars + 1;                 // [2]
-    uint64_t* acc_empty = bars + 3;                // [2]
-    uint64_t* b_full = bars + 5;                   // [MAX_STAGES]
-    uint64_t* b_empty = bars + 5 + MAX_STAGES;     // [MAX_STAGES]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5 + 2 * MAX_STAGES);
+    // every 128-row sub-tile is its own pipeline (own issuer warp, own barriers): its four epilogue warps only
+    // ever wait for each other, not for the slowest of all 4 * SUB warps of the CTA
+    uint64_t* a_full = bars + 0;                   // [3]      z of the sub-tile sits in TMEM
+    uint64_t* acc_full = bars + 3;                 // [3][2]
+    uint64_t* acc_empty = bars + 9;                // [3][2]
+    uint64_t* b_full = bars + 15;                  // [MAX_STAGES]
+    uint64_t* b_empty = bars + 15 + MAX_STAGES;    // [MAX_STAGES]   one arrival per sub-tile pipeline
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15 + 2 * MAX_STAGES);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int items = p.G * p.tiles_m;
 
     if (warp == 0 && lane == 0) tc::tma_prefetch_desc(&mapE);
     if (warp == 1 && lane == 0) {
-        tc::mbar_init(a_full, C::EPI_WARPS);
-        for (int s = 0; s < 2; ++s) {
-            tc::mbar_init(&acc_full[s], 1);
-            tc::mbar_init(&acc_empty[s], C::EPI_WARPS);      // one arrival per epilogue warp
+        for (int u = 0; u < 3; ++u) {
+            tc::mbar_init(&a_full[u], 4);                    // one arrival per epilogue warp of the sub-tile
+            for (int s = 0; s < 2; ++s) {
+                tc::mbar_init(&acc_full[u * 2 + s], 1);
+                tc::mbar_init(&acc_empty[u * 2 + s], 4);
+            }
         }
         for (int s = 0; s < MAX_STAGES; ++s) {
             tc::mbar_init(&b_full[s], 1);
-            tc::mbar_init(&b_empty[s], 1);
+            tc::mbar_init(&b_empty[s], SUB);
         }
         tc::fence_barrier_init();
     }
@@ -176,33 +180,30 @@ vq_assign_f16_kernel(const __grid_constant__ CUtensorMap mapE, const Vq16P p) {
                 if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1; }
             }
         }
-    } else if (warp == 1) {
-        // ===================== MMA issuer (warp-uniform loop, one elected lane issues)
+    } else if (warp >= 1 && warp <= SUB) {
+        // ===================== MMA issuers: warp 1 + u serves sub-tile u (warp-uniform loop, one elected lane issues)
+        const int u = warp - 1;
         const uint32_t idesc = tc::make_idesc(0, TM, C::BN, 0, 0);
         const uint64_t descB0 = tc::make_smem_desc(tc::smem_u32(sB), 16, 1024);
         const uint32_t stage_stride = (uint32_t)stage_bytes >> 4;
-        const uint32_t a_sub = (uint32_t)(p.KD >> 1);        // TMEM columns of one sub-tile's z operand
+        const uint32_t a_tmem = tmem_base + u * (uint32_t)(p.KD >> 1);     // this sub-tile's z operand
         uint32_t it = 0, item_n = 0, s = 0, ph = 0;
         for (int item = blockIdx.x; item < items; item += gridDim.x, ++item_n) {
-            tc::mbar_wait(a_full, item_n & 1);               // z of this row tile sits in TMEM
+            tc::mbar_wait(&a_full[u], item_n & 1);           // z of this sub-tile sits in TMEM
             for (int t = 0; t < p.tiles_n; ++t, ++it) {
                 const uint32_t ab = it & 1, aph = (it >> 1) & 1;
                 tc::mbar_wait(&b_full[s], ph);
-                tc::mbar_wait(&acc_empty[ab], aph ^ 1);
+                tc::mbar_wait(&acc_empty[u * 2 + ab], aph ^ 1);
                 tc::fence_after_thread_sync();
                 if (tc::elect_one()) {
                     const uint64_t descB = descB0 + (uint64_t)(s * stage_stride);
-#pragma unroll
-                    for (int sub = 0; sub < SUB; ++sub) {
-                        const uint32_t d_tmem = tmem_base + A_COLS + (ab * SUB + sub) * C::BN;
-                        const uint32_t a_tmem = tmem_base + sub * a_sub;
-                        for (int ks = 0; ks < p.ksteps; ++ks) {
-                            const uint32_t offB = (uint32_t)((ks >> 2) * B_KB_BYTES + (ks & 3) * 32) >> 4;
-                            tc::mma_f16_ts(d_tmem, a_tmem + ks * 8, descB + offB, idesc, ks > 0 ? 1u : 0u);
-                        }
+                    const uint32_t d_tmem = tmem_base + A_COLS + (ab * SUB + u) * C::BN;
+                    for (int ks = 0; ks < p.ksteps; ++ks) {
+                        const uint32_t offB = (uint32_t)((ks >> 2) * B_KB_BYTES + (ks & 3) * 32) >> 4;
+                        tc::mma_f16_ts(d_tmem, a_tmem + ks * 8, descB + offB, idesc, ks > 0 ? 1u : 0u);
                     }
-                    tc::mma_commit(&b_empty[s]);      // smem stage free once these MMAs have read it
-                    tc::mma_commit(&acc_full[ab]);    // scores ready for the epilogue
+                    tc::mma_commit(&b_empty[s]);             // the stage is free once every sub-tile's MMAs have read it
+                    tc::mma_commit(&acc_full[u * 2 + ab]);   // scores ready for this sub-tile's epilogue warps
                 }
                 __syncwarp();
                 if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1; }
@@ -255,7 +256,7 @@ vq_assign_f16_kernel(const __grid_constant__ CUtensorMap mapE, const Vq16P p) {
                 tc::tmem_st_wait();
                 tc::fence_before_thread_sync();
                 __syncwarp();
-                if (lane == 0) tc::mbar_arrive(a_full);
+                if (lane == 0) tc::mbar_arrive(&a_full[sub]);
             }
             const float znorm = sqrtf(zz);
             // margins in distance units (d = |z|^2 - 2 s); the scores use half of them
@@ -311,7 +312,7 @@ vq_assign_f16_kernel(const __grid_constant__ CUtensorMap mapE, const Vq16P p) {
             float va[32], vb[32];
             {
                 const uint32_t ab = it & 1;
-                tc::mbar_wait(&acc_full[ab], (it >> 1) & 1);
+                tc::mbar_wait(&acc_full[sub * 2 + ab], (it >> 1) & 1);
                 tc::fence_after_thread_sync();
                 tc::tmem_ld_32x32(acc_addr + ab * SUB * C::BN, va);
             }
@@ -323,10 +324,10 @@ vq_assign_f16_kernel(const __grid_constant__ CUtensorMap mapE, const Vq16P p) {
                 tc::tmem_ld_wait(vb);
                 tc::fence_before_thread_sync();
                 __syncwarp();
-                if (lane == 0) tc::mbar_arrive(&acc_empty[ab]);          // both chunks of this buffer are in registers
+                if (lane == 0) tc::mbar_arrive(&acc_empty[sub * 2 + ab]);          // both chunks of this buffer are in registers
                 if (t + 1 < p.tiles_n) {
                     const uint32_t nb = (git + 1) & 1;
-                    tc::mbar_wait(&acc_full[nb], ((git + 1) >> 1) & 1);
+                    tc::mbar_wait(&acc_full[sub * 2 + nb], ((git + 1) >> 1) & 1);
                     tc::fence_after_thread_sync();
                     tc::tmem_ld_32x32(acc_addr + nb * SUB * C::BN, va);
                 }
