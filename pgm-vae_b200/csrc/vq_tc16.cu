@@ -37,7 +37,7 @@ namespace {
 
 constexpr int TM = 128;                       // rows per MMA (TMEM lanes)
 constexpr int KB_BYTES = 128;                 // one k-block = one 128-byte swizzle row = 64 halves
-constexpr int RING = 16;                      // recorded (chunk max, code) pairs kept per row
+constexpr int RING = 8;                       // recorded 8-code groups kept per row: (group max, first code) + the 8 scores
 constexpr int MAX_STAGES = 6;
 constexpr int A_COLS = 128;                   // TMEM columns reserved for the z operand
 
@@ -125,8 +125,11 @@ vq_assign_f16_kernel(const __grid_constant__ CUtensorMap mapE, const Vq16P p) {
     constexpr int B_KB_BYTES = C::BN * KB_BYTES;                       // one k-block of one code tile
     const int stage_bytes = p.kblocks * B_KB_BYTES;
     uint8_t* sB = smem;                                                // [stages][kblocks][BN * 128]
-    float2* ring = reinterpret_cast<float2*>(sB + (size_t)p.stages * stage_bytes);   // [RING][TMR]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(ring + RING * C::TMR);
+    // record ring, three row-contiguous planes (a warp's 32 rows are 16 / 8 bytes apart: conflict-free stores)
+    float4* ringA = reinterpret_cast<float4*>(sB + (size_t)p.stages * stage_bytes);   // [RING][TMR] scores 0..3
+    float4* ringB = ringA + RING * C::TMR;                                           // [RING][TMR] scores 4..7
+    float2* ringH = reinterpret_cast<float2*>(ringB + RING * C::TMR);                // [RING][TMR] (group max, first code)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(ringH + RING * C::TMR);
     // every 128-row sub-tile is its own pipeline (own issuer warp, own barriers): its four epilogue warps only
     // ever wait for each other, not for the slowest of all 4 * SUB warps of the CTA
     uint64_t* a_full = bars + 0;                   // [3]      z of the sub-tile sits in TMEM
@@ -215,7 +218,9 @@ vq_assign_f16_kernel(const __grid_constant__ CUtensorMap mapE, const Vq16P p) {
         const int sub = (warp - 4) >> 2;               // 128-row sub-tile
         const int r = sub * TM + q * 32 + lane;
         const float emax = *p.emax;
-        float2* myring = ring + r;                     // slot i at myring[i * TMR]
+        float4* myA = ringA + r;                       // slot i at my?[i * TMR]
+        float4* myB = ringB + r;
+        float2* myH = ringH + r;
         const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
         uint32_t it = 0;
         for (int item = blockIdx.x; item < items; item += gridDim.x) {
@@ -283,23 +288,19 @@ vq_assign_f16_kernel(const __grid_constant__ CUtensorMap mapE, const Vq16P p) {
                                       fmaxf(v[8 * qq + 6], v[8 * qq + 7]));
                 const float cm = fmaxf(tc::max3(gm[0], gm[1], gm[2]), gm[3]);
                 if (__any_sync(0xffffffffu, cm >= thr)) {
-                    // some row of this warp has a score within the band of its running maximum
+                    // some row of this warp has a score within the band of its running maximum: that row records
+                    // every 8-code group whose maximum is in the band -- the group's eight scores go to the ring as
+                    // they are (three stores), which code(s) matter is sorted out once, at the end of the row
                     runmax = fmaxf(runmax, cm);
                     thr = runmax - margin;
 #pragma unroll
                     for (int qq = 0; qq < 4; ++qq) {
-                        if (!__any_sync(0xffffffffu, gm[qq] >= thr)) continue;
-                        uint32_t mask = 0;
-#pragma unroll
-                        for (int j = 0; j < 8; ++j)
-                            if (v[8 * qq + j] >= thr) mask |= 1u << j;
-                        const int kbase = n * 32 + 8 * qq;       // chunks are consecutive 32-code blocks
-                        while (mask) {
-                            const int j = __ffs(mask) - 1;
-                            mask &= mask - 1;
-                            float2* slot = myring + (cnt & (RING - 1)) * C::TMR;
-                            if (cnt >= RING) evmax = fmaxf(evmax, slot->x);
-                            *slot = make_float2(gm[qq], __int_as_float(kbase + j));   // bound: s_k <= group max
+                        if (gm[qq] >= thr) {
+                            const int sl = (cnt & (RING - 1)) * C::TMR;
+                            if (cnt >= RING) evmax = fmaxf(evmax, myH[sl].x);
+                            myH[sl] = make_float2(gm[qq], __int_as_float(n * 32 + 8 * qq));
+                            myA[sl] = make_float4(v[8 * qq], v[8 * qq + 1], v[8 * qq + 2], v[8 * qq + 3]);
+                            myB[sl] = make_float4(v[8 * qq + 4], v[8 * qq + 5], v[8 * qq + 6], v[8 * qq + 7]);
                             ++cnt;
                         }
                     }
@@ -342,13 +343,22 @@ vq_assign_f16_kernel(const __grid_constant__ CUtensorMap mapE, const Vq16P p) {
                 bool ok = !zbad && (runmax > -3.0e38f) && (runmax < 3.0e38f) && !(evmax >= thr_f) && cnt > 0;
                 int nq = 0, k0 = 0;
                 const int nring = cnt < RING ? cnt : RING;
-                if (ok) {
-                    for (int i = 0; i < nring; ++i) {
-                        const float2 c = myring[i * C::TMR];
-                        if (c.x >= thr_f && __float_as_int(c.y) < p.K) { k0 = __float_as_int(c.y); ++nq; }
+                // candidates: codes of the recorded groups whose score lies in the band of the FINAL maximum
+                // (bit j of cmask[i]: code j of ring entry i)
+                uint32_t cmask[RING];
+#pragma unroll
+                for (int i = 0; i < RING; ++i) {
+                    cmask[i] = 0u;
+                    if (ok && i < nring && myH[i * C::TMR].x >= thr_f) {
+                        const float4 a = myA[i * C::TMR], b = myB[i * C::TMR];
+                        const int kb = __float_as_int(myH[i * C::TMR].y);
+                        const float sc[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            if (sc[j] >= thr_f && kb + j < p.K) { cmask[i] |= 1u << j; k0 = kb + j; ++nq; }
                     }
-                    ok = nq >= 1;
                 }
+                if (ok) ok = nq >= 1;
                 if (ok) {
                     int bi = k0;
                     if (nq > 1 || p.best || p.gap) {
@@ -356,16 +366,20 @@ vq_assign_f16_kernel(const __grid_constant__ CUtensorMap mapE, const Vq16P p) {
                         float best = INFINITY, second = INFINITY;
                         bi = 0x7fffffff;
                         const float* eg = p.e + (long long)g * p.e_gs;
-                        for (int i = 0; i < nring; ++i) {
-                            const float2 c = myring[i * C::TMR];
-                            const int k = __float_as_int(c.y);
-                            if (!(c.x >= thr_f) || k >= p.K) continue;
-                            const float* er = eg + (long long)k * p.lde;
-                            float acc = 0.f;
-                            for (int d = 0; d < p.D; ++d) acc = fmaf(zr[d], __ldg(er + d), acc);
-                            const float dist = (zz - 2.0f * acc) + __ldg(p.ee + (long long)g * p.Kpad + k);
-                            if (dist < best || (dist == best && k < bi)) { second = best; best = dist; bi = k; }
-                            else if (dist < second) second = dist;
+#pragma unroll
+                        for (int i = 0; i < RING; ++i) {
+                            uint32_t mk = cmask[i];
+                            const int kb = mk ? __float_as_int(myH[i * C::TMR].y) : 0;
+                            while (mk) {
+                                const int k = kb + __ffs(mk) - 1;
+                                mk &= mk - 1;
+                                const float* er = eg + (long long)k * p.lde;
+                                float acc = 0.f;
+                                for (int d = 0; d < p.D; ++d) acc = fmaf(zr[d], __ldg(er + d), acc);
+                                const float dist = (zz - 2.0f * acc) + __ldg(p.ee + (long long)g * p.Kpad + k);
+                                if (dist < best || (dist == best && k < bi)) { second = best; best = dist; bi = k; }
+                                else if (dist < second) second = dist;
+                            }
                         }
                         if (p.best) p.best[o] = best;
                         // exact gap when a runner-up lies inside the error band, otherwise a lower bound
@@ -455,7 +469,7 @@ template <int SUB>
 int launch16(pgmvae_ctx* ctx, cudaStream_t st, const CUtensorMap& mapE, Vq16P& p) {
     using C = Cfg<SUB>;
     p.tiles_m = (int)pg_cdiv(p.B, C::TMR);
-    const size_t fixed = 1024 + (size_t)RING * C::TMR * sizeof(float2) + 256;
+    const size_t fixed = 1024 + (size_t)RING * C::TMR * (2 * sizeof(float4) + sizeof(float2)) + 256;
     const size_t stage_bytes = (size_t)p.kblocks * C::BN * KB_BYTES;
     p.stages = MAX_STAGES;
     while (p.stages > 2 && fixed + p.stages * stage_bytes > ctx->smem_optin) --p.stages;
