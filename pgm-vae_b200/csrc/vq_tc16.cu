@@ -201,9 +201,17 @@ vq_assign_f16_kernel(const __grid_constant__ CUtensorMap mapE, const Vq16P p) {
                 if (tc::elect_one()) {
                     const uint64_t descB = descB0 + (uint64_t)(s * stage_stride);
                     const uint32_t d_tmem = tmem_base + A_COLS + (ab * SUB + u) * C::BN;
-                    for (int ks = 0; ks < p.ksteps; ++ks) {
-                        const uint32_t offB = (uint32_t)((ks >> 2) * B_KB_BYTES + (ks & 3) * 32) >> 4;
-                        tc::mma_f16_ts(d_tmem, a_tmem + ks * 8, descB + offB, idesc, ks > 0 ? 1u : 0u);
+                    constexpr int KBB = C::BN * KB_BYTES;
+                    if (p.ksteps == 5) {         // D = 64 (+ the two correction columns): straight-line, literal offsets
+#pragma unroll
+                        for (int ks = 0; ks < 5; ++ks)
+                            tc::mma_f16_ts(d_tmem, a_tmem + ks * 8, descB + ((uint32_t)((ks >> 2) * KBB + (ks & 3) * 32) >> 4),
+                                           idesc, ks > 0 ? 1u : 0u);
+                    } else {
+                        for (int ks = 0; ks < p.ksteps; ++ks) {
+                            const uint32_t offB = (uint32_t)((ks >> 2) * KBB + (ks & 3) * 32) >> 4;
+                            tc::mma_f16_ts(d_tmem, a_tmem + ks * 8, descB + offB, idesc, ks > 0 ? 1u : 0u);
+                        }
                     }
                     tc::mma_commit(&b_empty[s]);             // the stage is free once every sub-tile's MMAs have read it
                     tc::mma_commit(&acc_full[u * 2 + ab]);   // scores ready for this sub-tile's epilogue warps
