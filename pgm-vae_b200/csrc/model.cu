@@ -185,6 +185,9 @@ struct pgmvae_model {
     unsigned int* p2p_counter = nullptr;
     int* p2p_err = nullptr;            // pinned host word: a peer barrier timed out
     std::vector<void*> ipc_opened;
+    // stage 2 (count) walks the data in slabs larger than the training batch: nothing but codes and counts
+    // leaves the SM, so the slab only needs its own copy of the data (uint8 + fp32)
+    uint8_t* cnt_y8 = nullptr; float* cnt_yf = nullptr; int cnt_rows = 0;
     cudaStream_t aux_stream[2] = {nullptr, nullptr};
     cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
 
@@ -406,15 +409,16 @@ void chain_bwd_stages(const pgmvae_model* m, int g0, int j0, PgChainArgs& a) {
 
 // encoder + assignment (+ PLL histogram when n1/n0 are given) in one launch
 int chain_encode(pgmvae_model* m, int g0, int Gn, int B, const uint8_t* y_dev, unsigned long long* n1,
-                 unsigned long long* n0) {
+                 unsigned long long* n0, const float* yf = nullptr) {
     PgChainArgs a{};
     a.mode = PG_CHAIN_ENCODE;
     chain_fwd_stages(m, g0, 0, 5, a);
     for (int j = 0; j < 5; ++j) a.st[j].outp = nullptr;        // nothing but the codes leaves the SM
     chain_common(m, g0, Gn, B, a);
     a.vq_stage = 4;
-    a.a0 = m->yf; a.a0_gs = 0; a.lda0 = m->Vp; a.a0_cols = m->Vp;
+    a.a0 = yf ? yf : m->yf; a.a0_gs = 0; a.lda0 = m->Vp; a.a0_cols = m->Vp;
     a.y8 = y_dev; a.ldy8 = m->V; a.n1 = n1; a.n0 = n0;
+    if (n1) a.idx = nullptr;                                   // counting: the codes never leave the SM
     return pg_chain_launch(m->ctx, m->ctx->stream, a);
 }
 
@@ -987,6 +991,27 @@ int pgmvae_model_count(pgmvae_model* m, const uint8_t* y, int y_on_device, int64
     const size_t cs = (size_t)m->V * m->K;
     PG_CUDA(cudaMemsetAsync(m->n1, 0, cs * 8, st));
     PG_CUDA(cudaMemsetAsync(m->n0, 0, cs * 8, st));
+    if (use_chain(m) && m->Vg >= m->V && N > m->max_batch) {
+        // slabs of up to 32768 samples per launch: 86 tile triples per variable instead of 11, so the items divide
+        // evenly over the SMs, and an eighth of the launches
+        const int CB = (int)std::min<int64_t>(N, 32768);
+        if (m->cnt_rows < CB) {
+            PG_TRY(dev_alloc(m, (void**)&m->cnt_y8, (size_t)CB * m->V));
+            PG_TRY(dev_alloc(m, (void**)&m->cnt_yf, (size_t)CB * m->Vp * 4));
+            m->cnt_rows = CB;
+        }
+        for (int64_t s = 0; s < N; s += CB) {
+            const int B = (int)std::min<int64_t>(CB, N - s);
+            const uint8_t* y_dev = y + (size_t)s * m->V;
+            if (!y_on_device) {
+                PG_CUDA(cudaMemcpyAsync(m->cnt_y8, y_dev, (size_t)B * m->V, cudaMemcpyHostToDevice, st));
+                y_dev = m->cnt_y8;
+            }
+            PG_TRY(pgmvae_y_to_f32(ctx, st, y_dev, m->V, m->cnt_yf, m->Vp, B, m->V));
+            PG_TRY(chain_encode(m, 0, m->V, B, y_dev, m->n1, m->n0, m->cnt_yf));
+        }
+        N = 0;                                                   // (the loop below has nothing left to do)
+    }
     for (int64_t s = 0; s < N; s += m->max_batch) {
         const int B = (int)std::min<int64_t>(m->max_batch, N - s);
         const uint8_t* y_dev = nullptr;
