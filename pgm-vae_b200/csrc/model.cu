@@ -190,6 +190,10 @@ struct pgmvae_model {
     uint8_t* cnt_y8 = nullptr; float* cnt_yf = nullptr; int cnt_rows = 0;
     cudaStream_t aux_stream[2] = {nullptr, nullptr};
     cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
+    // the codebook update only needs the statistics of the forward pass: it runs on a side stream under the
+    // weight-gradient kernel
+    cudaStream_t ema_stream = nullptr;
+    cudaEvent_t ev_ema_fork = nullptr, ev_ema = nullptr;
 
     float* E() const { return params + e_off; }
     float* dE() const { return grads + e_off; }
@@ -540,6 +544,9 @@ int pgmvae_model_destroy(pgmvae_model* m) {
         if (m->ev_join[i]) cudaEventDestroy(m->ev_join[i]);
     }
     if (m->ev_fork) cudaEventDestroy(m->ev_fork);
+    if (m->ema_stream) cudaStreamDestroy(m->ema_stream);
+    if (m->ev_ema_fork) cudaEventDestroy(m->ev_ema_fork);
+    if (m->ev_ema) cudaEventDestroy(m->ev_ema);
     if (m->ev_compute) cudaEventDestroy(m->ev_compute);
     if (m->ev_comm) cudaEventDestroy(m->ev_comm);
     if (m->ev_stats) cudaEventDestroy(m->ev_stats);
@@ -720,7 +727,14 @@ int run_step(pgmvae_model* m, const uint8_t* y, int y_on_device, int B, int glob
     const float cscale = (float)(m->cost * 2.0 / n_lat);
 
     const bool chain = use_chain(m) && out_dev == nullptr;
-    bool overlapped = false, use_p2p = false;
+    bool overlapped = false, use_p2p = false, ema_done = false, ema_side = false;
+    auto ema_update = [&](cudaStream_t es) -> int {
+        if (ema_done || (flags & (STEP_NO_UPDATE | STEP_FWD_ONLY)) || !m->ema || (flags & STEP_NO_EMA)) return PGMVAE_OK;
+        ema_done = true;
+        m->step_c += 1; m->step_w += 1;
+        return pgmvae_ema_apply(ctx, es, m->stat_c, m->stat_w, m->biased_c, m->biased_w, m->ema_c, m->ema_w, m->E(), V, K,
+                                Dp, Dp, m->decay, m->epsilon, m->step_c, 1);
+    };
     for (int g0 = 0; g0 < V && chain; g0 += m->Vg) {
         const int Gn = std::min(m->Vg, V - g0);
         const int64_t MB = m->max_batch;
@@ -758,6 +772,21 @@ int run_step(pgmvae_model* m, const uint8_t* y, int y_on_device, int B, int glob
             PG_TRY(pg_comm_group_end(comm));
             PG_CUDA(cudaEventRecord(m->ev_stats, m->comm_stream));
             overlapped = true;
+            if (!ctx->profiling) PG_TRY(ema_update(m->comm_stream));      // right behind the exchanged statistics
+        } else if (Gn == V && comm == nullptr && !ctx->profiling && m->ema && !(flags & (STEP_NO_UPDATE | STEP_FWD_ONLY | STEP_NO_EMA))) {
+            // single GPU: the codebook update runs on a side stream under the kernels that follow
+            if (!m->ema_stream) {
+                int prio_lo = 0, prio_hi = 0;
+                PG_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+                PG_CUDA(cudaStreamCreateWithPriority(&m->ema_stream, cudaStreamNonBlocking, prio_hi));
+                PG_CUDA(cudaEventCreateWithFlags(&m->ev_ema_fork, cudaEventDisableTiming));
+                PG_CUDA(cudaEventCreateWithFlags(&m->ev_ema, cudaEventDisableTiming));
+            }
+            PG_CUDA(cudaEventRecord(m->ev_ema_fork, st));
+            PG_CUDA(cudaStreamWaitEvent(m->ema_stream, m->ev_ema_fork, 0));
+            PG_TRY(ema_update(m->ema_stream));
+            PG_CUDA(cudaEventRecord(m->ev_ema, m->ema_stream));
+            ema_side = true;
         }
         if (flags & STEP_FWD_ONLY) continue;
         if (!m->ema)    // q_latent_loss gradient wrt the codebook: 2 (q - z) / (V B D)   (core/quantizer.py:51)
@@ -893,17 +922,11 @@ int run_step(pgmvae_model* m, const uint8_t* y, int y_on_device, int B, int glob
         }
     }
 
-    auto ema_update = [&]() -> int {
-        if ((flags & STEP_NO_UPDATE) || !m->ema || (flags & STEP_NO_EMA)) return PGMVAE_OK;
-        m->step_c += 1; m->step_w += 1;
-        return pgmvae_ema_apply(ctx, st, m->stat_c, m->stat_w, m->biased_c, m->biased_w, m->ema_c, m->ema_w, m->E(), V, K,
-                                Dp, Dp, m->decay, m->epsilon, m->step_c, 1);
-    };
     if (comm && overlapped) {
         // join: the statistics were exchanged long ago, so the codebook update runs while the gradient exchange is
         // still in flight; the optimiser waits for that one
         PG_CUDA(cudaStreamWaitEvent(st, m->ev_stats, 0));
-        PG_TRY(ema_update());
+        PG_TRY(ema_update(st));
         PG_CUDA(cudaEventRecord(m->ev_comm, m->comm_stream));
         PG_CUDA(cudaStreamWaitEvent(st, m->ev_comm, 0));
     } else if (comm) {
@@ -936,7 +959,8 @@ int run_step(pgmvae_model* m, const uint8_t* y, int y_on_device, int B, int glob
                                     1e-7));
         }
     }
-    if (!(comm && overlapped)) PG_TRY(ema_update());
+    PG_TRY(ema_update(st));
+    if (ema_side) PG_CUDA(cudaStreamWaitEvent(st, m->ev_ema, 0));       // later work sees the new codebook
     if (metrics4) {
         PG_CUDA(cudaMemcpyAsync(m->acc_host, m->acc, 4 * sizeof(double), cudaMemcpyDeviceToHost, st));
         PG_CUDA(cudaStreamSynchronize(st));
