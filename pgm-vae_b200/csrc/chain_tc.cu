@@ -1,28 +1,29 @@
 // Chain kernels: a whole stack of packed per-variable dense layers in ONE launch, the
 // activations of a 128-sample tile never leaving the SM.
 //
-//   forward (training)  fd0..fd4 -> VQ (assignment, straight-through, commitment loss, EMA
-//                       statistics) -> fd5..fd9 -> sigmoid + MSE/MAE + d(loss)/d(pre-activation)
-//                       reference core/model.py:39-55, core/quantizer.py:120-162, run.py:61
+//   train               forward, then the dgrad stages of the same rows (19 stages): fd0..fd4 -> VQ (assignment,
+//                       straight-through, commitment loss, EMA statistics) -> fd5..fd9 -> sigmoid + MSE/MAE +
+//                       d(loss)/d(pre-activation) -> dgrad fd9..fd1 with the commitment gradient injected at the
+//                       VQ boundary      reference core/model.py:39-55, core/quantizer.py:120-162, run.py:61-62
+//   forward / backward  the two halves as separate launches (forward-only calls, PGMVAE_CHAIN_SPLIT=1)
 //   encode              fd0..fd4 -> VQ assignment (-> PLL histogram)   core/model.py:48, :58-82
-//   backward            the dgrad chain fd9 -> fd1 (autodiff of core/dense.py:106-110) with the
-//                       commitment gradient injected at the VQ boundary
 //
-// Layout of one CTA (192 threads, persistent over (variable, 128-row tile) items):
-//   warp 0   TMA producer: streams the weight k-blocks of every layer of every item through a
+// Layout of one CTA (64 + 128 * nch threads, persistent over (variable, nch x 128-row tile) items, nch <= 3
+// independent chains in flight):
+//   warp 0   TMA producer: streams the weight k-blocks of every stage of every item through a
 //            shared-memory ring; weights do not depend on activations, so it runs ahead of the
-//            compute across layers AND items
-//   warp 1   MMA issuer (tcgen05.mma kind::tf32, M = 128): the A operand is read from TENSOR
-//            MEMORY, where the previous layer's epilogue left the activations; B = weights from
-//            the ring; D = a second TMEM region.  Owns the TMEM allocation.
-//   warps 2-5 epilogue, one sample row per thread: tcgen05.ld the pre-activations, bias +
+//            compute across stages AND items; a slot is released when every chain has consumed it
+//   warp 1   owns the TMEM allocation (otherwise idle)
+//   warps 2.. epilogue, four per chain, one sample row per thread: tcgen05.ld the pre-activations, bias +
 //            activation (or the VQ / loss / act' step), store the row to HBM for the kernels that
-//            need it later (wgrad, backward), and tcgen05.st it back IN PLACE as the next A operand
-//   Two TMEM regions ping-pong: layer j reads region (j & 1), writes region (~j & 1).
+//            need it later (wgrad), and tcgen05.st it back IN PLACE as the next A operand.  The chain's
+//            first warp also ISSUES the chain's MMAs (tcgen05.mma kind::tf32, M = 128, A operand read from
+//            TENSOR MEMORY, B = weights from the ring) once the four warps have met at the chain's named barrier.
+//   Two TMEM regions ping-pong: stage j reads region (j & 1), writes region (~j & 1).
 //
-// What leaves the SM per layer is one write of the activations; nothing is read back except the
-// weights (L2-resident) -- against one read + one write per layer and ~47 launches per step for
-// the layer-by-layer kernels in dense_tc.cu.  Chains are used when the network is narrow
+// What leaves the SM per layer is one write of the activations (256-bit stores: a thread owns a row); nothing is
+// read back from HBM except the weights (L2-resident) -- against one read + one write per layer and ~47 launches
+// per step for the layer-by-layer kernels in dense_tc.cu.  Chains are used when the network is narrow
 // enough for TMEM (every padded width <= 256 and both regions within 512 columns), the codebook
 // fits shared memory and D <= 32; otherwise the per-layer kernels run.
 #include <stdlib.h>
@@ -231,7 +232,7 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ Cha
     uint64_t* bars = reinterpret_cast<uint64_t*>(sB + (size_t)CH_RING * p.stage_bytes);
     uint64_t* b_full = bars;                   // [CH_RING]
     uint64_t* b_empty = bars + CH_RING;        // [CH_RING]   one arrival per chain
-    uint64_t* a_ready = bars + 2 * CH_RING;    // [CH_MAXCH]  one arrival per epilogue warp of the chain
+    // (bars + 2 * CH_RING .. : CH_MAXCH spare slots)
     uint64_t* d_full = bars + 2 * CH_RING + CH_MAXCH;   // [CH_MAXCH]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * CH_RING + 2 * CH_MAXCH);
     float* tables = reinterpret_cast<float*>(bars + 2 * CH_RING + 2 * CH_MAXCH + 2);     // per chain: sE | sEE | sHist | sBias
@@ -268,7 +269,6 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ Cha
             tc::mbar_init(&b_empty[s], p.nch);   // a weight k-block is released once every chain has consumed it
         }
         for (int c = 0; c < CH_MAXCH; ++c) {
-            tc::mbar_init(&a_ready[c], 4);       // (unused: the chain's warps meet at a named barrier instead)
             tc::mbar_init(&d_full[c], 1);
         }
         tc::fence_barrier_init();

@@ -7,7 +7,8 @@
 //   forward : C[B,out] = A[B,in]   (K-major)  x  W[in,out]  (N contiguous -> MN-major B)
 //   dgrad   : C[B,in]  = dY[B,out] (K-major)  x  W[in,out] read as [n=in][k=out] (K-major B)
 //   wgrad   : C[in,out]= X[B,in] read as [k=b][m=in] (MN-major A) x dY[B,out] (MN-major B),
-//             reduction over the batch split across CTAs, fp32 reductions into dW
+//             reduction over the batch split across CTAs, fp32 vector reductions into dW;
+//             wgrad_multi_kernel runs the wgrad CTAs of ALL layers of a step as one launch
 //
 // One CTA computes one 128 x BN output tile of one variable: warp 0 = TMA producer over the
 // k-blocks (32 fp32 = one swizzle row per k-block, `stages`-deep ring), warp 1 = MMA issuer,

@@ -15,17 +15,20 @@
 //          the row tile (no fp16 copy of z in HBM, no shared-memory traffic for A)
 //   E      [BN codes, KD] fp16 tiles, TMA -> shared-memory ring (128-byte swizzle), B operand
 //   acc    SUB x [128, BN] fp32 in TMEM, double buffered (MMA of tile t+1 overlaps epilogue t)
-//   warp 0 TMA producer | warp 1 MMA issuer | warp 2 TMEM allocator | warps 4.. epilogue
+//   warp 0 TMA producer | warps 1..SUB MMA issuers, one per 128-row sub-tile (warp 2 also owns the TMEM
+//   allocation) | warps 4.. epilogue, four per sub-tile.  A sub-tile is its own pipeline (own issuer, own
+//   acc_full / acc_empty barriers): its warps never wait for the slowest warp of another sub-tile.
 //
 // Exactness.  fp16 products only PROPOSE candidates; fp32 decides.  eps bounds the error of an
 // approximate score (2^-10 |z| max|e| for round-to-nearest fp16 operands).  In ONE pass each
-// row keeps a running maximum m and records every code whose score is >= m - 2 eps at the time
-// it is seen, together with the maximum of its 8-code group.  m only grows, so the final
-// candidate set {k : s~_k >= m_final - 2 eps} is a subset of the recorded codes, and the true
-// arg-min is in it (header of vq_tc.cu).  A row with a single candidate is decided; rows with
-// several are re-scored with exactly the fp32 arithmetic of the CUDA-core kernel (lowest index
-// on ties).  Rows whose record ring overflowed with still-relevant entries (many identical dead
-// codes) or whose fp16 image is not finite go to the exact full-scan kernel.
+// row keeps a running maximum m and records every 8-code group whose maximum is >= m - 2 eps at
+// the time it is seen: the group maximum, its first code and its eight scores go to a ring in
+// shared memory.  m only grows, so the final candidate set {k : s~_k >= m_final - 2 eps} is a
+// subset of the recorded scores, and the true arg-min is in it (header of vq_tc.cu); which codes
+// they are is sorted out once, after the last tile.  A row with a single candidate is decided;
+// rows with several are re-scored with exactly the fp32 arithmetic of the CUDA-core kernel
+// (lowest index on ties).  Rows whose ring overflowed with still-relevant entries (many identical
+// dead codes) or whose fp16 image is not finite go to the exact full-scan kernel.
 #include <cuda_fp16.h>
 #include <stdlib.h>
 

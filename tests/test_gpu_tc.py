@@ -223,3 +223,69 @@ def test_chain_kernels_equal_layer_by_layer_kernels(ctx, monkeypatch, V, units, 
     assert (a[6] != b[6]).mean() <= 2e-3
     assert (a[4] + a[5]).sum() == (b[4] + b[5]).sum() == 2 * B * V
     assert np.abs(a[4].astype(np.int64) - b[4].astype(np.int64)).sum() <= 4e-3 * B * V
+
+
+def _step_snapshot(ctx, monkeypatch, env, V, units, D, K, B, ema=True, steps=2):
+    """Gradients of one step and the state after `steps` optimiser steps with the given environment switches."""
+    from core.model import VqVAE
+    from pgmvae import _ffi, data
+    for k in ("PGMVAE_WGRAD_PER_LAYER", "PGMVAE_CHAIN_SPLIT", "PGMVAE_CHAIN_NO_TAIL", "PGMVAE_NO_CHAIN"):
+        monkeypatch.delenv(k, raising=False)
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    y = data.synthetic_binary(steps * B, V, seed=7)
+    names = [f"fd{l}.{t}" for l in range(10) for t in ("kernel", "bias")]
+    ctx.set_precision(_ffi.PREC_TF32)
+    try:
+        m = VqVAE(units, V, D, K, cost=0.25, decay=0.99, ema=ema, seed=3, max_batch=B)
+        met = (C.c_double * 4)()
+        _ffi.check(_ffi.lib().pgmvae_model_train_step(m._h, y[:B].ctypes.data, 0, B, B, 1e-3, None, 1, met))
+        first = list(met)
+        grads = {n: m._get_tensor("grad." + n) for n in names}
+        mets = []
+        for s in range(steps):
+            _ffi.check(_ffi.lib().pgmvae_model_train_step(m._h, y[s * B:(s + 1) * B].ctypes.data, 0, B, B, 1e-3, None, 0, met))
+            mets.append(list(met))
+        return first, grads, np.array(mets), m._get_tensor("vq.embeddings"), m._get_tensor("fd3.kernel")
+    finally:
+        ctx.set_precision(_ffi.PREC_FP32)
+
+
+@pytest.mark.parametrize("switch", ["PGMVAE_WGRAD_PER_LAYER", "PGMVAE_CHAIN_SPLIT", "PGMVAE_CHAIN_NO_TAIL"])
+@pytest.mark.parametrize("V,units,D,K,B,ema", [(69, [50, 40, 30, 20], 16, 128, 4096, True),
+                                               (16, [15, 14, 13, 12], 4, 32, 53, False),
+                                               (200, [20, 12, 9, 8], 8, 16, 300, True)])
+def test_fast_paths_equal_their_unfused_counterparts(ctx, monkeypatch, switch, V, units, D, K, B, ema):
+    """The default training step -- forward + dgrad stages in one chain launch, all weight-gradient GEMMs in one
+    launch, left-over items as single tiles -- against the same step with one of these switched off: the arithmetic
+    is the same (tf32 products, fp32 accumulation), only the order of the fp32 reductions over the batch differs."""
+    a = _step_snapshot(ctx, monkeypatch, {}, V, units, D, K, B, ema)
+    b = _step_snapshot(ctx, monkeypatch, {switch: "1"}, V, units, D, K, B, ema)
+    np.testing.assert_allclose(b[0][:3], a[0][:3], rtol=1e-6)
+    for n in a[1]:
+        assert rel_err(b[1][n], a[1][n]) < 2e-5, (switch, n, rel_err(b[1][n], a[1][n]))
+    np.testing.assert_allclose(b[2][:, :3], a[2][:, :3], rtol=1e-5)
+    assert rel_err(b[3], a[3]) < 1e-5 and rel_err(b[4], a[4]) < 1e-4
+
+
+def test_count_in_slabs_equals_count_in_batches(ctx, monkeypatch):
+    """Stage 2 walks the data in slabs of up to 32768 samples when the chains are in use; the counts are the sums
+    of the counts of the training-batch-sized pieces (exactly: integers)."""
+    from core.model import VqVAE
+    from pgmvae import _ffi, data
+    V, units, D, K, B = 69, [50, 40, 30, 20], 16, 128, 512
+    y = data.synthetic_binary(40000, V, seed=9)
+    ctx.set_precision(_ffi.PREC_TF32)
+    try:
+        m = VqVAE(units, V, D, K, cost=0.25, decay=0.99, ema=True, seed=4, max_batch=B)
+        n1, n0 = m.count(y)                                  # 32768 + 7232 rows
+        p1 = np.zeros_like(n1)
+        p0 = np.zeros_like(n0)
+        for s in range(0, len(y), B):                        # <= max_batch rows per call: the per-batch path
+            a1, a0 = m.count(y[s:s + B])
+            p1 += a1
+            p0 += a0
+    finally:
+        ctx.set_precision(_ffi.PREC_FP32)
+    assert (n1 + n0).sum() == len(y) * V
+    assert np.array_equal(n1, p1) and np.array_equal(n0, p0)
