@@ -532,7 +532,7 @@ int pg_dense_wgrad_multi_tc(pgmvae_ctx* ctx, cudaStream_t st, const PgWgradProbl
         pgmvae_set_error("wgrad (multi): %d problems (1..%d)", n, WG_MAX);
         return PGMVAE_EINVAL;
     }
-    static WgradMultiP P;                 // 4.7 KB of kernel parameters (one host thread per context)
+    WgradMultiP P;                        // 4.7 KB of kernel parameters
     double bytes = 0.0, flops = 0.0, cost[WG_MAX];
     size_t smem = 0;
     // batch splits: the fewest that still give ~4 waves of CTAs over all problems together (a CTA spends a fixed

@@ -268,6 +268,22 @@ def test_fast_paths_equal_their_unfused_counterparts(ctx, monkeypatch, switch, V
     assert rel_err(b[3], a[3]) < 1e-5 and rel_err(b[4], a[4]) < 1e-4
 
 
+def test_single_tile_tail_with_two_chains(ctx, monkeypatch):
+    """Two chains per CTA (what a network with wider layers gets): 1104 items over 148 CTAs leave 68, which run
+    as 136 single tiles; same results as whole left-over items."""
+    V, units, D, K, B = 69, [50, 40, 30, 20], 16, 128, 4096
+    monkeypatch.setenv("PGMVAE_CHAINS", "2")
+    try:
+        a = _step_snapshot(ctx, monkeypatch, {}, V, units, D, K, B, True, steps=1)
+        b = _step_snapshot(ctx, monkeypatch, {"PGMVAE_CHAIN_NO_TAIL": "1"}, V, units, D, K, B, True, steps=1)
+    finally:
+        monkeypatch.delenv("PGMVAE_CHAINS", raising=False)
+    np.testing.assert_allclose(b[0][:3], a[0][:3], rtol=1e-6)
+    for n in a[1]:
+        assert rel_err(b[1][n], a[1][n]) < 2e-5, (n, rel_err(b[1][n], a[1][n]))
+    assert rel_err(b[3], a[3]) < 1e-5
+
+
 def test_count_in_slabs_equals_count_in_batches(ctx, monkeypatch):
     """Stage 2 walks the data in slabs of up to 32768 samples when the chains are in use; the counts are the sums
     of the counts of the training-batch-sized pieces (exactly: integers)."""
