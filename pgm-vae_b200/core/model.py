@@ -114,13 +114,14 @@ class VqVAE:
     def _setup_p2p(self):
         """Data parallel on one node: map every rank's gradient buffer into every other rank (CUDA IPC) so that the
         library can fuse the gradient exchange with Adam (pgmvae_model_p2p_*).  Collective: every rank creates its
-        model at the same point.  torch.distributed (gloo) only carries the 128 handle bytes.  Opt-in (PGMVAE_P2P=1): measured on
-        8 B200 the NCCL all-reduce of the gradient buffer (0.77 ms per cfg2 step) beats every rank reading all eight
-        buffers (0.80 ms); at 2 GPUs the two tie."""
+        model at the same point.  torch.distributed (gloo) only carries the 128 handle bytes."""
         comm = self.comm
         if comm is None or getattr(comm, "h", None) is None or comm.nranks < 2 or comm.nranks > 8:
             return
-        if os.environ.get("PGMVAE_P2P", "0") != "1":      # opt-in: NCCL (in-switch reduction) wins at 8 GPUs
+        # measured (cfg2 step): 2 GPUs 0.686 ms peer-to-peer vs 0.702 ms NCCL; 8 GPUs 0.80 vs 0.77 ms (every rank
+        # reads all eight buffers; NCCL reduces in the switch) -> default on for two ranks only, PGMVAE_P2P=0/1 overrides
+        want = os.environ.get("PGMVAE_P2P")
+        if want == "0" or (want != "1" and comm.nranks != 2):
             return
         import torch.distributed as dist
         buf = C.create_string_buffer(128)
