@@ -327,7 +327,9 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ Cha
         // tcgen05.mma itself (one elected lane) -- no polling warp that competes for issue slots, no mbarrier
         // round trip between the last tcgen05.st and the first MMA.  All chains consume the same k-block
         // sequence of the weight ring; a slot is released when every chain's MMAs have read it.
-        const bool issuer = ((warp - 2) & 3) == 0;
+        // the issuers of the three chains sit on three different schedulers (1, 2, 3; scheduler 0 hosts the TMA
+        // producer): with all of them on one, that scheduler's epilogue warps lagged and their siblings waited
+        const bool issuer = q4 == 1 + ch;
         const uint64_t dB_mn = tc::make_smem_desc(tc::smem_u32(sB), 4096, 512, 1);
         const uint64_t dB_k = tc::make_smem_desc(tc::smem_u32(sB), 16, 1024, 2);
         const uint32_t stage_stride = p.stage_bytes >> 4;
