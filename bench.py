@@ -151,7 +151,7 @@ def run_reference(args, wl):
         "e2e": {"value": sps, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def measured_traffic(kernel):
@@ -386,10 +386,35 @@ def run_ours(args, wl):
         "gpu_launches": launches, "clocks": clocks, "pll_eval": pll_eval, "vq_assign": vq_assign, "hbm_stages": hbm_stages,
         "loss_after": {"loss": met[0], "mse": met[1], "mae": met[2], "vq_loss": met[3]},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_RESULT_FD = None
+
+
+def claim_stdout():
+    """The contract is ONE JSON line on stdout, but libraries write there too (NCCL prints its version banner to
+    stdout when the communicator comes up).  From here on file descriptor 1 is stderr; the result line goes to the
+    original stdout through emit()."""
+    global _RESULT_FD
+    if _RESULT_FD is None:
+        sys.stdout.flush()
+        _RESULT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    text = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(text.decode())
+        sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_RESULT_FD, text)
 
 
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
