@@ -269,6 +269,11 @@ int pgmvae_model_set_adam_step(pgmvae_model* m, int64_t t);
  * pgmvae_model_train_step reduces the gradients through the communicator.                                  */
 int pgmvae_model_p2p_export(pgmvae_model* m, void* handles_out128);
 int pgmvae_model_p2p_import(pgmvae_model* m, int rank, int nranks, const void* all_handles);
+/* Reduce-scatter form (opt-in, not yet measured on hardware): rank r sums and updates only its 1/nranks of the
+ * parameters and writes the result into every rank's parameter buffer.  export_rs writes 3 x 64 bytes (gradient
+ * buffer, flag block, parameter buffer); import_rs takes nranks x 192 bytes in rank order.                     */
+int pgmvae_model_p2p_export_rs(pgmvae_model* m, void* handles_out192);
+int pgmvae_model_p2p_import_rs(pgmvae_model* m, int rank, int nranks, const void* all_handles);
 
 /* One training step on a batch y [B,V] uint8 (host or device pointer).
  * global_B is the batch size over all data-parallel ranks (== B without DP); comm may be NULL.

@@ -120,16 +120,22 @@ class VqVAE:
             return
         # measured (cfg2 step): 2 GPUs 0.686 ms peer-to-peer vs 0.702 ms NCCL; 8 GPUs 0.80 vs 0.77 ms (every rank
         # reads all eight buffers; NCCL reduces in the switch) -> default on for two ranks only, PGMVAE_P2P=0/1 overrides
+        # PGMVAE_P2P=2: the reduce-scatter form (every rank sums and updates 1/nranks of the parameters and writes
+        # it to the peers) -- built for more than two ranks, not yet measured
         want = os.environ.get("PGMVAE_P2P")
-        if want == "0" or (want != "1" and comm.nranks != 2):
+        if want == "0" or (want not in ("1", "2") and comm.nranks != 2):
             return
         import torch.distributed as dist
-        buf = C.create_string_buffer(128)
-        _ffi.check(_ffi.lib().pgmvae_model_p2p_export(self._h, buf))
+        rs = want == "2"
+        nbytes = 192 if rs else 128
+        lib = _ffi.lib()
+        buf = C.create_string_buffer(nbytes)
+        _ffi.check((lib.pgmvae_model_p2p_export_rs if rs else lib.pgmvae_model_p2p_export)(self._h, buf))
         handles = [None] * comm.nranks
         dist.all_gather_object(handles, buf.raw)
-        blob = C.create_string_buffer(b"".join(handles), 128 * comm.nranks)
-        _ffi.check(_ffi.lib().pgmvae_model_p2p_import(self._h, comm.rank, comm.nranks, blob))
+        blob = C.create_string_buffer(b"".join(handles), nbytes * comm.nranks)
+        _ffi.check((lib.pgmvae_model_p2p_import_rs if rs else lib.pgmvae_model_p2p_import)(self._h, comm.rank,
+                                                                                          comm.nranks, blob))
         dist.barrier()
 
     def _ensure_capacity(self, batch: int):

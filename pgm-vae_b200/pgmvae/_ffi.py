@@ -92,6 +92,8 @@ SIGNATURES = {
     "pgmvae_model_set_adam_step": (_i, [_vp, _i64]),
     "pgmvae_model_p2p_export": (_i, [_vp, _vp]),
     "pgmvae_model_p2p_import": (_i, [_vp, _i, _i, _vp]),
+    "pgmvae_model_p2p_export_rs": (_i, [_vp, _vp]),
+    "pgmvae_model_p2p_import_rs": (_i, [_vp, _i, _i, _vp]),
     "pgmvae_model_train_step": (_i, [_vp, _vp, _i, _i, _i, _f, _vp, _i, _vp]),
     "pgmvae_model_forward": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
     "pgmvae_model_encode": (_i, [_vp, _vp, _i, _i, _vp]),
