@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(256) p2p_sum_adam_kernel(const P2pArgs a) {
         for (int q = 0; q < a.R && good; ++q) {
             long long spins = 0;
             while (ld_volatile_i32(a.my_flags + q) < a.step) {
-                if (++spins > 20000000ll) { good = 0; break; }
+                if (++spins > 100000000ll) { good = 0; break; }
                 __nanosleep(100);
             }
         }
@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(256) p2p_rs_adam_kernel(const P2pArgs a) {
         for (int q = 0; q < a.R && good; ++q) {
             long long spins = 0;
             while (ld_volatile_i32(a.my_flags + q) < a.step) {
-                if (++spins > 20000000ll) { good = 0; break; }
+                if (++spins > 100000000ll) { good = 0; break; }
                 __nanosleep(100);
             }
         }
@@ -199,7 +199,7 @@ __global__ void p2p_wait_done_kernel(const int* my_flags, int R, int step, int* 
     if ((int)threadIdx.x < R) {
         long long spins = 0;
         while (ld_volatile_i32(my_flags + R + threadIdx.x) < step) {
-            if (++spins > 20000000ll) { *reinterpret_cast<volatile int*>(err) = 1; break; }
+            if (++spins > 100000000ll) { *reinterpret_cast<volatile int*>(err) = 1; break; }
             __nanosleep(100);
         }
     }
