@@ -229,7 +229,7 @@ def run_ours(args, wl):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     ctx = _ffi.get_context(local)
-    ctx.set_precision(_ffi.PREC_TF32 if args.precision == "tf32" else _ffi.PREC_FP32)
+    ctx.set_precision({"tf32": _ffi.PREC_TF32, "bf16": _ffi.PREC_BF16, "fp32": _ffi.PREC_FP32}[args.precision])
     comm, rank, world = dist.init_from_env(ctx)
     if world != args.gpus and rank == 0:
         print(f"warning: --gpus {args.gpus} but WORLD_SIZE={world}", file=sys.stderr)
@@ -316,7 +316,7 @@ def run_ours(args, wl):
     intensity = top["flops"] / max(top["bytes"], 1.0)
     # the measured tensor peak is bf16; tf32 runs at half that rate
     tc_peak = tc_peak / 2 if args.precision == "tf32" else tc_peak
-    tensor_bound = intensity > (tc_peak * 1e12) / (hbm_peak * 1e9) and "_tc" in top["name"]
+    tensor_bound = intensity > (tc_peak * 1e12) / (hbm_peak * 1e9) and ("_tc" in top["name"] or "_bf16" in top["name"])
     roofline = {
         "kernel": top["name"], "bound": "tensor" if tensor_bound else "hbm",
         "achieved": tfs if tensor_bound else gbs, "peak": tc_peak if tensor_bound else hbm_peak,
@@ -374,7 +374,7 @@ def run_ours(args, wl):
     line = {
         "metric": "train_samples_per_s", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "tf32" if args.precision == "tf32" else "f32", "data": "synthetic",
+        "vs_baseline": None, "dtype": {"tf32": "tf32", "bf16": "bf16", "fp32": "f32"}[args.precision], "data": "synthetic",
         "config": {"workload": desc, "per_gpu_batch": B, "precision": args.precision + " operands, fp32 accumulate", "global_batch": gB, "parallelism": f"dp{world}",
                    "l2": "per-step working set (activations + gradients, >400 MB at cfg2) exceeds the 126 MB L2; "
                          "8 distinct input batches rotated",
@@ -424,7 +424,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-microbench", action="store_true", help="skip the cfg4 VQ and HBM-stage micro-benchmarks")
     ap.add_argument("--vq-n", type=int, default=1 << 22, help="vectors of the cfg4-shaped VQ micro-benchmark")
-    ap.add_argument("--precision", default="tf32", choices=["fp32", "tf32"],
+    ap.add_argument("--precision", default="tf32", choices=["fp32", "tf32", "bf16"],
                     help="arithmetic of the GEMM-shaped kernels: tcgen05 tf32 (fp32 accumulate) or exact fp32 CUDA cores")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

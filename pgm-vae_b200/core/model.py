@@ -372,6 +372,10 @@ class VqVAE:
     def device_bytes(self) -> int:
         return int(_ffi.lib().pgmvae_model_device_bytes(self._h))
 
+    def group_size(self) -> int:
+        """Variables per workspace group (the step walks the V independent networks group by group)."""
+        return int(_ffi.lib().pgmvae_model_group_size(self._h))
+
     def save_weights(self, path: str):
         np.savez(path, **self.state_dict())
 

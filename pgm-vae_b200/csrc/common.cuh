@@ -32,6 +32,8 @@ struct pgmvae_ctx {
     void* scratch_sort = nullptr; // counting sort of the sorted scatter (vq.cu), grown on demand
     size_t scratch_sort_bytes = 0;
     size_t vq_cnt_off = 0;
+    void* scratch_b = nullptr;    // bf16 operand copies of the operator-level bf16 entry points (dense_bf16_ops.cu)
+    size_t scratch_b_bytes = 0;
 };
 
 void pgmvae_set_error(const char* fmt, ...);

@@ -12,6 +12,9 @@ int pgmvae_dense_fwd(pgmvae_ctx* ctx, void* stream, const float* x, int64_t x_gs
     PG_CHECK_ARG(G >= 0 && B >= 0 && in > 0 && out_dim > 0);
     PG_CHECK_ARG(ldx >= in && ldw >= out_dim && ldo >= out_dim);
     PG_CHECK_ARG(act >= PGMVAE_ACT_NONE && act <= PGMVAE_ACT_SIGMOID);
+    if (ctx->precision == PGMVAE_PREC_BF16)
+        return pg_dense_fwd_bf16(ctx, pg_stream(ctx, stream), x, x_gs, ldx, w, w_gs, ldw, bias, bias_gs, out, out_gs, ldo, G, B,
+                                 in, out_dim, act);
     if (ctx->precision != PGMVAE_PREC_FP32 && pg_dense_tc_supported(x, x_gs, ldx, w, w_gs, ldw))
         return pg_dense_fwd_tc(ctx, pg_stream(ctx, stream), x, x_gs, ldx, w, w_gs, ldw, bias, bias_gs, out, out_gs, ldo,
                                G, B, in, out_dim, act);
@@ -26,6 +29,9 @@ int pgmvae_dense_fwd_sigmoid_mse(pgmvae_ctx* ctx, void* stream, const float* x, 
     PG_CHECK_ARG(ctx && x && w && y && dpre && acc2);
     PG_CHECK_ARG(G >= 0 && B >= 0 && in > 0 && V > 0 && g0 >= 0 && g0 + G <= V);
     PG_CHECK_ARG(ldx >= in && ldw >= V && ldd >= V && ldy >= V);
+    if (ctx->precision == PGMVAE_PREC_BF16)
+        return pg_dense_fwd_sigmoid_mse_bf16(ctx, pg_stream(ctx, stream), x, x_gs, ldx, w, w_gs, ldw, bias, bias_gs, y, ldy, dpre,
+                                             dpre_gs, ldd, out_opt, acc2, G, g0, B, in, V, grad_scale);
     if (ctx->precision != PGMVAE_PREC_FP32 && pg_dense_tc_supported(x, x_gs, ldx, w, w_gs, ldw))
         return pg_dense_fwd_sigmoid_mse_tc(ctx, pg_stream(ctx, stream), x, x_gs, ldx, w, w_gs, ldw, bias, bias_gs, y, ldy,
                                            dpre, dpre_gs, ldd, out_opt, acc2, G, g0, B, in, V, grad_scale);
@@ -42,6 +48,9 @@ int pgmvae_dense_dgrad(pgmvae_ctx* ctx, void* stream, const float* dy, int64_t d
     PG_CHECK_ARG(lddy >= out_dim && ldw >= out_dim && lddx >= in);
     PG_CHECK_ARG((z == nullptr) == (q == nullptr));
     PG_CHECK_ARG(!h_in || ldh >= in);
+    if (ctx->precision == PGMVAE_PREC_BF16)
+        return pg_dense_dgrad_bf16(ctx, pg_stream(ctx, stream), dy, dy_gs, lddy, w, w_gs, ldw, h_in, h_gs, ldh, z, q, zq_gs, ldzq,
+                                   cscale, dx, dx_gs, lddx, G, B, in, out_dim, act_below);
     if (ctx->precision != PGMVAE_PREC_FP32 && pg_dense_tc_supported(dy, dy_gs, lddy, w, w_gs, ldw))
         return pg_dense_dgrad_tc(ctx, pg_stream(ctx, stream), dy, dy_gs, lddy, w, w_gs, ldw, h_in, h_gs, ldh, z, q, zq_gs,
                                  ldzq, cscale, dx, dx_gs, lddx, G, B, in, out_dim, act_below);
@@ -55,6 +64,9 @@ int pgmvae_dense_wgrad(pgmvae_ctx* ctx, void* stream, const float* x, int64_t x_
     PG_CHECK_ARG(ctx && x && dy && dw);
     PG_CHECK_ARG(G >= 0 && B >= 0 && in > 0 && out_dim > 0);
     PG_CHECK_ARG(ldx >= in && lddy >= out_dim && lddw >= out_dim);
+    if (ctx->precision == PGMVAE_PREC_BF16)
+        return pg_dense_wgrad_bf16(ctx, pg_stream(ctx, stream), x, x_gs, ldx, dy, dy_gs, lddy, dw, dw_gs, lddw, db, db_gs, G, B,
+                                   in, out_dim, zero_row_base);
     if (ctx->precision != PGMVAE_PREC_FP32 && pg_dense_tc_supported(x, x_gs, ldx, dy, dy_gs, lddy))
         return pg_dense_wgrad_tc(ctx, pg_stream(ctx, stream), x, x_gs, ldx, dy, dy_gs, lddy, dw, dw_gs, lddw, db, db_gs, G,
                                  B, in, out_dim, zero_row_base);

@@ -258,6 +258,18 @@ struct pgmvae_model {
     // weight-gradient kernel
     cudaStream_t ema_stream = nullptr;
     cudaEvent_t ev_ema_fork = nullptr, ev_ema = nullptr;
+    // bf16 tensor-core mode (csrc/dense_bf16.cu): networks too wide for the chain kernels (cfg3).  Operands live in
+    // bf16: the data matrix, every activation / pre-activation gradient of the current variable group, and two
+    // shadows of the weights (wt: transposed [V][out][in] for the forward GEMMs, wc: as stored [V][in][out] for
+    // the dgrad GEMMs), refreshed from the fp32 master weights whenever those change.
+    bool bf16 = false, shadow_dirty = true;
+    __nv_bfloat16* yb = nullptr;            // [max_batch][Vp]
+    __nv_bfloat16* Hb[10] = {};             // activations (layer 4 = the latent stays fp32 in H[4])
+    __nv_bfloat16* Gb[10] = {};             // d(loss)/d(pre-activation)
+    __nv_bfloat16* stb = nullptr;           // straight-through output of the VQ layer
+    __nv_bfloat16* wt[10] = {};
+    __nv_bfloat16* wc[10] = {};
+    __nv_bfloat16* cnt_yb = nullptr;
 
     float* E() const { return params + e_off; }
     float* dE() const { return grads + e_off; }
@@ -408,7 +420,20 @@ int upload_batch(pgmvae_model* m, const uint8_t* y, int on_device, int B, const 
         PG_CUDA(cudaMemcpyAsync(m->y_u8, y, (size_t)B * m->V, cudaMemcpyHostToDevice, st));
         *y_dev = m->y_u8;
     }
+    if (m->bf16) return pg_y_to_bf16(m->ctx, st, *y_dev, m->V, m->yb, m->Vp, B, m->V);
     return pgmvae_y_to_f32(m->ctx, st, *y_dev, m->V, m->yf, m->Vp, B, m->V);
+}
+
+// bf16 shadows of the weights, rebuilt from the fp32 master copy when it has changed (Adam, init, set_tensor)
+int refresh_shadows(pgmvae_model* m) {
+    if (!m->bf16 || !m->shadow_dirty) return PGMVAE_OK;
+    for (int l = 0; l < 10; ++l) {
+        const Layer& L = m->L[l];
+        PG_TRY(pg_bf16_shadow(m->ctx, m->ctx->stream, m->params + L.w_off, (int64_t)L.pin * L.pout, L.pout, L.in, L.out, m->wt[l],
+                              (int64_t)L.pout * L.pin, L.pin, m->wc[l], (int64_t)L.pin * L.pout, L.pout, m->V));
+    }
+    m->shadow_dirty = false;
+    return PGMVAE_OK;
 }
 
 // all-reduce `buf` on the communication stream once everything issued so far on the compute stream is done
@@ -430,7 +455,7 @@ int overlapped_allreduce(pgmvae_model* m, pgmvae_comm* comm, void* buf, int64_t 
 }
 
 bool use_chain(const pgmvae_model* m) {
-    return m->chain_ok && getenv("PGMVAE_NO_CHAIN") == nullptr && m->ctx->precision != PGMVAE_PREC_FP32;
+    return !m->bf16 && m->chain_ok && getenv("PGMVAE_NO_CHAIN") == nullptr && m->ctx->precision != PGMVAE_PREC_FP32;
 }
 
 // forward stages fd[l0, l1) of variables [g0, g0 + Gn) as chain stages
@@ -490,10 +515,34 @@ int chain_encode(pgmvae_model* m, int g0, int Gn, int B, const uint8_t* y_dev, u
     return pg_chain_launch(m->ctx, m->ctx->stream, a);
 }
 
-// encoder fd0..fd4 + assignment for variables [g0, g0+Gn) of the current batch (in m->yf)
-int encode_group(pgmvae_model* m, int g0, int Gn, int B) {
+// bf16 mode: forward layers fd[l0, l1) of variables [g0, g0 + Gn) on the tensor cores (csrc/dense_bf16.cu); the
+// latent (layer 4) is written in fp32 for the VQ step, everything else as the bf16 operand of the next GEMM
+int bf16_forward_layers(pgmvae_model* m, int g0, int Gn, int B, int l0, int l1, const __nv_bfloat16* yb) {
     pgmvae_ctx* ctx = m->ctx;
     cudaStream_t st = ctx->stream;
+    const int64_t MB = m->max_batch;
+    for (int l = l0; l < l1; ++l) {
+        const Layer& L = m->L[l];
+        const __nv_bfloat16* x = l == 0 ? yb : (l == 5 ? m->stb : m->Hb[l - 1]);
+        const int ldx = l == 0 ? m->Vp : (l == 5 ? m->Dp : m->L[l - 1].pout);
+        const int64_t x_gs = l == 0 ? 0 : MB * ldx;
+        PG_TRY(pg_bf16_fwd(ctx, st, x, x_gs, ldx, m->wt[l] + (size_t)g0 * L.pout * L.pin, (int64_t)L.pout * L.pin, L.pin,
+                           m->params + L.b_off + (size_t)g0 * L.pout, L.pout, l == 4 ? nullptr : m->Hb[l], MB * L.pout, L.pout,
+                           l == 4 ? m->H[4] : nullptr, MB * L.pout, L.pout, Gn, B, L.in, L.out, L.act));
+    }
+    return PGMVAE_OK;
+}
+
+// encoder fd0..fd4 + assignment for variables [g0, g0+Gn) of the current batch (in m->yf / m->yb)
+int encode_group(pgmvae_model* m, int g0, int Gn, int B, const __nv_bfloat16* yb = nullptr) {
+    pgmvae_ctx* ctx = m->ctx;
+    cudaStream_t st = ctx->stream;
+    if (m->bf16) {
+        PG_TRY(bf16_forward_layers(m, g0, Gn, B, 0, 5, yb ? yb : m->yb));
+        return pg_vq_assign_f16(ctx, st, m->H[4], (int64_t)m->max_batch * m->Dp, m->Dp, m->E() + (size_t)g0 * m->K * m->Dp,
+                                (int64_t)m->K * m->Dp, m->Dp, m->idx, B, nullptr, nullptr, nullptr, 0, nullptr, 0, 0, Gn, B,
+                                m->D, m->K);
+    }
     for (int l = 0; l < 5; ++l) {
         const Layer& L = m->L[l];
         const float* x = l == 0 ? m->yf : m->H[l - 1];
@@ -559,24 +608,46 @@ int pgmvae_model_create(pgmvae_ctx* ctx, const int* units4, int nvar, int dim, i
         A((void**)&m->ema_w, cb * 4); A((void**)&m->biased_w, cb * 4); A((void**)&m->stat_w, cb * 4);
         A((void**)&m->ema_c, cs * 4); A((void**)&m->biased_c, cs * 4); A((void**)&m->stat_c, cs * 4);
     }
-    // group size: keep the per-group activation workspace under ~12 GB
-    size_t per_vb = 0;   // floats per (variable, sample)
-    for (int l = 0; l < 9; ++l) per_vb += (size_t)m->L[l].pout;       // H_0..H_8
-    for (int l = 0; l < 10; ++l) per_vb += (size_t)m->L[l].pout;      // Gd_0..Gd_9
-    per_vb += 2 * (size_t)m->Dp + 1;                                  // q, st, idx
-    const size_t budget = (size_t)12 << 30;
-    size_t vg = budget / (per_vb * 4 * (size_t)max_batch);
+    // bf16 mode: decided once, at creation (the operand buffers differ)
+    m->bf16 = ctx->precision == PGMVAE_PREC_BF16 && (!m->chain_ok || getenv("PGMVAE_NO_CHAIN") != nullptr);
+    // group size: keep the per-group activation workspace under ~12 GB (PGMVAE_WS_GB), or PGMVAE_GROUP_VARS variables
+    size_t per_vb = 0;   // bytes per (variable, sample)
+    if (m->bf16) {
+        for (int l = 0; l < 9; ++l) per_vb += (size_t)m->L[l].pout * (l == 4 ? 4 : 2);     // Hb_0..Hb_8 (latent fp32)
+        for (int l = 0; l < 10; ++l) per_vb += (size_t)m->L[l].pout * 2;                    // Gb_0..Gb_9
+        per_vb += (size_t)m->Dp * 6 + 4;                                                     // q (fp32), st (bf16), idx
+    } else {
+        for (int l = 0; l < 9; ++l) per_vb += (size_t)m->L[l].pout * 4;       // H_0..H_8
+        for (int l = 0; l < 10; ++l) per_vb += (size_t)m->L[l].pout * 4;      // Gd_0..Gd_9
+        per_vb += (2 * (size_t)m->Dp + 1) * 4;                                // q, st, idx
+    }
+    size_t budget = (size_t)12 << 30;
+    if (const char* ev = getenv("PGMVAE_WS_GB")) budget = atof(ev) > 0.0 ? (size_t)(atof(ev) * (double)(1ull << 30)) : budget;
+    size_t vg = budget / (per_vb * (size_t)max_batch);
+    if (const char* ev = getenv("PGMVAE_GROUP_VARS")) vg = atoi(ev) > 0 ? (size_t)atoi(ev) : vg;
     if (vg < 1) vg = 1;
     if (vg > (size_t)nvar) vg = nvar;
     m->Vg = (int)vg;
     A((void**)&m->y_u8, (size_t)max_batch * nvar);
-    A((void**)&m->yf, (size_t)max_batch * m->Vp * 4);
-    for (int l = 0; l < 10; ++l) {
-        if (l < 9) A((void**)&m->H[l], vg * max_batch * m->L[l].pout * 4);
-        A((void**)&m->Gd[l], vg * max_batch * m->L[l].pout * 4);
+    if (m->bf16) {
+        A((void**)&m->yb, (size_t)max_batch * m->Vp * 2);
+        for (int l = 0; l < 10; ++l) {
+            if (l < 9 && l != 4) A((void**)&m->Hb[l], vg * max_batch * m->L[l].pout * 2);
+            A((void**)&m->Gb[l], vg * max_batch * m->L[l].pout * 2);
+            A((void**)&m->wt[l], (size_t)nvar * m->L[l].pout * m->L[l].pin * 2);
+            if (l > 0) A((void**)&m->wc[l], (size_t)nvar * m->L[l].pin * m->L[l].pout * 2);
+        }
+        A((void**)&m->H[4], vg * max_batch * m->Dp * 4);
+        A((void**)&m->stb, vg * max_batch * m->Dp * 2);
+    } else {
+        A((void**)&m->yf, (size_t)max_batch * m->Vp * 4);
+        for (int l = 0; l < 10; ++l) {
+            if (l < 9) A((void**)&m->H[l], vg * max_batch * m->L[l].pout * 4);
+            A((void**)&m->Gd[l], vg * max_batch * m->L[l].pout * 4);
+        }
+        A((void**)&m->st, vg * max_batch * m->Dp * 4);
     }
     A((void**)&m->q, vg * max_batch * m->Dp * 4);
-    A((void**)&m->st, vg * max_batch * m->Dp * 4);
     // idx holds all V variables of a batch (encode / count expose [V,B])
     A((void**)&m->idx, (size_t)nvar * max_batch * 4);
     A((void**)&m->acc, 4 * sizeof(double));
@@ -658,6 +729,7 @@ int pgmvae_model_init(pgmvae_model* m, uint64_t seed) {
         m->step_c = m->step_w = 0;
     }
     PG_CUDA(cudaStreamSynchronize(st));
+    m->shadow_dirty = true;
     return PGMVAE_OK;
 }
 
@@ -682,6 +754,7 @@ int pgmvae_model_set_tensor(pgmvae_model* m, const char* name, const float* host
     to_internal(m, t, host, in.data());
     PG_CUDA(cudaStreamSynchronize(m->ctx->stream));
     PG_CUDA(cudaMemcpy(t.base, in.data(), sizeof(float) * (size_t)t.int_count, cudaMemcpyHostToDevice));
+    m->shadow_dirty = true;
     return PGMVAE_OK;
 }
 
@@ -813,7 +886,10 @@ int run_step(pgmvae_model* m, const uint8_t* y, int y_on_device, int B, int glob
         p2p_wait_done_kernel<<<1, 32, 0, st>>>(m->p2p_flags, m->p2p_n, m->p2p_step, m->p2p_err);
         PG_LAUNCHED(ctx);
     }
-    PG_CUDA(cudaMemsetAsync(m->grads, 0, trainable * 4, st));
+    PG_TRY(refresh_shadows(m));
+    // (bf16 mode: every gradient element is written exactly once per step, nothing accumulates into the buffer)
+    if (!m->bf16) PG_CUDA(cudaMemsetAsync(m->grads, 0, trainable * 4, st));
+    else if (!m->ema) PG_CUDA(cudaMemsetAsync(m->dE(), 0, (trainable - m->n_dense) * 4, st));   // the scatter accumulates
     PG_CUDA(cudaMemsetAsync(m->acc, 0, 4 * sizeof(double), st));
     if (m->ema) {
         PG_CUDA(cudaMemsetAsync(m->stat_w, 0, (size_t)V * K * Dp * 4, st));
@@ -964,7 +1040,89 @@ int run_step(pgmvae_model* m, const uint8_t* y, int y_on_device, int B, int glob
         if (overlap && !m->ema && !use_p2p)
             PG_TRY(overlapped_allreduce(m, comm, m->dE(), (int64_t)V * K * Dp, 0));
     }
-    for (int g0 = 0; g0 < V && !chain; g0 += m->Vg) {
+    // ---- layer-by-layer path (networks too wide for the chain kernels, or exact fp32): one variable group at a time.
+    // Under data parallelism group g's gradient slices (and EMA statistics) are all-reduced on the communication
+    // stream while group g+1 computes; only the last group's exchange is exposed.
+    bool group_overlap = false;
+    auto exchange_group = [&](int g0, int Gn) -> int {
+        if (!comm) return PGMVAE_OK;
+        if (!m->comm_stream) {
+            int prio_lo = 0, prio_hi = 0;
+            PG_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+            PG_CUDA(cudaStreamCreateWithPriority(&m->comm_stream, cudaStreamNonBlocking, prio_hi));
+            PG_CUDA(cudaEventCreateWithFlags(&m->ev_compute, cudaEventDisableTiming));
+            PG_CUDA(cudaEventCreateWithFlags(&m->ev_comm, cudaEventDisableTiming));
+            PG_CUDA(cudaEventCreateWithFlags(&m->ev_stats, cudaEventDisableTiming));
+        }
+        PG_CUDA(cudaEventRecord(m->ev_compute, st));
+        PG_CUDA(cudaStreamWaitEvent(m->comm_stream, m->ev_compute, 0));
+        PG_TRY(pg_comm_group_begin(comm));
+        if (!(flags & STEP_FWD_ONLY)) {
+            for (int l = 0; l < 10; ++l) {
+                const Layer& L = m->L[l];
+                PG_TRY(pg_comm_allreduce(comm, m->grads + L.w_off + (size_t)g0 * L.pin * L.pout, (int64_t)Gn * L.pin * L.pout, 0,
+                                         m->comm_stream));
+                PG_TRY(pg_comm_allreduce(comm, m->grads + L.b_off + (size_t)g0 * L.pout, (int64_t)Gn * L.pout, 0, m->comm_stream));
+            }
+            if (!m->ema)
+                PG_TRY(pg_comm_allreduce(comm, m->dE() + (size_t)g0 * K * Dp, (int64_t)Gn * K * Dp, 0, m->comm_stream));
+        }
+        if (m->ema && !(flags & STEP_NO_EMA)) {
+            PG_TRY(pg_comm_allreduce(comm, m->stat_w + (size_t)g0 * K * Dp, (int64_t)Gn * K * Dp, 0, m->comm_stream));
+            PG_TRY(pg_comm_allreduce(comm, m->stat_c + (size_t)g0 * K, (int64_t)Gn * K, 0, m->comm_stream));
+        }
+        if (g0 + Gn >= V) PG_TRY(pg_comm_allreduce(comm, m->acc, 4, 1, m->comm_stream));      // loss accumulators: after the last group
+        PG_TRY(pg_comm_group_end(comm));
+        group_overlap = true;
+        return PGMVAE_OK;
+    };
+    for (int g0 = 0; g0 < V && !chain && m->bf16; g0 += m->Vg) {
+        // bf16 tensor-core path (csrc/dense_bf16.cu, vq_tc16.cu)
+        const int Gn = std::min(m->Vg, V - g0);
+        const int64_t MB = m->max_batch;
+        const int64_t zgs = MB * Dp;
+        const bool stats = m->ema && !(flags & STEP_NO_EMA);
+        PG_TRY(bf16_forward_layers(m, g0, Gn, B, 0, 5, m->yb));
+        // VQ: assignment + EMA statistics + quantise + commitment loss in one kernel (core/quantizer.py:135-156)
+        PG_TRY(pg_vq_assign_f16(ctx, st, m->H[4], zgs, Dp, m->E() + (size_t)g0 * K * Dp, (int64_t)K * Dp, Dp, m->idx, B, nullptr,
+                                nullptr, stats ? m->stat_c + (size_t)g0 * K : nullptr, K,
+                                stats ? m->stat_w + (size_t)g0 * K * Dp : nullptr, (int64_t)K * Dp, Dp, Gn, B, D, K, m->q, m->stb,
+                                zgs, Dp, m->acc + 2));
+        if (!m->ema && !(flags & STEP_FWD_ONLY))
+            PG_TRY(pgmvae_vq_codebook_grad(ctx, st, m->H[4], m->q, zgs, Dp, m->idx, B, m->dE() + (size_t)g0 * K * Dp,
+                                           (int64_t)K * Dp, Dp, (float)(2.0 / n_lat), Gn, B, D, K));
+        PG_TRY(bf16_forward_layers(m, g0, Gn, B, 5, 9, m->yb));
+        {   // fd9 + loss + d(loss)/d(pre-activation)
+            const Layer& L = m->L[9];
+            PG_TRY(pg_bf16_fwd_sigmoid_mse(ctx, st, m->Hb[8], MB * m->L[8].pout, m->L[8].pout,
+                                           m->wt[9] + (size_t)g0 * L.pout * L.pin, (int64_t)L.pout * L.pin, L.pin,
+                                           m->params + L.b_off + (size_t)g0 * L.pout, L.pout, m->yb, m->Vp, m->Gb[9], MB * L.pout,
+                                           L.pout, out_dev ? out_dev + (size_t)g0 * MB * L.pout : nullptr, MB * L.pout, L.pout,
+                                           m->acc, Gn, g0, B, L.in, V, gscale));
+        }
+        for (int l = (flags & STEP_FWD_ONLY) ? -1 : 9; l >= 0; --l) {
+            const Layer& L = m->L[l];
+            const __nv_bfloat16* x = l == 0 ? m->yb : (l == 5 ? m->stb : m->Hb[l - 1]);
+            const int ldx = l == 0 ? m->Vp : (l == 5 ? Dp : m->L[l - 1].pout);
+            const int64_t x_gs = l == 0 ? 0 : MB * ldx;
+            PG_TRY(pg_bf16_wgrad(ctx, st, x, x_gs, ldx, m->Gb[l], MB * L.pout, L.pout,
+                                 m->grads + L.w_off + (size_t)g0 * L.pin * L.pout, (int64_t)L.pin * L.pout, L.pout, Gn, B, L.in,
+                                 L.out, l == 0 ? g0 : -1, 0));
+            PG_TRY(pg_bf16_colsum(ctx, st, m->Gb[l], MB * L.pout, L.pout, m->grads + L.b_off + (size_t)g0 * L.pout, L.pout, Gn, B,
+                                  L.out, 0));
+            if (l > 0) {
+                const Layer& P = m->L[l - 1];
+                const bool vqb = (l == 5);
+                PG_TRY(pg_bf16_dgrad(ctx, st, m->Gb[l], MB * L.pout, L.pout, m->wc[l] + (size_t)g0 * L.pin * L.pout,
+                                     (int64_t)L.pin * L.pout, L.pout, vqb ? nullptr : m->Hb[l - 1], MB * P.pout, P.pout,
+                                     vqb ? m->H[4] : nullptr, MB * P.pout, P.pout, vqb ? m->H[4] : nullptr, vqb ? m->q : nullptr,
+                                     zgs, Dp, cscale, m->Gb[l - 1], MB * P.pout, P.pout, nullptr, 0, 0, Gn, B, L.in, L.out,
+                                     PGMVAE_ACT_SELU));
+            }
+        }
+        PG_TRY(exchange_group(g0, Gn));
+    }
+    for (int g0 = 0; g0 < V && !chain && !m->bf16; g0 += m->Vg) {
         const int Gn = std::min(m->Vg, V - g0);
         PG_TRY(encode_group(m, g0, Gn, B));
         // m->idx rows [0, Gn) now hold this group's codes
@@ -1019,6 +1177,7 @@ int run_step(pgmvae_model* m, const uint8_t* y, int y_on_device, int B, int glob
                                           P.pout, Gn, B, L.in, L.out, PGMVAE_ACT_SELU));
             }
         }
+        PG_TRY(exchange_group(g0, Gn));
     }
 
     if (comm && overlapped) {
@@ -1026,6 +1185,10 @@ int run_step(pgmvae_model* m, const uint8_t* y, int y_on_device, int B, int glob
         // still in flight; the optimiser waits for that one
         PG_CUDA(cudaStreamWaitEvent(st, m->ev_stats, 0));
         PG_TRY(ema_update(st));
+        PG_CUDA(cudaEventRecord(m->ev_comm, m->comm_stream));
+        PG_CUDA(cudaStreamWaitEvent(st, m->ev_comm, 0));
+    } else if (comm && group_overlap) {
+        // every group's exchange has been issued; the optimiser and the codebook update wait for the last one
         PG_CUDA(cudaEventRecord(m->ev_comm, m->comm_stream));
         PG_CUDA(cudaStreamWaitEvent(st, m->ev_comm, 0));
     } else if (comm) {
@@ -1067,6 +1230,7 @@ int run_step(pgmvae_model* m, const uint8_t* y, int y_on_device, int B, int glob
             PG_TRY(pgmvae_adam_step(ctx, st, m->params, m->grads, m->adam_m, m->adam_v, (int64_t)trainable, alpha, b1, b2,
                                     1e-7));
         }
+        m->shadow_dirty = true;
     }
     PG_TRY(ema_update(st));
     if (ema_side) PG_CUDA(cudaStreamWaitEvent(st, m->ev_ema, 0));       // later work sees the new codebook
@@ -1104,6 +1268,7 @@ int pgmvae_model_encode(pgmvae_model* m, const uint8_t* y, int y_on_device, int 
     PG_CHECK_ARG(B >= 1 && B <= m->max_batch);
     PG_CUDA(cudaSetDevice(m->ctx->device));
     const uint8_t* y_dev = nullptr;
+    PG_TRY(refresh_shadows(m));
     PG_TRY(upload_batch(m, y, y_on_device, B, &y_dev));
     for (int g0 = 0; g0 < m->V; g0 += m->Vg) {
         const int Gn = std::min(m->Vg, m->V - g0);
@@ -1122,6 +1287,7 @@ int pgmvae_model_count(pgmvae_model* m, const uint8_t* y, int y_on_device, int64
     cudaStream_t st = ctx->stream;
     PG_CUDA(cudaSetDevice(ctx->device));
     const size_t cs = (size_t)m->V * m->K;
+    PG_TRY(refresh_shadows(m));
     PG_CUDA(cudaMemsetAsync(m->n1, 0, cs * 8, st));
     PG_CUDA(cudaMemsetAsync(m->n0, 0, cs * 8, st));
     if (use_chain(m) && m->Vg >= m->V && N > m->max_batch) {

@@ -29,6 +29,7 @@
 // rows with several are re-scored with exactly the fp32 arithmetic of the CUDA-core kernel
 // (lowest index on ties).  Rows whose ring overflowed with still-relevant entries (many identical
 // dead codes) or whose fp16 image is not finite go to the exact full-scan kernel.
+#include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <stdlib.h>
 
@@ -55,7 +56,7 @@ struct Cfg {
 
 struct Vq16P {
     int G, B, D, K;
-    int KD, ksteps, kblocks, tiles_m, tiles_n, Kpad, stages, zvec;
+    int KD, ksteps, kblocks, tiles_m, tiles_n, Kpad, stages, zvec, qvec;
     const float* z; long long z_gs; int ldz;
     const float* e; long long e_gs; int lde;
     const float* ee;        // [G][Kpad] exact fp32 squared norms
@@ -66,6 +67,9 @@ struct Vq16P {
     float* dw; long long dw_gs; int lddw;
     int* flag_count; int2* flag_list;
     float margin_scale, margin_abs;
+    // fused quantise step (optional; core/quantizer.py:141-142,156): q = E[idx] (fp32), the straight-through output
+    // z + (q - z) as the bf16 operand of the first decoder layer, and sum (q - z)^2 into *loss
+    float* q; __nv_bfloat16* stb; long long q_gs; int ldq; double* loss;
 };
 
 // Per code: exact |e|^2 (sequential fmaf, the order every fp32 path uses), the fp16 row
@@ -117,6 +121,47 @@ __device__ __forceinline__ void scatter_row(const Vq16P& p, int g, const float* 
         for (int d = 0; d < p.D; ++d) atomicAdd(dst + d, zr[d]);
     }
     atomicAdd(p.cnt + (long long)g * p.c_gs + k, 1.0f);
+}
+
+// quantise one row with its decided code: q, straight-through output (bf16), returns sum_d (q - z)^2
+__device__ __forceinline__ float quantize_row(const Vq16P& p, int g, int row, const float* zr, int k) {
+    const float* er = p.e + (long long)g * p.e_gs + (long long)k * p.lde;
+    const long long o = (long long)g * p.q_gs + (long long)row * p.ldq;
+    float part = 0.f;
+    if (p.qvec) {
+        for (int d = 0; d < p.D; d += 8) {
+            float ev[8], zv[8], sv[8];
+            *reinterpret_cast<float4*>(ev) = __ldg(reinterpret_cast<const float4*>(er + d));
+            *reinterpret_cast<float4*>(ev + 4) = __ldg(reinterpret_cast<const float4*>(er + d + 4));
+            *reinterpret_cast<float4*>(zv) = *reinterpret_cast<const float4*>(zr + d);
+            *reinterpret_cast<float4*>(zv + 4) = *reinterpret_cast<const float4*>(zr + d + 4);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float diff = ev[j] - zv[j];
+                part = fmaf(diff, diff, part);
+                sv[j] = zv[j] + diff;                    // inputs + stop_gradient(quantized - inputs)
+            }
+            if (p.q) {
+                *reinterpret_cast<float4*>(p.q + o + d) = *reinterpret_cast<const float4*>(ev);
+                *reinterpret_cast<float4*>(p.q + o + d + 4) = *reinterpret_cast<const float4*>(ev + 4);
+            }
+            if (p.stb) {
+                __nv_bfloat162 h[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(sv[2 * j], sv[2 * j + 1]);
+                *reinterpret_cast<uint4*>(p.stb + o + d) = *reinterpret_cast<const uint4*>(h);
+            }
+        }
+    } else {
+        for (int d = 0; d < p.D; ++d) {
+            const float ev = __ldg(er + d), zv = zr[d];
+            const float diff = ev - zv;
+            part = fmaf(diff, diff, part);
+            if (p.q) p.q[o + d] = ev;
+            if (p.stb) p.stb[o + d] = __float2bfloat16_rn(zv + diff);
+        }
+    }
+    return part;
 }
 
 template <int SUB>
@@ -234,6 +279,7 @@ vq_assign_f16_kernel(const __grid_constant__ CUtensorMap mapE, const Vq16P p) {
         float2* myH = ringH + r;
         const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
         uint32_t it = 0;
+        double qloss = 0.0;
         for (int item = blockIdx.x; item < items; item += gridDim.x) {
             const int g = item / p.tiles_m, mt = item - g * p.tiles_m;
             const int row = mt * C::TMR + r;
@@ -398,12 +444,17 @@ vq_assign_f16_kernel(const __grid_constant__ CUtensorMap mapE, const Vq16P p) {
                     }
                     p.idx[o] = bi;
                     if (p.dw) scatter_row(p, g, zr, bi);
+                    if (p.q || p.stb || p.loss) qloss += (double)quantize_row(p, g, row, zr, bi);
                 } else {
                     p.idx[o] = 0;
                     const int slot = atomicAdd(p.flag_count, 1);
                     p.flag_list[slot] = make_int2(g, row);
                 }
             }
+        }
+        if (p.loss) {
+            qloss = pg_warp_sum_d(qloss);
+            if (lane == 0 && qloss != 0.0) atomicAdd(p.loss, qloss);
         }
     }
     tc::fence_before_thread_sync();
@@ -457,6 +508,10 @@ __global__ void __launch_bounds__(256) vq16_rescore_kernel(const Vq16P p) {
             if (p.best) p.best[o] = gb;
             if (p.gap) p.gap[o] = cand - gb;
             if (p.dw) scatter_row(p, gr.x, zr, gi);
+            if (p.q || p.stb || p.loss) {
+                const float part = quantize_row(p, gr.x, gr.y, zr, gi);
+                if (p.loss) atomicAdd(p.loss, (double)part);
+            }
         }
     }
 }
@@ -507,9 +562,11 @@ bool pg_vq_assign_f16_supported(int D, int K) { return K >= 1 && D >= 1 && D + 2
 // assignment (+ optional fused EMA statistics when cnt/dw are given; they are accumulated into)
 int pg_vq_assign_f16(pgmvae_ctx* ctx, cudaStream_t st, const float* z, int64_t z_gs, int ldz, const float* e,
                      int64_t e_gs, int lde, int32_t* idx, int64_t idx_gs, float* best_opt, float* gap_opt,
-                     float* cnt_opt, int64_t c_gs, float* dw_opt, int64_t dw_gs, int lddw, int G, int B, int D, int K) {
+                     float* cnt_opt, int64_t c_gs, float* dw_opt, int64_t dw_gs, int lddw, int G, int B, int D, int K,
+                     float* q_opt, __nv_bfloat16* stb_opt, int64_t q_gs, int ldq, double* loss_opt) {
     if (G <= 0 || B <= 0) return PGMVAE_OK;
     Vq16P p{};
+    p.q = q_opt; p.stb = stb_opt; p.q_gs = q_gs; p.ldq = ldq; p.loss = loss_opt;
     p.G = G; p.B = B; p.D = D; p.K = K;
     p.KD = pg_round_up(D + 2, 16);
     p.ksteps = p.KD / 16;
@@ -535,6 +592,8 @@ int pg_vq_assign_f16(pgmvae_ctx* ctx, cudaStream_t st, const float* z, int64_t z
     __half* e16 = (__half*)(sc + off_e16);
     p.z = z; p.z_gs = z_gs; p.ldz = ldz; p.e = e; p.e_gs = e_gs; p.lde = lde; p.ee = ee; p.emax = emax;
     p.zvec = !((uintptr_t)z & 15) && ldz % 4 == 0 && z_gs % 4 == 0;
+    p.qvec = p.zvec && D % 8 == 0 && !((uintptr_t)e & 15) && lde % 4 == 0 && e_gs % 4 == 0 && ldq % 8 == 0 && q_gs % 8 == 0 &&
+             !((uintptr_t)q_opt & 15) && !((uintptr_t)stb_opt & 15);
     p.idx = idx; p.idx_gs = idx_gs; p.best = best_opt; p.gap = gap_opt;
     p.cnt = cnt_opt; p.c_gs = c_gs; p.dw = (cnt_opt && dw_opt) ? dw_opt : nullptr; p.dw_gs = dw_gs; p.lddw = lddw;
     p.flag_count = cnt; p.flag_list = list;
