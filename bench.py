@@ -1,23 +1,25 @@
 #!/usr/bin/env python
 """Benchmark of the pgm-vae hot path on B200 (see BASELINE.md / SURVEY.md 8d).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg3|cfg1]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg3|cfg2|cfg1]
 
-A "step" is one training step (forward, MSE + VQ loss, backward, Adam, EMA codebook update)
-over one batch of synthetic binary data.  Default workload = BASELINE.json configs[1]
-("cfg2": 69 variables, units 50/40/30/20, K=128, D=16, EMA, batch 4096 per GPU).
-Prints ONE JSON line on rank 0.
+A "step" is one training step (forward, MSE + VQ loss, backward, Adam, EMA codebook update) over one batch of
+synthetic binary data.  Default workload = BASELINE.json configs[2] ("cfg3": 1556 variables, units 400/200/100/50,
+K=512, D=64, EMA, batch 4096 per GPU -- the configuration the metric "train samples/s at 1/2/4/8 B200" is quoted
+on; it fits one GPU: ~58 GB).  Prints ONE JSON line on rank 0.
 
-  value      whole-job training samples/s, batches already resident in HBM (device pointers)
-  e2e        the same through the public API (core.model.VqVAE.train_on_batch) with PINNED HOST
-             batches: H2D copy of the batch and D2H read of the loss inside every step
-  roofline   the dominant kernel of the step, from a per-kernel CUDA-event pass over the same steps
-  cpu_baseline / --impl reference : the CPU restatement of the reference (oracle/, torch-CPU fp32;
-             TensorFlow itself is not installable in this image) timed on the host cores
-  pll_eval   stage 2 (encoder + VQ assignment + histogram) samples/s, device-resident and e2e
-  vq_assign  BASELINE.json configs[3] shape (D=64, K=8192; 4 Mi vectors unless --vq-n): fused fp16 tcgen05
-             assignment + EMA scatter, useful TFLOP/s against the measured bf16 peak
-  hbm_stages the stand-alone EMA scatter / EMA update / PLL histogram kernels against the measured HBM peak
+  value       whole-job training samples/s, batches already resident in HBM (device pointers)
+  e2e         the same through the public API (core.model.VqVAE.train_on_batch) with PINNED HOST batches: H2D copy
+              of the batch and D2H read of the loss inside every step
+  roofline    the dominant kernel of the step, from a per-kernel CUDA-event pass over the same steps
+  dp_parity   N > 1 only, outside the timed region: three steps through the data-parallel path on every rank vs the
+              same global batches on one GPU (rank 0) -- losses, weights, codebook, PLL counts; the run FAILS above 1e-3
+  cpu_baseline / --impl reference : the CPU restatement of the reference (oracle/, torch-CPU fp32; TensorFlow itself is
+              not installable in this image) timed on the host cores on a bounded sample
+  pll_eval    stage 2 (encoder + VQ assignment + histogram) samples/s: sample-sharded, variable-sharded, e2e
+  cfg2        (N = 1) the round-1 headline workload (69 variables, chain kernels) as a secondary block
+  vq_assign   BASELINE.json configs[3] (16 Mi vectors, D=64, K=8192): fused fp16 tcgen05 assignment + EMA scatter
+  hbm_stages  the stand-alone EMA scatter / EMA update / PLL histogram kernels against the measured HBM peak
 """
 import argparse
 import json
@@ -108,23 +110,67 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------- reference arm (CPU)
-def cpu_train_samples_per_s(V, units, D, K, B, steps, warmup, seed=0):
-    """Times the oracle's training step (the CPU restatement of the reference) on the host."""
+def cpu_train_rate(V, units, D, K, B, steps, warmup, budget_s, seed=0):
+    """Times the oracle's training step (the CPU restatement of the reference) on the host cores.
+
+    The V networks of the model are independent (one GEMM chain per variable), so for models whose full state does
+    not fit a CPU step budget the sample is a SUBSET OF THE NETWORKS at the full layer widths: `nets` of the V nets,
+    batch Bc, and the rate is scaled by nets / V (work is linear in the number of nets).  Returns
+    (samples_per_s, seconds_per_sampled_step, cores, description)."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import torch
     import pgmvae_oracle as O
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    m = O.OracleVqVAE(units, V, D, K, cost=0.25, decay=0.99, ema=True, seed=seed)
-    y = O.synthetic_binary(B * 2, V, seed=seed)
-    xs = [O.make_xs(y[:B]), O.make_xs(y[B:])]
+    train_fl, _ = flops_per_sample(V, units, D, K)
+
+    def build(nets, Bc):
+        rng = np.random.default_rng(seed)
+        p = {}
+        for i, (fin, fout) in enumerate(O.layer_dims(units, V, D)):
+            lim = np.sqrt(6.0 / (V * fin)) if i < 9 else np.sqrt(6.0 / (V * fin + V * fout))
+            p[f"fd{i}.kernel"] = torch.from_numpy(rng.uniform(-lim, lim, (nets, fin, fout)).astype(np.float32))
+            p[f"fd{i}.bias"] = torch.zeros(nets, 1, fout)
+        lim = np.sqrt(3.0 / (V * D))
+        p["vq.embeddings"] = torch.from_numpy(rng.uniform(-lim, lim, (nets, D, K)).astype(np.float32))
+        m = O.OracleVqVAE(units, nets, D, K, cost=0.25, decay=0.99, ema=True, params=p)
+        y = O.synthetic_binary(2 * Bc, V, seed=seed)
+        xs = [torch.from_numpy(np.stack([np.delete(y[i * Bc:(i + 1) * Bc], v, axis=1) for v in range(nets)], axis=1)
+                               .astype(np.float32)) for i in range(2)]
+        return m, xs
+
+    # size the sample from a probe: ~flops the host does per second
+    nets, Bc = min(V, 8), min(B, 64)
+    m, xs = build(nets, Bc)
+    m.train_step(xs[0], lr=1e-3)
+    t0 = time.perf_counter()
+    m.train_step(xs[1], lr=1e-3)
+    t_probe = time.perf_counter() - t0
+    rate = train_fl * Bc * nets / V / max(t_probe, 1e-6)                       # flop/s
+    per_step = budget_s / max(steps + warmup, 1)
+    want = rate * per_step                                                     # flops one sampled step may cost
+    full = train_fl * B
+    if want >= full:
+        nets, Bc = V, B
+    else:
+        Bc = min(B, 256)
+        nets = int(max(1, min(V, want / (train_fl * Bc / V))))
+        if nets >= V:                                   # all networks fit: spend the rest of the budget on the batch
+            Bc = int(min(B, max(Bc, want / train_fl)))
+        if nets < 4:
+            nets = min(V, 4)
+            Bc = int(min(B, max(16, want / (train_fl * nets / V))))
+    m, xs = build(nets, Bc)
     for i in range(warmup):
         m.train_step(xs[i % 2], lr=1e-3)
     t0 = time.perf_counter()
     for i in range(steps):
         m.train_step(xs[i % 2], lr=1e-3)
-    dt = time.perf_counter() - t0
-    return B * steps / dt, dt / steps, cores
+    dt = (time.perf_counter() - t0) / steps
+    sps = Bc * (nets / V) / dt
+    desc = (f"{steps} training steps of {nets} of the {V} per-variable networks (full layer widths) x batch {Bc} after {warmup} "
+            f"warm-up (torch-CPU fp32 oracle, {cores} threads); samples/s scaled by {nets}/{V} (the networks are independent)")
+    return sps, dt, cores, desc
 
 
 def run_reference(args, wl):
@@ -132,19 +178,12 @@ def run_reference(args, wl):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    # bounded sample: largest per-step batch such that the whole run stays within ~2.5 minutes
-    sps, t_probe, cores = cpu_train_samples_per_s(V, units, D, K, min(B, 128), 1, 1)
-    per_sample = t_probe / min(B, 128)
-    Bref = B
-    while Bref > 64 and (args.steps + args.warmup) * per_sample * Bref > 150.0:
-        Bref //= 2
-    sps, t_step, cores = cpu_train_samples_per_s(V, units, D, K, Bref, args.steps, args.warmup)
-    sample = f"{args.steps} training steps of batch {Bref} (full workload batch {B})"
+    sps, t_step, cores, sample = cpu_train_rate(V, units, D, K, B, args.steps, args.warmup, budget_s=120.0)
     line = {
         "impl": "reference", "metric": "train_samples_per_s", "value": sps, "unit": "samples/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_step * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": desc, "per_step_batch": Bref,
+        "config": {"workload": desc, "per_gpu_batch": B,
                    "note": "CPU restatement of the reference (oracle/pgmvae_oracle.py, torch-CPU fp32); "
                            "TensorFlow, which the reference needs, is not installable in this image"},
         "cpu_baseline": {"value": sps, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample},
@@ -154,13 +193,10 @@ def run_reference(args, wl):
     emit(line)
 
 
-def measured_traffic(kernel):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture of this
-    workload (profiles/r1_dram_traffic.json), or None when the kernel was not captured."""
-    p = os.path.join(ROOT, "profiles", "r1_dram_traffic.json")
-    if not os.path.exists(p):
-        return None
-    return json.load(open(p)).get(kernel)
+def committed(name):
+    """a number taken from a committed ncu capture (profiles/<name>), or None"""
+    p = os.path.join(ROOT, "profiles", name)
+    return json.load(open(p)) if os.path.exists(p) else None
 
 
 def vq_and_hbm_stages(ctx, _ffi, L, n_vq, hbm_peak, tc_peak_bf16):
@@ -171,26 +207,36 @@ def vq_and_hbm_stages(ctx, _ffi, L, n_vq, hbm_peak, tc_peak_bf16):
     e = rng.uniform(-1, 1, (1, K, D)).astype(np.float32) * np.float32(np.sqrt(3.0 / D))
     z = rng.standard_normal((1, n_vq, D), dtype=np.float32)
     dz, de = _ffi.DeviceArray.from_numpy(ctx, z), _ffi.DeviceArray.from_numpy(ctx, e)
+    del z
     idx = _ffi.DeviceArray(ctx, (1, n_vq), np.int32)
     cnt, dw = _ffi.DeviceArray(ctx, (1, K)), _ffi.DeviceArray(ctx, (1, K, D))
 
     def fused():
         _ffi.check(L.pgmvae_vq_assign_ema(ctx.h, None, dz.ptr, n_vq * D, D, de.ptr, K * D, D, idx.ptr, n_vq, cnt.ptr, K,
                                           dw.ptr, K * D, D, 1, n_vq, D, K))
-    for _ in range(2):
-        fused()
-    ctx.sync()
-    ctx.timer_start()
-    reps = 3
-    for _ in range(reps):
-        fused()
-    ms = ctx.timer_stop_ms() / reps
+
+    def plain():
+        _ffi.check(L.pgmvae_vq_assign(ctx.h, None, dz.ptr, n_vq * D, D, de.ptr, K * D, D, idx.ptr, n_vq, None, None, 1, n_vq,
+                                      D, K))
+    out = {}
+    ctx.set_precision(_ffi.PREC_BF16)
+    for name, fn in (("fused_assign_ema", fused), ("assign_only", plain)):
+        for _ in range(2):
+            fn()
+        ctx.sync()
+        ctx.timer_start()
+        reps = 3
+        for _ in range(reps):
+            fn()
+        ms = ctx.timer_stop_ms() / reps
+        tf = 2.0 * n_vq * D * K / (ms * 1e-3) / 1e12
+        out[name] = {"ms": ms, "vectors_per_s": n_vq / (ms * 1e-3), "useful_tflops": tf, "frac_of_bf16_peak": tf / tc_peak_bf16}
     nres = C.c_int(0)
     _ffi.check(L.pgmvae_vq_assign_rescored(ctx.h, 1, K, C.byref(nres)))
-    tf = 2.0 * n_vq * D * K / (ms * 1e-3) / 1e12
-    vq = {"workload": f"cfg4 shape: {n_vq} vectors, D=64, K=8192, fp16 tcgen05 assignment + fused EMA scatter",
-          "ms": ms, "vectors_per_s": n_vq / (ms * 1e-3), "useful_tflops": tf, "peak_tflops_bf16": tc_peak_bf16,
-          "frac_of_bf16_peak": tf / tc_peak_bf16, "full_scan_rows": nres.value,
+    cap = committed("r2_vq_tensor_pipe.json")
+    vq = {"workload": f"cfg4: {n_vq} vectors, D=64, K=8192, fp16 tcgen05 assignment (+ fused EMA scatter), exact indices",
+          **out["fused_assign_ema"], "assign_only": out["assign_only"], "peak_tflops_bf16": tc_peak_bf16,
+          "full_scan_rows": nres.value, "tensor_pipe_pct": cap,
           "note": "useful flops = 2*D*K per vector; the |e|^2 column adds 25 % MMA work that is not counted"}
     # stand-alone scatter + update on the same vectors / codes
     bc, bw = _ffi.DeviceArray(ctx, (1, K)), _ffi.DeviceArray(ctx, (1, K, D))
@@ -220,7 +266,36 @@ def vq_and_hbm_stages(ctx, _ffi, L, n_vq, hbm_peak, tc_peak_bf16):
 
 
 # --------------------------------------------------------------------------- our arm
-def run_ours(args, wl):
+def time_training(args, ctx, L, _ffi, model, y_dev, B, gB, V, nb, comm_h, barrier, max_over_ranks, min_ms=400.0):
+    """W warm-up steps, then K * R timed steps (R repeats of the --steps loop so that the timed region is at least
+    ~0.4 s: a 12 ms sample is noise at 8 GPUs); device timed, max over ranks."""
+    import ctypes as C
+    lr = C.c_float(1e-3)
+
+    def step_dev(i, met=None):
+        off = (i % nb) * B * V
+        _ffi.check(L.pgmvae_model_train_step(model._h, y_dev.ptr + off, 1, B, gB, lr, comm_h, 0, met))
+    for i in range(args.warmup):
+        step_dev(i)
+    barrier()
+    ctx.timer_start()
+    for i in range(args.steps):
+        step_dev(i)
+    probe = max_over_ranks(ctx.timer_stop_ms())
+    R = int(max(1, min(200, np.ceil(min_ms / max(probe, 1e-3)))))
+    barrier()
+    l0 = ctx.launches
+    ctx.timer_start()
+    for i in range(args.steps * R):
+        step_dev(i)
+    ms = ctx.timer_stop_ms()
+    launches = ctx.launches - l0
+    barrier()
+    ms = max_over_ranks(ms)
+    return ms, R, launches, step_dev
+
+
+def run_ours(args, wl, wl_name):
     V, units, D, K, B, desc = wl
     from pgmvae import _ffi, data, dist
     from core.model import VqVAE, Adam
@@ -229,7 +304,8 @@ def run_ours(args, wl):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     ctx = _ffi.get_context(local)
-    ctx.set_precision({"tf32": _ffi.PREC_TF32, "bf16": _ffi.PREC_BF16, "fp32": _ffi.PREC_FP32}[args.precision])
+    prec = {"tf32": _ffi.PREC_TF32, "bf16": _ffi.PREC_BF16, "fp32": _ffi.PREC_FP32}[args.precision]
+    ctx.set_precision(prec)
     comm, rank, world = dist.init_from_env(ctx)
     if world != args.gpus and rank == 0:
         print(f"warning: --gpus {args.gpus} but WORLD_SIZE={world}", file=sys.stderr)
@@ -250,34 +326,32 @@ def run_ours(args, wl):
         tdist.all_reduce(t, op=tdist.ReduceOp.MAX)
         return float(t[0])
 
+    # ---- data-parallel parity of exactly the path that is timed below (outside the timed region)
+    dp_par = None
+    if world > 1 and not args.no_dp_parity:
+        sys.path.insert(0, os.path.join(ROOT, "pgm-vae_b200", "tools"))
+        import dp_check
+        dp_par = dp_check.dp_parity(ctx, comm, rank, world, units, V, D, K, min(B, 256), args.precision, ema=True, local=local,
+                                    eval_samples=4096)
+        ctx.set_precision(prec)
+        if rank == 0:
+            dp_par["failed"] = dp_check.check(dp_par)
+
     model = VqVAE(units, V, D, K, cost=0.25, decay=0.99, ema=True, seed=0, max_batch=B, device=local, comm=comm)
     model.compile(optimizer=Adam(lr=1e-3), loss="mse", metrics=["mae"])
+    arith = {0: "fp32", 1: "tf32", 2: "bf16"}[int(L.pgmvae_model_arithmetic(model._h))]
     gB = B * world
     nb = 8                                              # distinct batches, rotated
     y = data.synthetic_binary(nb * B, V, seed=1000 + rank)
     y_dev = _ffi.DeviceArray.from_numpy(ctx, y)
     comm_h = comm.h if comm is not None else None
-    lr = C.c_float(1e-3)
-
-    def step_dev(i, met=None):
-        off = (i % nb) * B * V
-        _ffi.check(L.pgmvae_model_train_step(model._h, y_dev.ptr + off, 1, B, gB, lr, comm_h, 0, met))
 
     # ---- device-resident timing ("value")
-    for i in range(args.warmup):
-        step_dev(i)
-    barrier()
     sampler = ClockSampler(local) if rank == 0 else None
-    l0 = ctx.launches
-    ctx.timer_start()
-    for i in range(args.steps):
-        step_dev(i)
-    ms = ctx.timer_stop_ms()
-    launches = ctx.launches - l0
-    barrier()
+    ms, R, launches, step_dev = time_training(args, ctx, L, _ffi, model, y_dev, B, gB, V, nb, comm_h, barrier, max_over_ranks)
     clocks = sampler.stop() if sampler else None
-    ms = max_over_ranks(ms)
-    value = gB * args.steps / (ms * 1e-3)
+    nsteps = args.steps * R
+    value = gB * nsteps / (ms * 1e-3)
     met = (C.c_double * 4)()
     step_dev(0, met)
     assert all(np.isfinite(v) for v in met), "non-finite loss"
@@ -292,13 +366,13 @@ def run_ours(args, wl):
     barrier()
     ctx.timer_start()
     t0 = time.perf_counter()
-    for i in range(args.steps):
+    for i in range(nsteps):
         model.train_on_batch(pinned[(i % nb) * B:(i % nb + 1) * B], global_batch=gB, sync=True)
     e2e_ms = ctx.timer_stop_ms()
     e2e_wall = (time.perf_counter() - t0) * 1e3
     barrier()
     e2e_ms = max_over_ranks(max(e2e_ms, e2e_wall))
-    e2e_value = gB * args.steps / (e2e_ms * 1e-3)
+    e2e_value = gB * nsteps / (e2e_ms * 1e-3)
 
     # ---- per-kernel pass (CUDA events around every launch of the same steps) -> roofline of the top kernel
     ctx.profile_begin()
@@ -306,7 +380,7 @@ def run_ours(args, wl):
     for i in range(psteps):
         step_dev(i)
     prof = ctx.profile_end()
-    hbm_peak, tc_peak, peak_src = peaks()
+    hbm_peak, tc_peak_bf16, peak_src = peaks()
     tot_ms = sum(k["ms"] for k in prof) or 1.0
     prof.sort(key=lambda k: -k["ms"])
     top = prof[0]
@@ -315,14 +389,18 @@ def run_ours(args, wl):
     tfs = top["flops"] / top["launches"] / (avg_ms * 1e-3) / 1e12
     intensity = top["flops"] / max(top["bytes"], 1.0)
     # the measured tensor peak is bf16; tf32 runs at half that rate
-    tc_peak = tc_peak / 2 if args.precision == "tf32" else tc_peak
+    tc_peak = tc_peak_bf16 / 2 if arith == "tf32" else tc_peak_bf16
     tensor_bound = intensity > (tc_peak * 1e12) / (hbm_peak * 1e9) and ("_tc" in top["name"] or "_bf16" in top["name"])
+    traffic = committed("r2_dram_traffic.json")
     roofline = {
         "kernel": top["name"], "bound": "tensor" if tensor_bound else "hbm",
         "achieved": tfs if tensor_bound else gbs, "peak": tc_peak if tensor_bound else hbm_peak,
         "unit": "TFLOP/s" if tensor_bound else "GB/s",
-        "frac": (tfs / tc_peak) if tensor_bound else (gbs / hbm_peak), "traffic": measured_traffic(top["name"]),
-        "peak_source": peak_src, "avg_launch_ms": avg_ms, "launches_per_step": top["launches"] / psteps,
+        "frac": (tfs / tc_peak) if tensor_bound else (gbs / hbm_peak),
+        "traffic": (traffic or {}).get(wl_name, {}).get(top["name"]) if traffic else None,
+        "traffic_source": "ncu --set full capture committed as profiles/r2_dram_traffic.json (per launch)" if traffic else None,
+        "peak_source": peak_src + (" bf16 sustained" if arith != "tf32" else " bf16 sustained / 2 (tf32 operands)"),
+        "avg_launch_ms": avg_ms, "launches_per_step": top["launches"] / psteps,
         "share_of_step": top["ms"] / tot_ms, "algorithmic_bytes_per_launch": top["bytes"] / top["launches"],
         "algorithmic_flops_per_launch": top["flops"] / top["launches"],
         "method": "CUDA events around every library launch over %d of the timed steps (separate pass)" % psteps,
@@ -331,62 +409,93 @@ def run_ours(args, wl):
                     for k in prof],
     }
 
-    # ---- stage 2: PLL evaluation (encoder + assignment + histogram)
+    # ---- stage 2: PLL evaluation (encoder + assignment + histogram); cfg5 = the cfg3 model over 10 M samples, here a
+    # bounded sample of it per GPU
+    train_fl, pll_fl = flops_per_sample(V, units, D, K)
     n_eval = nb * B
     n1 = np.zeros((V, K), np.uint64)
     n0 = np.zeros((V, K), np.uint64)
-    reps = max(2, min(10, args.steps))
+    reps = 2
     _ffi.check(L.pgmvae_model_count(model._h, y_dev.ptr, 1, n_eval, n1.ctypes.data, n0.ctypes.data))
     barrier()
     ctx.timer_start()
     for _ in range(reps):
         _ffi.check(L.pgmvae_model_count(model._h, y_dev.ptr, 1, n_eval, n1.ctypes.data, n0.ctypes.data))
     pll_ms = max_over_ranks(ctx.timer_stop_ms())
-    t0 = time.perf_counter()
-    for _ in range(reps):
-        model.dist = model.cpt(pinned)
-        pll = model.pseudo_log_likelihood(pinned, total=n_eval * world)
-    pll_e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / 2.0)      # two passes over the data per rep
     assert (n1 + n0).sum() == n_eval * V
-    pll_eval = {"metric": "pll_eval_samples_per_s", "value": world * n_eval * reps / (pll_ms * 1e-3),
-                "e2e_value": world * n_eval * reps / (pll_e2e_ms * 1e-3), "unit": "samples/s",
-                "samples_per_pass": world * n_eval, "pll": pll}
+    # variable-sharded: every rank evaluates its own V / world networks on the same n_eval samples
+    v0, v1 = model.var_shard()
+    barrier()
+    ctx.timer_start()
+    for _ in range(reps):
+        _ffi.check(L.pgmvae_model_count_vars(model._h, y_dev.ptr, 1, n_eval, v0, v1, n1.ctypes.data, n0.ctypes.data))
+    pllv_ms = max_over_ranks(ctx.timer_stop_ms())
+    t0 = time.perf_counter()
+    model.dist = model.cpt(pinned)
+    pll = model.pseudo_log_likelihood(pinned, total=n_eval * world)
+    pll_e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / 2.0)      # two passes over the data
+    pll_value = world * n_eval * reps / (pll_ms * 1e-3)
+    pll_eval = {"metric": "pll_eval_samples_per_s", "value": pll_value, "unit": "samples/s",
+                "variable_sharded_value": n_eval * reps / (pllv_ms * 1e-3),
+                "e2e_value": world * n_eval / (pll_e2e_ms * 1e-3),
+                "samples_per_pass": world * n_eval, "pll": pll,
+                "tensor_roofline_frac": pll_value * pll_fl / 1e12 / (world * tc_peak),
+                "note": ("cfg5 (BASELINE.json configs[4]) is this model over 10 M samples; this is a bounded sample of it, "
+                         "%d samples per GPU and pass" % n_eval) if wl_name == "cfg3" else None}
     _ffi.check(L.pgmvae_free_host(ctx.h, hp))
 
     if rank != 0:
         return
-    vq_assign = hbm_stages = None
     device_bytes = model.device_bytes()
+    groups = -(-V // model.group_size())
+    del model, y_dev
+    vq_assign = hbm_stages = cfg2 = None
     if world == 1 and not args.no_microbench:
-        del model, y_dev
-        vq_assign, hbm_stages = vq_and_hbm_stages(ctx, _ffi, L, args.vq_n, hbm_peak, peaks()[1])
+        vq_assign, hbm_stages = vq_and_hbm_stages(ctx, _ffi, L, args.vq_n, hbm_peak, tc_peak_bf16)
+    if world == 1 and wl_name != "cfg2" and not args.no_secondary:
+        # the round-1 headline workload (chain kernels, tf32) beside it
+        V2, u2, D2, K2, B2, desc2 = WORKLOADS["cfg2"]
+        ctx.set_precision(_ffi.PREC_TF32)
+        m2 = VqVAE(u2, V2, D2, K2, cost=0.25, decay=0.99, ema=True, seed=0, max_batch=B2, device=local)
+        m2.compile(optimizer=Adam(lr=1e-3))
+        y2 = data.synthetic_binary(nb * B2, V2, seed=1000)
+        y2d = _ffi.DeviceArray.from_numpy(ctx, y2)
+        a2 = argparse.Namespace(steps=50, warmup=5)
+        ms2, R2, _, _ = time_training(a2, ctx, L, _ffi, m2, y2d, B2, B2, V2, nb, None, barrier, max_over_ranks)
+        fl2, _ = flops_per_sample(V2, u2, D2, K2)
+        v2 = B2 * 50 * R2 / (ms2 * 1e-3)
+        cfg2 = {"workload": desc2, "value": v2, "unit": "samples/s", "ms_per_step": ms2 / (50 * R2), "steps": 50 * R2,
+                "dtype": "tf32", "achieved_tflops": v2 * fl2 / 1e12}
+        del m2, y2d
+        ctx.set_precision(prec)
     # ---- CPU baseline beside it (rank 0, N == 1 only): bounded sample of the same workload
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        Bc = B
-        sps, t_probe, cores = cpu_train_samples_per_s(V, units, D, K, min(B, 128), 1, 1)
-        while Bc > 64 and 4 * (t_probe / min(B, 128)) * Bc > 25.0:
-            Bc //= 2
-        sps, t_step, cores = cpu_train_samples_per_s(V, units, D, K, Bc, 3, 1)
-        cpu = {"value": sps, "unit": "samples/s", "cores": cores, "kind": "port",
-               "sample": f"3 training steps of batch {Bc} after 1 warm-up (torch-CPU fp32 oracle, {cores} threads)"}
-    train_fl, pll_fl = flops_per_sample(V, units, D, K)
+        sps, t_step, cores, sample = cpu_train_rate(V, units, D, K, B, 3, 1, budget_s=20.0)
+        cpu = {"value": sps, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample}
+    step_tf = value * train_fl / 1e12
     line = {
         "metric": "train_samples_per_s", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": {"tf32": "tf32", "bf16": "bf16", "fp32": "f32"}[args.precision], "data": "synthetic",
-        "config": {"workload": desc, "per_gpu_batch": B, "precision": args.precision + " operands, fp32 accumulate", "global_batch": gB, "parallelism": f"dp{world}",
-                   "l2": "per-step working set (activations + gradients, >400 MB at cfg2) exceeds the 126 MB L2; "
-                         "8 distinct input batches rotated",
+        "repeats": R, "timed_steps": nsteps, "warmup": args.warmup, "ms_per_step": ms / nsteps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": arith, "data": "synthetic",
+        "config": {"workload": desc, "per_gpu_batch": B, "precision": arith + " operands, fp32 accumulate",
+                   "global_batch": gB, "parallelism": f"dp{world}", "variable_groups_per_step": groups,
+                   "l2": "per-step working set (activations + gradients: GBs) exceeds the 126 MB L2; 8 distinct input "
+                         "batches rotated",
                    "flop_per_sample_train": train_fl, "flop_per_sample_pll": pll_fl,
-                   "achieved_tflops": value * train_fl / 1e12, "device_bytes": device_bytes},
+                   "achieved_tflops": step_tf, "step_tensor_roofline_frac": step_tf / (world * tc_peak),
+                   "device_bytes": device_bytes},
         "roofline": roofline, "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": B * V, "d2h_bytes_per_step": 32,
-                "ms_per_step": e2e_ms / args.steps},
-        "gpu_launches": launches, "clocks": clocks, "pll_eval": pll_eval, "vq_assign": vq_assign, "hbm_stages": hbm_stages,
+                "ms_per_step": e2e_ms / nsteps},
+        "gpu_launches": launches, "clocks": clocks, "pll_eval": pll_eval, "dp_parity": dp_par, "cfg2": cfg2,
+        "vq_assign": vq_assign, "hbm_stages": hbm_stages,
         "loss_after": {"loss": met[0], "mse": met[1], "mae": met[2], "vq_loss": met[3]},
     }
     emit(line)
+    if dp_par and dp_par.get("failed"):
+        print(f"dp_parity FAILED: {dp_par['failed']}", file=sys.stderr)
+        sys.exit(3)
 
 
 _RESULT_FD = None
@@ -417,22 +526,25 @@ def main():
     claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-microbench", action="store_true", help="skip the cfg4 VQ and HBM-stage micro-benchmarks")
-    ap.add_argument("--vq-n", type=int, default=1 << 22, help="vectors of the cfg4-shaped VQ micro-benchmark")
-    ap.add_argument("--precision", default="tf32", choices=["fp32", "tf32", "bf16"],
-                    help="arithmetic of the GEMM-shaped kernels: tcgen05 tf32 (fp32 accumulate) or exact fp32 CUDA cores")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the cfg2 block")
+    ap.add_argument("--no-dp-parity", action="store_true", help="skip the data-parallel parity check (N > 1)")
+    ap.add_argument("--vq-n", type=int, default=1 << 24, help="vectors of the cfg4 VQ micro-benchmark (16 Mi)")
+    ap.add_argument("--precision", default="bf16", choices=["fp32", "tf32", "bf16"],
+                    help="arithmetic of the GEMM-shaped kernels: bf16 = the fastest tensor-core path for the geometry (bf16 "
+                         "tcgen05 for wide networks, tf32 chain kernels for narrow ones); tf32; or exact fp32 CUDA cores")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":
         run_reference(args, wl)
     else:
-        run_ours(args, wl)
+        run_ours(args, wl, args.workload)
 
 
 if __name__ == "__main__":

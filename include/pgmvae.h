@@ -269,11 +269,10 @@ int pgmvae_model_set_adam_step(pgmvae_model* m, int64_t t);
  * pgmvae_model_train_step reduces the gradients through the communicator.                                  */
 int pgmvae_model_p2p_export(pgmvae_model* m, void* handles_out128);
 int pgmvae_model_p2p_import(pgmvae_model* m, int rank, int nranks, const void* all_handles);
-/* Reduce-scatter form (opt-in, not yet measured on hardware): rank r sums and updates only its 1/nranks of the
- * parameters and writes the result into every rank's parameter buffer.  export_rs writes 3 x 64 bytes (gradient
- * buffer, flag block, parameter buffer); import_rs takes nranks x 192 bytes in rank order.                     */
-int pgmvae_model_p2p_export_rs(pgmvae_model* m, void* handles_out192);
-int pgmvae_model_p2p_import_rs(pgmvae_model* m, int rank, int nranks, const void* all_handles);
+/* turn the peer-to-peer exchange off again (a rank failed to map its peers): NCCL is used instead */
+int pgmvae_model_p2p_disable(pgmvae_model* m);
+/* cudaDeviceCanAccessPeer(device, peer): whether the CUDA-IPC mapping behind pgmvae_model_p2p_import can work */
+int pgmvae_device_can_access_peer(int device, int peer, int* out);
 
 /* One training step on a batch y [B,V] uint8 (host or device pointer).
  * global_B is the batch size over all data-parallel ranks (== B without DP); comm may be NULL.
@@ -294,6 +293,14 @@ int pgmvae_model_encode(pgmvae_model* m, const uint8_t* y, int y_on_device, int 
 /* VqVAE.count over N samples (core/model.py:58-82): n1,n0 [V,K] uint64 on the HOST. */
 int pgmvae_model_count(pgmvae_model* m, const uint8_t* y, int y_on_device, int64_t N,
                        unsigned long long* n1_host, unsigned long long* n0_host);
+/* The same over the variables [v0, v1) only (rows v0..v1-1 of n1 / n0 are written, the others left untouched):
+ * stage 2 sharded over VARIABLE groups -- every rank evaluates its own nets on all samples and only the float64
+ * PLL scalar crosses ranks (north_star; core/model.py:91-96 is a sum over variables). */
+int pgmvae_model_count_vars(pgmvae_model* m, const uint8_t* y, int y_on_device, int64_t N, int v0, int v1,
+                            unsigned long long* n1_host, unsigned long long* n0_host);
+/* arithmetic of the model's GEMM-shaped kernels, fixed at creation: 0 = fp32 CUDA cores, 1 = tf32 tcgen05
+ * (per-layer or chain kernels), 2 = bf16 tcgen05 (wide networks under PGMVAE_PREC_BF16) */
+int pgmvae_model_arithmetic(pgmvae_model* m);
 /* bytes of device memory held by the model (weights, optimiser, workspace) */
 int64_t pgmvae_model_device_bytes(pgmvae_model* m);
 /* variables processed per group inside a step (workspace is sized for one group) */

@@ -120,28 +120,56 @@ class VqVAE:
             return
         # measured (cfg2 step): 2 GPUs 0.686 ms peer-to-peer vs 0.702 ms NCCL; 8 GPUs 0.80 vs 0.77 ms (every rank
         # reads all eight buffers; NCCL reduces in the switch) -> default on for two ranks only, PGMVAE_P2P=0/1 overrides
-        # PGMVAE_P2P=2: the reduce-scatter form (every rank sums and updates 1/nranks of the parameters and writes
-        # it to the peers) -- built for more than two ranks, not yet measured
         want = os.environ.get("PGMVAE_P2P")
-        if want == "0" or (want not in ("1", "2") and comm.nranks != 2):
+        if want == "0" or (want != "1" and comm.nranks != 2):
             return
+        import socket
         import torch.distributed as dist
-        rs = want == "2"
-        nbytes = 192 if rs else 128
         lib = _ffi.lib()
+        nbytes = 128
+        # every rank must sit on the same host with peer access between all devices; otherwise (two nodes, GPUs
+        # without NVLink / PCIe peer access) the NCCL path is the one that works.  The decision is collective.
+        infos = [None] * comm.nranks
+        dist.all_gather_object(infos, (socket.gethostname(), int(self.ctx.device)))
+        ok = len({h for h, _ in infos}) == 1
+        if ok:
+            can = C.c_int(0)
+            for _, dev in infos:
+                if dev != int(self.ctx.device):
+                    _ffi.check(lib.pgmvae_device_can_access_peer(int(self.ctx.device), int(dev), C.byref(can)))
+                    ok = ok and bool(can.value)
+        flags = [None] * comm.nranks
+        dist.all_gather_object(flags, bool(ok))
+        if not all(flags):
+            return
         buf = C.create_string_buffer(nbytes)
-        _ffi.check((lib.pgmvae_model_p2p_export_rs if rs else lib.pgmvae_model_p2p_export)(self._h, buf))
+        rc = lib.pgmvae_model_p2p_export(self._h, buf)
         handles = [None] * comm.nranks
-        dist.all_gather_object(handles, buf.raw)
-        blob = C.create_string_buffer(b"".join(handles), nbytes * comm.nranks)
-        _ffi.check((lib.pgmvae_model_p2p_import_rs if rs else lib.pgmvae_model_p2p_import)(self._h, comm.rank,
-                                                                                          comm.nranks, blob))
+        dist.all_gather_object(handles, buf.raw if rc == 0 else None)
+        good = all(h is not None for h in handles)
+        if good:
+            blob = C.create_string_buffer(b"".join(handles), nbytes * comm.nranks)
+            rc = lib.pgmvae_model_p2p_import(self._h, comm.rank, comm.nranks, blob)
+            good = rc == 0
+        flags = [None] * comm.nranks
+        dist.all_gather_object(flags, bool(good))
+        if not all(flags):
+            # some rank could not map its peers: nobody uses the peer-to-peer exchange
+            _ffi.check(lib.pgmvae_model_p2p_disable(self._h))
         dist.barrier()
 
-    def _ensure_capacity(self, batch: int):
-        """The workspace is sized for max_batch samples; grow it (state is carried over)."""
+    def _ensure_capacity(self, batch: int, collective: bool = False):
+        """The workspace is sized for max_batch samples; grow it (state is carried over).  Re-creating the model is
+        a COLLECTIVE operation under data parallelism (the peer-to-peer mapping is set up again), so there it only
+        happens where every rank arrives with the same number (``collective=True``: fit / train_on_batch size the
+        workspace for ceil(global_batch / world), the largest share any rank can get); rank-local calls
+        (``model(x)``, evaluation) must stay within the capacity."""
         if batch <= self.max_batch:
             return
+        multi = self.comm is not None and getattr(self.comm, "nranks", 1) > 1 and getattr(self.comm, "h", None) is not None
+        if multi and not collective:
+            raise ValueError(f"batch of {batch} samples exceeds the model's capacity ({self.max_batch}); on a data-parallel "
+                             f"model the workspace only grows inside fit()/train_on_batch(), where every rank takes part")
         state = self.state_dict()
         old = self._h
         self._create(int(batch))
@@ -262,7 +290,9 @@ class VqVAE:
         if self.optimizer is None:
             self.compile()
         B = y_batch.shape[0]
-        self._ensure_capacity(B)
+        world = self.comm.nranks if self.comm is not None else 1
+        # the same number on every rank: the largest share of the global batch (shares differ by at most one sample)
+        self._ensure_capacity(max(B, -(-int(global_batch or B) // world)) if world > 1 else B, collective=True)
         met = (C.c_double * 4)() if sync else None
         comm_h = self.comm.h if self.comm is not None else None
         _ffi.check(_ffi.lib().pgmvae_model_train_step(self._h, y_batch.ctypes.data, 0, B, int(global_batch or B),
@@ -320,37 +350,61 @@ class VqVAE:
         return hist
 
     # ---- stage 2 ---------------------------------------------------------------------
-    def count(self, x, y=None):
+    def var_shard(self):
+        """[v0, v1): the variables this rank owns when stage 2 is sharded over variable groups."""
+        if self.comm is None or self.comm.nranks <= 1:
+            return 0, self.nvar
+        return self.nvar * self.comm.rank // self.comm.nranks, self.nvar * (self.comm.rank + 1) // self.comm.nranks
+
+    def count(self, x, y=None, var_range=None):
         """n1[v,k] = #(y_v = 1, code_v = k), n0 likewise (reference core/model.py:58-82),
         as float64 [V,K].  With a communicator the samples are this rank's shard and the
-        counts are summed over ranks."""
+        counts are summed over ranks.  ``var_range=(v0, v1)``: only those variables are evaluated (on all the
+        samples given) and nothing is exchanged -- rows outside the range stay zero."""
         data = to_y(y if y is not None else x)
         n = data.shape[0]          # pgmvae_model_count walks the samples in chunks of max_batch
         n1 = np.zeros((self.nvar, self.k), dtype=np.uint64)
         n0 = np.zeros((self.nvar, self.k), dtype=np.uint64)
+        if var_range is not None:
+            v0, v1 = int(var_range[0]), int(var_range[1])
+            _ffi.check(_ffi.lib().pgmvae_model_count_vars(self._h, data.ctypes.data, 0, n, v0, v1, n1.ctypes.data,
+                                                          n0.ctypes.data))
+            return n1.astype(np.float64), n0.astype(np.float64)
         _ffi.check(_ffi.lib().pgmvae_model_count(self._h, data.ctypes.data, 0, n, n1.ctypes.data, n0.ctypes.data))
         if self.comm is not None and self.comm.nranks > 1:
             n1, n0 = self.comm.allreduce_u64(n1), self.comm.allreduce_u64(n0)
         return n1.astype(np.float64), n0.astype(np.float64)
 
-    def cpt(self, x, y=None):
-        """p(y=1 | code=k) with additive smoothing (reference core/model.py:85-88)."""
-        n1, n0 = self.count(x, y)
+    def cpt(self, x, y=None, shard="samples"):
+        """p(y=1 | code=k) with additive smoothing (reference core/model.py:85-88).  shard="variables": every rank
+        passes ALL samples and fills only the rows of its own variables (``var_shard``)."""
+        n1, n0 = self.count(x, y, var_range=self.var_shard() if shard == "variables" else None)
         return (n1 + 0.8) / (n1 + n0 + 1.6)
 
-    def pseudo_log_likelihood(self, x, y=None, total: Optional[int] = None):
+    def pseudo_log_likelihood(self, x, y=None, total: Optional[int] = None, shard="samples"):
         """Average pseudo log-likelihood (reference core/model.py:91-96); the float64
-        reduction runs on the device (pgmvae_pll_reduce)."""
+        reduction runs on the device (pgmvae_pll_reduce).
+
+        shard="samples" (default): x is this rank's shard of the samples, the [V,K] counts are summed over ranks.
+        shard="variables": x holds ALL samples on every rank; each rank evaluates only its own variables
+        (``var_shard``) against its rows of ``self.dist`` and ONE float64 scalar is all-reduced."""
         data = to_y(y if y is not None else x)
-        n1, n0 = self.count(data)
+        by_var = shard == "variables"
+        v0, v1 = self.var_shard() if by_var else (0, self.nvar)
+        n1, n0 = self.count(data, var_range=(v0, v1) if by_var else None)
         n = int(total if total is not None else data.shape[0])
         ctx, L = self.ctx, _ffi.lib()
-        d1 = _ffi.DeviceArray.from_numpy(ctx, n1.astype(np.uint64))
-        d0 = _ffi.DeviceArray.from_numpy(ctx, n0.astype(np.uint64))
-        dd = _ffi.DeviceArray.from_numpy(ctx, np.ascontiguousarray(self.dist, dtype=np.float64))
+        sl = slice(v0, v1)
+        d1 = _ffi.DeviceArray.from_numpy(ctx, np.ascontiguousarray(n1[sl]).astype(np.uint64))
+        d0 = _ffi.DeviceArray.from_numpy(ctx, np.ascontiguousarray(n0[sl]).astype(np.uint64))
+        dd = _ffi.DeviceArray.from_numpy(ctx, np.ascontiguousarray(self.dist[sl], dtype=np.float64))
         out = _ffi.DeviceArray(ctx, (1,), np.float64)
-        _ffi.check(L.pgmvae_pll_reduce(ctx.h, None, d1.ptr, d0.ptr, dd.ptr, n1.size, out.ptr))
-        return float(out.numpy()[0]) / n
+        if v1 > v0:
+            _ffi.check(L.pgmvae_pll_reduce(ctx.h, None, d1.ptr, d0.ptr, dd.ptr, (v1 - v0) * self.k, out.ptr))
+        s = float(out.numpy()[0])
+        if by_var and self.comm is not None and self.comm.nranks > 1:
+            s = float(self.comm.allreduce_f64(np.array([s], np.float64))[0])
+        return s / n
 
     def get_probability(self, x, fts=None):
         """p(y_i = 1 | code) of the selected nets (reference core/model.py:99-108);
@@ -376,11 +430,18 @@ class VqVAE:
         """Variables per workspace group (the step walks the V independent networks group by group)."""
         return int(_ffi.lib().pgmvae_model_group_size(self._h))
 
+    @staticmethod
+    def _npz_path(path: str) -> str:
+        path = os.fspath(path)
+        return path if path.endswith(".npz") else path + ".npz"          # np.savez appends the suffix itself
+
     def save_weights(self, path: str):
-        np.savez(path, **self.state_dict())
+        """Every tensor in the reference's layouts ([V,in,units], [V,1,units], [V,D,K]) + optimiser / EMA state
+        (run.py:63 intent).  tools/tf_crosscheck.py loads such a file into the unmodified reference."""
+        np.savez(self._npz_path(path), **self.state_dict())
 
     def load_weights(self, path: str):
-        with np.load(path) as z:
+        with np.load(self._npz_path(path)) as z:
             self.load_state_dict({k: z[k] for k in z.files})
 
     def __del__(self):

@@ -87,6 +87,12 @@ int pgmvae_device_count(int* n) {
     return PGMVAE_OK;
 }
 
+int pgmvae_device_can_access_peer(int device, int peer, int* out) {
+    PG_CHECK_ARG(out != nullptr);
+    PG_CUDA(cudaDeviceCanAccessPeer(out, device, peer));
+    return PGMVAE_OK;
+}
+
 int pgmvae_ctx_create(int device, pgmvae_ctx** out) {
     PG_CHECK_ARG(out != nullptr);
     int n = 0;

@@ -63,7 +63,6 @@ __global__ void init_uniform_kernel(float* __restrict__ dst, long long n, int ro
 // ---- peer-to-peer sum + Adam ------------------------------------------------------------------
 struct P2pArgs {
     float* const* peer_grads; int* const* peer_flags; int* my_flags;
-    float* const* peer_params;        // reduce-scatter form only: every rank's parameter buffer
     int rank, R, step;
     long long n;
     float *p, *m, *v;
@@ -132,68 +131,6 @@ __global__ void __launch_bounds__(256) p2p_sum_adam_kernel(const P2pArgs a) {
     }
 }
 
-// Reduce-scatter form of the same exchange (PGMVAE_P2P=2; built, NOT yet measured on hardware): rank r sums only
-// the r-th 1/R of the gradient buffer (reads (R-1)/R of it from the peers instead of (R-1) whole buffers), applies
-// Adam to that slice -- its Adam moments are the only ones that exist for it -- and writes the updated parameters
-// into every rank's parameter buffer.  Every slice is computed exactly once, so the replicas stay bit-identical.
-// The done flags then also mean "my slice has landed in your parameters": the step ends with p2p_wait_done_kernel.
-__global__ void __launch_bounds__(256) p2p_rs_adam_kernel(const P2pArgs a) {
-    __shared__ int ok;
-    if (blockIdx.x == 0 && threadIdx.x < a.R) {
-        __threadfence_system();
-        *reinterpret_cast<volatile int*>(a.peer_flags[threadIdx.x] + a.rank) = a.step;          // ready[rank] at peer
-    }
-    if (threadIdx.x == 0) {
-        int good = 1;
-        for (int q = 0; q < a.R && good; ++q) {
-            long long spins = 0;
-            while (ld_volatile_i32(a.my_flags + q) < a.step) {
-                if (++spins > 100000000ll) { good = 0; break; }
-                __nanosleep(100);
-            }
-        }
-        __threadfence_system();
-        ok = good;
-    }
-    __syncthreads();
-    if (!ok) {
-        if (threadIdx.x == 0) *reinterpret_cast<volatile int*>(a.err) = 1;
-        return;
-    }
-    const long long n4 = a.n >> 2;
-    const long long per = (n4 + a.R - 1) / a.R, lo = per * a.rank, hi = lo + per < n4 ? lo + per : n4;
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long i = lo + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += stride) {
-        float4 gg = reinterpret_cast<const float4*>(a.peer_grads[0])[i];
-        for (int q = 1; q < a.R; ++q) {
-            const float4 t = reinterpret_cast<const float4*>(a.peer_grads[q])[i];
-            gg.x += t.x; gg.y += t.y; gg.z += t.z; gg.w += t.w;
-        }
-        float4 pp = reinterpret_cast<float4*>(a.p)[i];
-        float4 mm = reinterpret_cast<float4*>(a.m)[i];
-        float4 vv = reinterpret_cast<float4*>(a.v)[i];
-#define PG_ADAM1(c)                                          \
-        mm.c += (gg.c - mm.c) * a.omb1;                      \
-        vv.c += (gg.c * gg.c - vv.c) * a.omb2;               \
-        pp.c -= (mm.c * a.alpha) / (sqrtf(vv.c) + a.eps);
-        PG_ADAM1(x) PG_ADAM1(y) PG_ADAM1(z) PG_ADAM1(w)
-#undef PG_ADAM1
-        reinterpret_cast<float4*>(a.m)[i] = mm;
-        reinterpret_cast<float4*>(a.v)[i] = vv;
-        for (int q = 0; q < a.R; ++q) reinterpret_cast<float4*>(a.peer_params[q])[i] = pp;   // own buffer included
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence_system();
-        if (atomicAdd(a.counter, 1u) == gridDim.x - 1) {           // last block: reads and remote writes are done
-            *a.counter = 0u;
-            __threadfence_system();
-            for (int q = 0; q < a.R; ++q)
-                *reinterpret_cast<volatile int*>(a.peer_flags[q] + a.R + a.rank) = a.step;      // done[rank] at peer
-        }
-    }
-}
-
 // before this rank overwrites its gradient buffer: every peer has finished reading the previous step's gradients
 __global__ void p2p_wait_done_kernel(const int* my_flags, int R, int step, int* err) {
     if ((int)threadIdx.x < R) {
@@ -240,8 +177,7 @@ struct pgmvae_model {
     // the tail of one overlaps the head of the next
     // peer-to-peer gradient exchange fused with Adam (single node, NVLink): every rank reads the gradient buffers
     // of all ranks directly and applies the identical update -- no NCCL launch on the critical path
-    bool p2p = false, p2p_rs = false;  // p2p_rs: reduce-scatter form (peer_params mapped as well)
-    float** peer_params = nullptr;     // device array [R] of parameter buffers (reduce-scatter form)
+    bool p2p = false;
     int p2p_rank = 0, p2p_n = 1, p2p_step = 0;
     float** peer_grads = nullptr;      // device array [R] of gradient buffers (own + IPC-mapped peers)
     int** peer_flags = nullptr;        // device array [R] of flag blocks: ready[R] | done[R]
@@ -452,6 +388,18 @@ int overlapped_allreduce(pgmvae_model* m, pgmvae_comm* comm, void* buf, int64_t 
     PG_CUDA(cudaEventRecord(m->ev_compute, st));
     PG_CUDA(cudaStreamWaitEvent(m->comm_stream, m->ev_compute, 0));
     return pg_comm_allreduce(comm, buf, n, dtype, m->comm_stream);
+}
+
+// a peer-to-peer exchange that timed out is fatal for this model: the replicas have diverged (some blocks skipped
+// the update) and the flag protocol is out of step.  The error word lives in pinned host memory, so every entry point
+// can look at it without synchronising.
+int p2p_check(const pgmvae_model* m) {
+    if (m->p2p_err && *reinterpret_cast<volatile int*>(m->p2p_err)) {
+        pgmvae_set_error("peer-to-peer gradient exchange: a rank did not reach the barrier (timed out); the model's replicas "
+                         "are no longer consistent -- re-create the model (PGMVAE_P2P=0 selects the NCCL exchange)");
+        return PGMVAE_ENCCL;
+    }
+    return PGMVAE_OK;
 }
 
 bool use_chain(const pgmvae_model* m) {
@@ -760,6 +708,7 @@ int pgmvae_model_set_tensor(pgmvae_model* m, const char* name, const float* host
 
 int pgmvae_model_get_tensor(pgmvae_model* m, const char* name, float* host, int64_t count) {
     PG_CHECK_ARG(m && name && host);
+    PG_TRY(p2p_check(m));
     TensorRef t;
     PG_TRY(resolve(m, name, &t));
     if (count != t.ref_count) {
@@ -817,38 +766,10 @@ int pgmvae_model_p2p_import(pgmvae_model* m, int rank, int nranks, const void* a
     return PGMVAE_OK;
 }
 
-/* reduce-scatter form: 3 x 64 bytes per rank (gradient buffer, flag block, parameter buffer) */
-int pgmvae_model_p2p_export_rs(pgmvae_model* m, void* handles_out) {
-    PG_CHECK_ARG(m && handles_out);
-    PG_TRY(pgmvae_model_p2p_export(m, handles_out));
-    cudaIpcMemHandle_t h;
-    PG_CUDA(cudaIpcGetMemHandle(&h, m->params));
-    memcpy((char*)handles_out + 2 * sizeof(h), &h, sizeof(h));
-    return PGMVAE_OK;
-}
-
-int pgmvae_model_p2p_import_rs(pgmvae_model* m, int rank, int nranks, const void* all_handles) {
-    PG_CHECK_ARG(m && all_handles && nranks >= 2 && nranks <= 8 && rank >= 0 && rank < nranks && m->p2p_flags);
-    PG_CUDA(cudaSetDevice(m->ctx->device));
-    constexpr size_t HS = sizeof(cudaIpcMemHandle_t);
-    char packed[8 * 2 * HS];                                    // the first two handles of every rank, repacked
-    float* prm[8];
-    for (int q = 0; q < nranks; ++q) {
-        const char* src = (const char*)all_handles + (size_t)q * 3 * HS;
-        memcpy(packed + (size_t)q * 2 * HS, src, 2 * HS);
-        if (q == rank) { prm[q] = m->params; continue; }
-        cudaIpcMemHandle_t h;
-        memcpy(&h, src + 2 * HS, HS);
-        void* pp = nullptr;
-        PG_CUDA(cudaIpcOpenMemHandle(&pp, h, cudaIpcMemLazyEnablePeerAccess));
-        m->ipc_opened.push_back(pp);
-        prm[q] = (float*)pp;
-    }
-    PG_TRY(pgmvae_model_p2p_import(m, rank, nranks, packed));
-    PG_TRY(dev_alloc(m, (void**)&m->peer_params, 8 * sizeof(float*)));
-    PG_CUDA(cudaMemcpyAsync(m->peer_params, prm, nranks * sizeof(float*), cudaMemcpyHostToDevice, m->ctx->stream));
-    PG_CUDA(cudaStreamSynchronize(m->ctx->stream));
-    m->p2p_rs = true;
+/* give up the peer-to-peer exchange (a rank could not map its peers): the NCCL path is used instead */
+int pgmvae_model_p2p_disable(pgmvae_model* m) {
+    PG_CHECK_ARG(m != nullptr);
+    m->p2p = false;
     return PGMVAE_OK;
 }
 
@@ -872,6 +793,7 @@ int run_step(pgmvae_model* m, const uint8_t* y, int y_on_device, int B, int glob
              int flags, float* out_dev, double* metrics4) {
     PG_CHECK_ARG(m && y);
     PG_CHECK_ARG(B >= 1 && B <= m->max_batch);
+    PG_TRY(p2p_check(m));
     if (global_B <= 0) global_B = B;
     PG_CHECK_ARG(global_B >= B);
     pgmvae_ctx* ctx = m->ctx;
@@ -1211,20 +1133,10 @@ int run_step(pgmvae_model* m, const uint8_t* y, int y_on_device, int B, int glob
             a.n = (long long)trainable; a.p = m->params; a.m = m->adam_m; a.v = m->adam_v;
             a.alpha = alpha; a.omb1 = (float)(1.0 - b1); a.omb2 = (float)(1.0 - b2); a.eps = 1e-7f;
             a.counter = m->p2p_counter; a.err = m->p2p_err;
-            a.peer_params = m->peer_params;
-            const int64_t mine = m->p2p_rs ? pg_cdiv((int64_t)trainable, m->p2p_n) : (int64_t)trainable;
-            int blocks = (int)std::min<int64_t>(pg_cdiv(mine, 256 * 4 * 2), (int64_t)ctx->sm_count * 4);
+            int blocks = (int)std::min<int64_t>(pg_cdiv((int64_t)trainable, 256 * 4 * 2), (int64_t)ctx->sm_count * 4);
             if (blocks < 1) blocks = 1;
-            if (m->p2p_rs) {
-                PG_KERNEL(ctx, st, "p2p_rs_adam", 4.0 * mine * (2.0 * m->p2p_n + 5.0), (10.0 + m->p2p_n) * mine);
-                p2p_rs_adam_kernel<<<blocks, 256, 0, st>>>(a);
-                PG_LAUNCHED(ctx);
-                // the step is over when every peer's slice has landed in this rank's parameters
-                p2p_wait_done_kernel<<<1, 32, 0, st>>>(m->p2p_flags, m->p2p_n, m->p2p_step, m->p2p_err);
-            } else {
-                PG_KERNEL(ctx, st, "p2p_sum_adam", 4.0 * trainable * (m->p2p_n + 6.0), (10.0 + m->p2p_n) * trainable);
-                p2p_sum_adam_kernel<<<blocks, 256, 0, st>>>(a);
-            }
+            PG_KERNEL(ctx, st, "p2p_sum_adam", 4.0 * trainable * (m->p2p_n + 6.0), (10.0 + m->p2p_n) * trainable);
+            p2p_sum_adam_kernel<<<blocks, 256, 0, st>>>(a);
             PG_LAUNCHED(ctx);
         } else {
             PG_TRY(pgmvae_adam_step(ctx, st, m->params, m->grads, m->adam_m, m->adam_v, (int64_t)trainable, alpha, b1, b2,
@@ -1237,10 +1149,7 @@ int run_step(pgmvae_model* m, const uint8_t* y, int y_on_device, int B, int glob
     if (metrics4) {
         PG_CUDA(cudaMemcpyAsync(m->acc_host, m->acc, 4 * sizeof(double), cudaMemcpyDeviceToHost, st));
         PG_CUDA(cudaStreamSynchronize(st));
-        if (m->p2p_err && *m->p2p_err) {
-            pgmvae_set_error("peer-to-peer gradient exchange: a rank did not reach the barrier (timed out)");
-            return PGMVAE_ENCCL;
-        }
+        PG_TRY(p2p_check(m));
         const double mse = m->acc_host[0] / n_out, mae = m->acc_host[1] / n_out;
         const double e_latent = m->acc_host[2] / n_lat;
         const double vq = m->ema ? m->cost * e_latent : (1.0 + m->cost) * e_latent;
@@ -1280,9 +1189,22 @@ int pgmvae_model_encode(pgmvae_model* m, const uint8_t* y, int y_on_device, int 
     return PGMVAE_OK;
 }
 
+int pgmvae_model_arithmetic(pgmvae_model* m) {
+    if (!m) return -1;
+    if (m->bf16) return 2;
+    return m->ctx->precision == PGMVAE_PREC_FP32 ? 0 : 1;
+}
+
 int pgmvae_model_count(pgmvae_model* m, const uint8_t* y, int y_on_device, int64_t N, unsigned long long* n1_host,
                        unsigned long long* n0_host) {
+    PG_CHECK_ARG(m != nullptr);
+    return pgmvae_model_count_vars(m, y, y_on_device, N, 0, m->V, n1_host, n0_host);
+}
+
+int pgmvae_model_count_vars(pgmvae_model* m, const uint8_t* y, int y_on_device, int64_t N, int v0, int v1,
+                            unsigned long long* n1_host, unsigned long long* n0_host) {
     PG_CHECK_ARG(m && y && n1_host && n0_host && N >= 0);
+    PG_CHECK_ARG(v0 >= 0 && v0 <= v1 && v1 <= m->V);
     pgmvae_ctx* ctx = m->ctx;
     cudaStream_t st = ctx->stream;
     PG_CUDA(cudaSetDevice(ctx->device));
@@ -1290,7 +1212,7 @@ int pgmvae_model_count(pgmvae_model* m, const uint8_t* y, int y_on_device, int64
     PG_TRY(refresh_shadows(m));
     PG_CUDA(cudaMemsetAsync(m->n1, 0, cs * 8, st));
     PG_CUDA(cudaMemsetAsync(m->n0, 0, cs * 8, st));
-    if (use_chain(m) && m->Vg >= m->V && N > m->max_batch) {
+    if (use_chain(m) && m->Vg >= m->V && N > m->max_batch && v0 == 0 && v1 == m->V) {
         // slabs of up to 32768 samples per launch: 86 tile triples per variable instead of 11, so the items divide
         // evenly over the SMs, and an eighth of the launches
         const int CB = (int)std::min<int64_t>(N, 32768);
@@ -1315,8 +1237,8 @@ int pgmvae_model_count(pgmvae_model* m, const uint8_t* y, int y_on_device, int64
         const int B = (int)std::min<int64_t>(m->max_batch, N - s);
         const uint8_t* y_dev = nullptr;
         PG_TRY(upload_batch(m, y + (size_t)s * m->V, y_on_device, B, &y_dev));
-        for (int g0 = 0; g0 < m->V; g0 += m->Vg) {
-            const int Gn = std::min(m->Vg, m->V - g0);
+        for (int g0 = v0; g0 < v1; g0 += m->Vg) {
+            const int Gn = std::min(m->Vg, v1 - g0);
             if (use_chain(m)) {      // encoder + assignment + histogram in one launch
                 PG_TRY(chain_encode(m, g0, Gn, B, y_dev, m->n1 + (size_t)g0 * m->K, m->n0 + (size_t)g0 * m->K));
                 continue;
@@ -1326,8 +1248,11 @@ int pgmvae_model_count(pgmvae_model* m, const uint8_t* y, int y_on_device, int64
                                     m->n0 + (size_t)g0 * m->K, Gn, B, m->K));
         }
     }
-    PG_CUDA(cudaMemcpyAsync(n1_host, m->n1, cs * 8, cudaMemcpyDeviceToHost, st));
-    PG_CUDA(cudaMemcpyAsync(n0_host, m->n0, cs * 8, cudaMemcpyDeviceToHost, st));
+    const size_t lo = (size_t)v0 * m->K, cnt = (size_t)(v1 - v0) * m->K;
+    if (cnt) {
+        PG_CUDA(cudaMemcpyAsync(n1_host + lo, m->n1 + lo, cnt * 8, cudaMemcpyDeviceToHost, st));
+        PG_CUDA(cudaMemcpyAsync(n0_host + lo, m->n0 + lo, cnt * 8, cudaMemcpyDeviceToHost, st));
+    }
     PG_CUDA(cudaStreamSynchronize(st));
     return PGMVAE_OK;
 }

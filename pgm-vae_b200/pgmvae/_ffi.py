@@ -92,12 +92,14 @@ SIGNATURES = {
     "pgmvae_model_set_adam_step": (_i, [_vp, _i64]),
     "pgmvae_model_p2p_export": (_i, [_vp, _vp]),
     "pgmvae_model_p2p_import": (_i, [_vp, _i, _i, _vp]),
-    "pgmvae_model_p2p_export_rs": (_i, [_vp, _vp]),
-    "pgmvae_model_p2p_import_rs": (_i, [_vp, _i, _i, _vp]),
+    "pgmvae_model_p2p_disable": (_i, [_vp]),
+    "pgmvae_device_can_access_peer": (_i, [_i, _i, _vp]),
     "pgmvae_model_train_step": (_i, [_vp, _vp, _i, _i, _i, _f, _vp, _i, _vp]),
     "pgmvae_model_forward": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
     "pgmvae_model_encode": (_i, [_vp, _vp, _i, _i, _vp]),
     "pgmvae_model_count": (_i, [_vp, _vp, _i, _i64, _vp, _vp]),
+    "pgmvae_model_count_vars": (_i, [_vp, _vp, _i, _i64, _i, _i, _vp, _vp]),
+    "pgmvae_model_arithmetic": (_i, [_vp]),
     "pgmvae_model_device_bytes": (_i64, [_vp]),
     "pgmvae_model_group_size": (_i, [_vp]),
     "pgmvae_comm_unique_id": (_i, [_vp]),
@@ -178,6 +180,9 @@ class Context:
 
     def set_precision(self, prec: int):
         check(lib().pgmvae_ctx_set_precision(self.h, int(prec)))
+
+    def get_precision(self) -> int:
+        return int(lib().pgmvae_ctx_get_precision(self.h))
 
     def profile_begin(self):
         check(lib().pgmvae_ctx_profile_begin(self.h))

@@ -21,6 +21,8 @@ def main():
     rng = np.random.default_rng(0)
     res = []
     shapes = [(1556, 400), (400, 200), (200, 100), (100, 50), (50, 64), (64, 50), (400, 1556)]
+    if len(sys.argv) > 3:
+        shapes = [tuple(int(t) for t in a.split("x")) for a in sys.argv[3:]]
     for fin, fout in shapes:
         pin, pout = (fin + 7) // 8 * 8, (fout + 7) // 8 * 8
         x = _ffi.DeviceArray.from_numpy(ctx, rng.standard_normal((G, B, pin), dtype=np.float32))

@@ -228,12 +228,16 @@ def test_bf16_model_gradients_vs_oracle(ctx, monkeypatch, V, units, D, K, B, ema
     assert abs(met[1] - exp["mse"]) <= 1e-3 * exp["mse"]
     assert abs(met[2] - exp["mae"]) <= 1e-3 * exp["mae"]
     assert abs(met[3] - exp["vq_loss"]) <= 2e-2 * exp["vq_loss"] + 1e-9
-    worst = 0.0
+    worst = worst_fro = 0.0
     for n, g in grads.items():
         e = rel_err(g, exp["grads"][n])
-        worst = max(worst, e)
+        ref = exp["grads"][n].astype(np.float64)
+        fro = np.linalg.norm(g - ref) / max(np.linalg.norm(ref), 1e-30)
+        worst, worst_fro = max(worst, e), max(worst_fro, fro)
+        # element-wise maximum: a flipped code changes a whole sample's contribution; norm-wise: bf16 rounding
         assert e < (5e-2 if flips == 0 else 0.5), (n, e, flips)
-    print(f"   worst gradient rel err {worst:.2e}")
+        assert fro < 6e-2, (n, fro, flips)
+    print(f"   worst gradient error: max-norm {worst:.2e}, Frobenius {worst_fro:.2e}")
 
 
 @pytest.mark.parametrize("V,units,D,K,B,ema,gv", GEOMS[1:])
@@ -250,9 +254,11 @@ def test_multi_group_equals_single_group(ctx, monkeypatch, prec, V, units, D, K,
         m = _model(ctx, P, units, V, D, K, B, ema, params, monkeypatch, g)
         assert m.group_size() == (g or V)
         met, grads = _grads(m, y[:B])
-        mets = [m.train_on_batch(np.ascontiguousarray(y[s * B:(s + 1) * B])) for s in range(2)]
+        mets = [m.train_on_batch(np.ascontiguousarray(y[:B]))]
+        emb1 = m._get_tensor("vq.embeddings")
+        mets.append(m.train_on_batch(np.ascontiguousarray(y[B:])))
         n1, n0 = m.count(y)
-        res[mode] = (met, grads, mets, m._get_tensor("vq.embeddings"), m._get_tensor("fd0.kernel"), n1, n0)
+        res[mode] = (met, grads, mets, m._get_tensor("vq.embeddings"), m._get_tensor("fd0.kernel"), n1, n0, emb1)
     a, b = res["one"], res["many"]
     np.testing.assert_allclose(b[0], a[0], rtol=1e-6)
     for n in a[1]:
@@ -260,8 +266,13 @@ def test_multi_group_equals_single_group(ctx, monkeypatch, prec, V, units, D, K,
     for s in range(2):
         for k in a[2][s]:
             assert abs(a[2][s][k] - b[2][s][k]) <= 1e-6 * abs(a[2][s][k]) + 1e-12
-    assert rel_err(b[3], a[3]) < 1e-6 and rel_err(b[4], a[4]) < 1e-6
-    assert np.array_equal(a[5], b[5]) and np.array_equal(a[6], b[6])
+    # the codebook after ONE update is the same to rounding (the statistics are sums of fp32 reductions whose order
+    # is not fixed); after the second step a latent within that rounding of a decision boundary may take the other
+    # code, which moves one code vector by ~decay/size of it
+    assert rel_err(b[7], a[7]) < 2e-6 and rel_err(b[4], a[4]) < 1e-5
+    assert rel_err(b[3], a[3]) < 1e-2
+    assert (a[5] + a[6]).sum() == (b[5] + b[6]).sum() == 2 * B * V
+    assert np.abs(a[5] - b[5]).sum() <= 1e-3 * B * V
 
 
 @pytest.mark.parametrize("prec,tol_loss", [("tf32", 1e-3), ("bf16", 1e-3)])
@@ -289,6 +300,7 @@ def test_three_steps_vs_oracle_cfg2_shapes_state_and_pll(ctx, monkeypatch, prec,
     emb, oemb = m._get_tensor("vq.embeddings"), om.p["vq.embeddings"].detach().numpy()
     used = np.abs(oemb).max(axis=1, keepdims=True) > 0                     # dead codes are exactly 0 on both sides
     e_emb = np.abs(emb - oemb).max() / np.abs(oemb).max()
+    e_fro = np.linalg.norm(emb.astype(np.float64) - oemb) / np.linalg.norm(oemb.astype(np.float64))
     idx = m(yall, code_only=True).argmax(-1)
     with torch.no_grad():
         oidx = om(O.make_xs(yall), code_only=True).argmax(-1).numpy()
@@ -297,8 +309,13 @@ def test_three_steps_vs_oracle_cfg2_shapes_state_and_pll(ctx, monkeypatch, prec,
     om.dist = om.cpt(O.make_xs(yall), yall)
     e_dist = np.abs(m.dist - om.dist.numpy()).max()
     pll, opll = m.pseudo_log_likelihood(yall), om.pseudo_log_likelihood(O.make_xs(yall), yall)
-    print(f"{prec} after 3 steps: codebook max err {e_emb:.2e} of max |e|, code flips {flips:.2e}, "
+    print(f"{prec} after 3 steps: codebook max err {e_emb:.2e} of max |e| (Frobenius {e_fro:.2e}), code flips {flips:.2e}, "
           f"dist max abs err {e_dist:.2e}, pll {pll:.6f} vs {opll:.6f} ({abs(pll - opll) / abs(opll):.1e}); used codes {used.mean():.2f}")
     assert abs(pll - opll) <= 1e-3 * abs(opll)
-    assert e_emb <= (5e-2 if flips > 0 else 1e-3)
+    # a code vector is the mean of the few latents assigned to it, so its error is the rounding error of z itself
+    # (2^-11 per tf32 operand, 2^-9 per bf16 operand, averaged over the contraction): the codebook as a whole agrees to
+    # 1e-3 (tf32) / 3e-3 (bf16) in norm; single entries of rarely used codes deviate a few times more
+    assert e_fro <= (1e-3 if prec == "tf32" else 3e-3)
+    assert e_emb <= (5e-3 if prec == "tf32" else 2e-2)
+    assert e_dist <= 2e-3
     assert flips <= 2e-2
