@@ -31,6 +31,7 @@
 //   WGRAD_D / WGRAD_T  fp32 weight gradient
 #include <cuda_bf16.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include <algorithm>
 
@@ -47,14 +48,18 @@ constexpr int PANEL_BYTES = BK * 128;       // MN-major operand: [64 k][64 mn] p
 constexpr int MAX_STAGES = 8;
 constexpr int THREADS = 384;
 constexpr int ACC_COLS = 256;               // TMEM columns per accumulator buffer
+constexpr int ONES_COL = 240;               // column of the bias-gradient accumulator (WGRAD_T, BN <= 240)
+constexpr int ONES_BYTES = 2048;            // [16 n][64 k] bf16 tile of 1.0 (K-major)
 
 enum { EPI_FWD = 0, EPI_SIGMOID_MSE = 1, EPI_DGRAD = 2, EPI_WGRAD_D = 3, EPI_WGRAD_T = 4 };
 
 struct Bf16P {
     int G, M, N, K, BN, tiles_m, tiles_n, kblocks, stages, total_tiles;
     int a_mn, b_mn, a_shared, b_shared, b_panels;
+    int pair, total_ptiles, tiles_mp, tiles_np;           // 2-CTA clusters: 0 none, 1 pair along M (B multicast), 2 pair along N (A multicast)
     unsigned a_bytes, b_bytes;
     int vec;                                              // rows allow 16-byte vector access
+    int tma_out, tma_in, in_shared;                       // bf16 output / epilogue operand move through staged TMA tiles
     __nv_bfloat16* cb; long long cb_gs; int ldcb;         // bf16 output rows (may be null)
     float* cf; long long cf_gs; int ldcf;                 // fp32 output rows (may be null)
     const float* bias; long long bias_gs; int act;
@@ -63,6 +68,7 @@ struct Bf16P {
     const float* hf; long long hf_gs; int ldhf;           // ... or fp32
     const float* z; const float* q; long long zq_gs; int ldzq; float cscale;
     float* dw; long long dw_gs; int lddw; int zero_row_base, accum;           // WGRAD (accum: dW += instead of =)
+    float* db; long long db_gs; int ones;                 // WGRAD_T: bias gradient = row sums of A through a ones-tile MMA
 };
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -141,20 +147,61 @@ __device__ __forceinline__ void load_f32_row(const float* src, float (&v)[32], i
     }
 }
 
+// Tensor maps of the epilogue's bf16 tiles: one map PER N TILE (the tensor seen through it starts at the tile's first
+// column and is as wide as the tile), so that TMA clips the columns a 32-wide chunk overhangs the tile as well as the
+// ragged edges of the tensor.  [64-byte swizzle, box = 128 rows x 32 columns]
+constexpr int MAX_NT_MAPS = 8;
+struct EpiMaps {
+    CUtensorMap out[MAX_NT_MAPS];      // bf16 output rows (activation / gradient)
+    CUtensorMap in[MAX_NT_MAPS];       // bf16 epilogue operand rows (targets of the MSE stage / activation below)
+};
+constexpr int STG_TILE = TM * 64;      // one staged chunk: 128 rows x 32 bf16 (64 B, 64-byte swizzle) = 8 KB
+constexpr int STG_WG = 3 * STG_TILE;   // per epilogue warpgroup: out | in[0] | in[1]
+
+// (variable, M tile, N tile) of pair-tile `pt` for the CTA of rank `crank` in its cluster.  N fastest, then M, then
+// the variable; the two CTAs of a pair take neighbouring M tiles of one N tile (pair == 1: they share the B tile) or
+// neighbouring N tiles of one M tile (pair == 2: they share the A tile).  Tiles past the edge are phantoms: their
+// loads are zero-filled and nothing of them is stored, but they keep the pair in lock step.
+__device__ __forceinline__ void decode_tile(const Bf16P& p, int pt, int crank, int& g, int& mt, int& nt) {
+    if (p.pair == 1) {
+        const int per_g = p.tiles_mp * p.tiles_n;
+        g = pt / per_g;
+        const int r = pt - g * per_g;
+        const int mtp = r / p.tiles_n;
+        nt = r - mtp * p.tiles_n;
+        mt = 2 * mtp + crank;
+    } else if (p.pair == 2) {
+        const int per_g = p.tiles_m * p.tiles_np;
+        g = pt / per_g;
+        const int r = pt - g * per_g;
+        mt = r / p.tiles_np;
+        nt = 2 * (r - mt * p.tiles_np) + crank;
+    } else {
+        const int per_g = p.tiles_m * p.tiles_n;
+        g = pt / per_g;
+        const int r = pt - g * per_g;
+        mt = r / p.tiles_n;
+        nt = r - mt * p.tiles_n;
+    }
+}
+
 template <int EPI>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
-                 const __grid_constant__ Bf16P p) {
+                 const __grid_constant__ EpiMaps em, const __grid_constant__ Bf16P p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-byte aligned, shared space
     uint8_t* sA = smem;                                           // [stages][16 KB]
     uint8_t* sB = sA + (size_t)p.stages * A_BYTES;                // [stages][b_bytes]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sB + (size_t)p.stages * p.b_bytes);
+    uint8_t* sStage = sB + (size_t)p.stages * p.b_bytes;          // [2 warpgroups][STG_WG] (only with tma_out / tma_in)
+    uint8_t* sOnes = sStage + ((p.tma_out || p.tma_in) ? 2 * STG_WG : 0);      // (only with p.ones)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sOnes + (p.ones ? ONES_BYTES : 0));
     uint64_t* full = bars;                        // [MAX_STAGES]   TMA -> MMA
     uint64_t* empty = bars + MAX_STAGES;          // [MAX_STAGES]   MMA -> TMA
     uint64_t* tmem_full = bars + 2 * MAX_STAGES;  // [2]            MMA -> epilogue warpgroup
     uint64_t* tmem_empty = tmem_full + 2;         // [2]            epilogue warpgroup -> MMA
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    uint64_t* in_full = tmem_empty + 2;           // [2 warpgroups][2 buffers]  epilogue operand chunk has landed
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(in_full + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -165,31 +212,47 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < MAX_STAGES; ++s) {
             tc::mbar_init(&full[s], 1);
-            tc::mbar_init(&empty[s], 1);
+            tc::mbar_init(&empty[s], p.pair ? 2 : 1);      // pairs: a stage is free when BOTH CTAs' MMAs have read it
         }
         for (int b = 0; b < 2; ++b) {
             tc::mbar_init(&tmem_full[b], 1);
             tc::mbar_init(&tmem_empty[b], 4);      // one arrival per warp of the warpgroup
         }
+        for (int b = 0; b < 4; ++b) tc::mbar_init(&in_full[b], 1);
         tc::fence_barrier_init();
     }
     if (warp == 2) {
         tc::tmem_alloc(tmem_slot, 512u);
         tc::tmem_relinquish();
     }
+    if (EPI == EPI_WGRAD_T && p.ones && warp == 3) {
+        // B tile of ones: D2[m][0..16) += A[m][k] * 1 leaves sum_k A[m][k] -- the bias gradient when A = dY^T -- in
+        // 16 spare accumulator columns, for 8 extra tensor cycles per k-step on one N tile (all-ones is swizzle-invariant)
+        for (int i = lane; i < ONES_BYTES / 16; i += 32)
+            reinterpret_cast<uint4*>(sOnes)[i] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
+        tc::fence_proxy_async_smem();
+    }
     tc::fence_before_thread_sync();
     __syncthreads();
+    if (p.pair) tc::cluster_sync_all();                   // the peer's barriers exist before anything is multicast to them
     tc::fence_after_thread_sync();
     const uint32_t tmem_base = *tmem_slot;
-    const int tiles_per_g = p.tiles_m * p.tiles_n;
+    const int crank = p.pair ? (int)tc::cluster_ctarank() : 0;
+    const int csize = p.pair ? 2 : 1;
+    const int cid = (int)blockIdx.x / csize, ncl = (int)gridDim.x / csize;
 
     if (warp == 0) {
         // ===================== TMA producer (warp-uniform loop, one elected lane issues) =====================
         const uint32_t stage_tx = p.a_bytes + p.b_bytes;
+        // pairs: this CTA loads ITS HALF of the shared operand and multicasts it into both CTAs (rows of a K-major
+        // tile, 64-wide panels of an MN-major one); every CTA still receives -- and expects -- the whole stage
+        const int a_rows_half = TM / 2, b_rows_half = p.BN / 2;
+        const int bp0 = p.pair == 1 ? (crank == 0 ? 0 : (p.b_panels + 1) / 2) : 0;
+        const int bp1 = p.pair == 1 ? (crank == 0 ? (p.b_panels + 1) / 2 : p.b_panels) : p.b_panels;
         uint32_t s = 0, ph = 0;
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-            const int g = tile / tiles_per_g, r = tile - g * tiles_per_g;
-            const int mt = r / p.tiles_n, nt = r - mt * p.tiles_n;
+        for (int pt = cid; pt < p.total_ptiles; pt += ncl) {
+            int g, mt, nt;
+            decode_tile(p, pt, crank, g, mt, nt);
             const int m0 = mt * TM, n0 = nt * p.BN;
             const int ga = p.a_shared ? 0 : g, gb = p.b_shared ? 0 : g;
             for (int kb = 0; kb < p.kblocks; ++kb) {
@@ -198,13 +261,27 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                     tc::mbar_arrive_expect_tx(&full[s], stage_tx);
                     uint8_t* a_dst = sA + (size_t)s * A_BYTES;
                     uint8_t* b_dst = sB + (size_t)s * p.b_bytes;
-                    if (!p.a_mn) {
+                    if (p.pair == 2) {                     // A shared by the pair
+                        if (!p.a_mn)
+                            tc::tma_load_3d_mc(a_dst + crank * a_rows_half * 128, &mapA, &full[s], kb * BK, m0 + crank * a_rows_half,
+                                               ga, 3);
+                        else
+                            tc::tma_load_3d_mc(a_dst + crank * PANEL_BYTES, &mapA, &full[s], m0 + crank * 64, kb * BK, ga, 3);
+                    } else if (!p.a_mn) {
                         tc::tma_load_3d(a_dst, &mapA, &full[s], kb * BK, m0, ga);                   // [128 m][64 k]
                     } else {
                         tc::tma_load_3d(a_dst, &mapA, &full[s], m0, kb * BK, ga);                   // 2 panels [64 k][64 m]
                         tc::tma_load_3d(a_dst + PANEL_BYTES, &mapA, &full[s], m0 + 64, kb * BK, ga);
                     }
-                    if (!p.b_mn) {
+                    if (p.pair == 1) {                     // B shared by the pair
+                        if (!p.b_mn) {
+                            tc::tma_load_3d_mc(b_dst + crank * b_rows_half * 128, &mapB, &full[s], kb * BK, n0 + crank * b_rows_half,
+                                               gb, 3);
+                        } else {
+                            for (int pn = bp0; pn < bp1; ++pn)
+                                tc::tma_load_3d_mc(b_dst + (size_t)pn * PANEL_BYTES, &mapB, &full[s], n0 + pn * 64, kb * BK, gb, 3);
+                        }
+                    } else if (!p.b_mn) {
                         tc::tma_load_3d(b_dst, &mapB, &full[s], kb * BK, n0, gb);                   // [BN n][64 k]
                     } else {
                         for (int pn = 0; pn < p.b_panels; ++pn)                                      // panels [64 k][64 n]
@@ -227,9 +304,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                                     : tc::make_smem_desc(tc::smem_u32(sB), 16, 1024, 2);
         const uint32_t a_step = (p.a_mn ? 2048u : 32u) >> 4, b_step = (p.b_mn ? 2048u : 32u) >> 4;
         const uint32_t a_stage = (uint32_t)A_BYTES >> 4, b_stage = p.b_bytes >> 4;
+        const uint32_t idesc1 = tc::make_idesc(1, TM, 16, p.a_mn, 0);
+        const uint64_t dOnes = tc::make_smem_desc(tc::smem_u32(sOnes), 16, 1024, 2);
         uint32_t s = 0, ph = 0, it = 0;
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+        for (int pt = cid; pt < p.total_ptiles; pt += ncl, ++it) {
             const uint32_t buf = it & 1, use = it >> 1;
+            int g, mt, nt;
+            decode_tile(p, pt, crank, g, mt, nt);
+            const bool ones = EPI == EPI_WGRAD_T && p.ones && nt == 0;
             tc::mbar_wait(&tmem_empty[buf], (use & 1) ^ 1);          // the epilogue has drained this buffer
             tc::fence_after_thread_sync();
             const uint32_t d_tmem = tmem_base + buf * ACC_COLS;
@@ -242,7 +324,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                     for (int k4 = 0; k4 < 4; ++k4)
                         tc::mma_f16(d_tmem, dA + (uint64_t)(k4 * a_step), dB + (uint64_t)(k4 * b_step), idesc,
                                     (kb > 0 || k4 > 0) ? 1u : 0u);
-                    tc::mma_commit(&empty[s]);
+                    if (ones) {
+#pragma unroll
+                        for (int k4 = 0; k4 < 4; ++k4)
+                            tc::mma_f16(d_tmem + ONES_COL, dA + (uint64_t)(k4 * a_step), dOnes + (uint64_t)(k4 * 2), idesc1,
+                                        (kb > 0 || k4 > 0) ? 1u : 0u);
+                    }
+                    if (p.pair) tc::mma_commit_mc(&empty[s], 3);
+                    else tc::mma_commit(&empty[s]);
                     if (kb == p.kblocks - 1) tc::mma_commit(&tmem_full[buf]);
                 }
                 __syncwarp();
@@ -253,26 +342,81 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         // ===================== epilogue: two warpgroups, thread = accumulator row =====================
         const int wg = (warp - 4) >> 2;                // drains accumulator buffer wg (tiles it with it & 1 == wg)
         const int qd = warp & 3;                       // TMEM lane quarter of this warp
+        const int rt = qd * 32 + lane;                 // row within the tile
+        const bool leader = rt == 0;                   // issues this warpgroup's TMA loads / stores
         const uint32_t lane_addr = tmem_base + ((uint32_t)(qd * 32) << 16) + wg * ACC_COLS;
+        // staged chunk [128 rows][64 B], 64-byte swizzle: the 16-byte piece j of row r sits at piece j ^ ((r >> 1) & 3)
+        uint8_t* sOut = sStage + (size_t)wg * STG_WG;
+        uint8_t* sIn = sOut + STG_TILE;
+        const uint32_t swz = (uint32_t)((rt >> 1) & 3);
+        uint64_t* my_in_full = in_full + wg * 2;
+        uint32_t in_uses[2] = {0u, 0u};
+        const bool tin = p.tma_in != 0, tout = p.tma_out != 0;
         double dsq = 0.0, dab = 0.0;
         uint32_t it = 0;
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+        for (int pt = cid; pt < p.total_ptiles; pt += ncl, ++it) {
             if ((int)(it & 1) != wg) continue;
             const uint32_t use = it >> 1;
-            const int g = tile / tiles_per_g, r = tile - g * tiles_per_g;
-            const int mt = r / p.tiles_n, nt = r - mt * p.tiles_n;
+            int g, mt, nt;
+            decode_tile(p, pt, crank, g, mt, nt);
             const int m0 = mt * TM, n0 = nt * p.BN;
-            const int row = m0 + qd * 32 + lane;
+            const int row = m0 + rt;
             const bool rvalid = row < p.M;
             const int ncols = min(p.BN, p.N - n0);
             const int nch = (ncols + 31) >> 5;
+            if (ncols <= 0) {                              // phantom N tile of a pair: nothing to store, hand the buffer back
+                tc::mbar_wait(&tmem_full[wg], use & 1);
+                tc::fence_after_thread_sync();
+                tc::fence_before_thread_sync();
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(&tmem_empty[wg]);
+                continue;
+            }
+            const int gin = p.in_shared ? 0 : g;
             float sq = 0.f, ab = 0.f;
+
+            // epilogue operand (targets / activation below) of chunk c -> staging buffer c & 1
+            auto fetch_in = [&](int c) {
+                if (leader) {
+                    tc::mbar_arrive_expect_tx(&my_in_full[c & 1], (uint32_t)STG_TILE);
+                    tc::tma_load_3d(sIn + (size_t)(c & 1) * STG_TILE, &em.in[nt], &my_in_full[c & 1], c * 32, m0, gin);
+                }
+            };
+            // the thread's 32 operand values of chunk c (bf16 -> fp32)
+            auto read_in = [&](int c, float (&t)[32]) {
+                const int b = c & 1;
+                tc::mbar_wait(&my_in_full[b], in_uses[b] & 1);
+                ++in_uses[b];
+                const uint8_t* rowp = sIn + (size_t)b * STG_TILE + rt * 64;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const uint4 u = *reinterpret_cast<const uint4*>(rowp + ((j ^ swz) << 4));
+                    t[8 * j] = bf16_lo(u.x); t[8 * j + 1] = bf16_hi(u.x); t[8 * j + 2] = bf16_lo(u.y); t[8 * j + 3] = bf16_hi(u.y);
+                    t[8 * j + 4] = bf16_lo(u.z); t[8 * j + 5] = bf16_hi(u.z); t[8 * j + 6] = bf16_lo(u.w); t[8 * j + 7] = bf16_hi(u.w);
+                }
+            };
+            // the thread's 32 bf16 results of chunk c -> staging tile -> one TMA store per warpgroup
+            auto write_out = [&](int c, const float (&v)[32]) {
+                if (leader) tc::bulk_wait_read();                  // the previous store has read the staging tile
+                tc::named_bar_sync(1 + wg, 128);
+                uint8_t* rowp = sOut + rt * 64;
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    *reinterpret_cast<uint4*>(rowp + ((j ^ swz) << 4)) =
+                        make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
+                                   pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
+                tc::fence_proxy_async_smem();
+                tc::named_bar_sync(1 + wg, 128);
+                if (leader) {
+                    tc::tma_store_3d(&em.out[nt], sOut, c * 32, m0, g);
+                    tc::bulk_commit();
+                }
+            };
 
             auto process = [&](float (&v)[32], int c) {
                 const int nb = n0 + c * 32;
                 const int nv = min(32, ncols - c * 32);            // valid columns of this chunk (tile and tensor bounds)
                 if (EPI == EPI_FWD) {
-                    if (!rvalid) return;
                     if (p.bias) {
                         float bv[32];
                         load_f32_row(p.bias + (long long)g * p.bias_gs + nb, bv, nv, p.vec);
@@ -286,35 +430,49 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 #pragma unroll
                         for (int j = 0; j < 32; ++j) v[j] = sigmoid_fast(v[j]);
                     }
-                    if (p.cb) store_bf16_row(p.cb + (long long)g * p.cb_gs + (long long)row * p.ldcb + nb, v, nv, p.vec);
-                    if (p.cf) store_f32_row(p.cf + (long long)g * p.cf_gs + (long long)row * p.ldcf + nb, v, nv, p.vec);
+                    if (p.cf && rvalid) store_f32_row(p.cf + (long long)g * p.cf_gs + (long long)row * p.ldcf + nb, v, nv, p.vec);
+                    if (tout) write_out(c, v);
+                    else if (p.cb && rvalid) store_bf16_row(p.cb + (long long)g * p.cb_gs + (long long)row * p.ldcb + nb, v, nv, p.vec);
                 } else if (EPI == EPI_SIGMOID_MSE) {
-                    if (!rvalid) return;
                     float t[32];
                     if (p.bias) {
                         load_f32_row(p.bias + (long long)g * p.bias_gs + nb, t, nv, p.vec);
 #pragma unroll
                         for (int j = 0; j < 32; ++j) v[j] += t[j];
                     }
-                    load_bf16_row(p.yb + (long long)row * p.ldyb + nb, t, nv, p.vec);       // targets (0 / 1)
-                    const int self = p.g0 + g - nb;                                         // masked column of this net
+                    if (tin) read_in(c, t);                                                 // targets (0 / 1)
+                    else load_bf16_row(p.yb + (long long)(rvalid ? row : 0) * p.ldyb + nb, t, nv, p.vec);
+                    const int self = rvalid ? p.g0 + g - nb : -1;                           // masked column of this net
+                    const int nvr = rvalid ? nv : 0;                                        // rows past the batch count nothing
                     float o[32];
+                    if (nvr == 32 && (unsigned)self >= 32u) {                               // interior chunk: nothing to mask
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        o[j] = sigmoid_fast(v[j]);
-                        float d = o[j] - t[j];
-                        if (j >= nv || j == self) d = 0.f;
-                        sq = fmaf(d, d, sq);
-                        ab += fabsf(d);
-                        const float u = p.gscale * o[j];
-                        v[j] = d * fmaf(-u, o[j], u);                                       // gscale * d * o * (1 - o)
+                        for (int j = 0; j < 32; ++j) {
+                            o[j] = sigmoid_fast(v[j]);
+                            const float d = o[j] - t[j];
+                            sq = fmaf(d, d, sq);
+                            ab += fabsf(d);
+                            const float u = p.gscale * o[j];
+                            v[j] = d * fmaf(-u, o[j], u);                                   // gscale * d * o * (1 - o)
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            o[j] = sigmoid_fast(v[j]);
+                            float d = o[j] - t[j];
+                            if (j >= nvr || j == self) d = 0.f;
+                            sq = fmaf(d, d, sq);
+                            ab += fabsf(d);
+                            const float u = p.gscale * o[j];
+                            v[j] = d * fmaf(-u, o[j], u);
+                        }
                     }
-                    if (p.cb) store_bf16_row(p.cb + (long long)g * p.cb_gs + (long long)row * p.ldcb + nb, v, nv, p.vec);
-                    if (p.cf) store_f32_row(p.cf + (long long)g * p.cf_gs + (long long)row * p.ldcf + nb, o, nv, p.vec);
+                    if (p.cf && rvalid) store_f32_row(p.cf + (long long)g * p.cf_gs + (long long)row * p.ldcf + nb, o, nv, p.vec);
+                    if (tout) write_out(c, v);
+                    else if (p.cb && rvalid) store_bf16_row(p.cb + (long long)g * p.cb_gs + (long long)row * p.ldcb + nb, v, nv, p.vec);
                 } else if (EPI == EPI_DGRAD) {
-                    if (!rvalid) return;
                     float t[32];
-                    if (p.z) {
+                    if (p.z && rvalid) {
                         const long long zo = (long long)g * p.zq_gs + (long long)row * p.ldzq + nb;
                         float qv[32];
                         load_f32_row(p.z + zo, t, nv, p.vec);
@@ -323,8 +481,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                         for (int j = 0; j < 32; ++j) v[j] = fmaf(p.cscale, t[j] - qv[j], v[j]);
                     }
                     if (p.hb || p.hf) {
-                        if (p.hb) load_bf16_row(p.hb + (long long)g * p.hb_gs + (long long)row * p.ldhb + nb, t, nv, p.vec);
-                        else load_f32_row(p.hf + (long long)g * p.hf_gs + (long long)row * p.ldhf + nb, t, nv, p.vec);
+                        if (tin) read_in(c, t);
+                        else if (p.hb) load_bf16_row(p.hb + (long long)g * p.hb_gs + (long long)(rvalid ? row : 0) * p.ldhb + nb, t, nv, p.vec);
+                        else load_f32_row(p.hf + (long long)g * p.hf_gs + (long long)(rvalid ? row : 0) * p.ldhf + nb, t, nv, p.vec);
                         if (p.act == PGMVAE_ACT_SELU) {
 #pragma unroll
                             for (int j = 0; j < 32; ++j) v[j] *= pg_dselu_from_out(t[j]);
@@ -333,8 +492,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                             for (int j = 0; j < 32; ++j) v[j] *= t[j] * (1.0f - t[j]);
                         }
                     }
-                    if (p.cb) store_bf16_row(p.cb + (long long)g * p.cb_gs + (long long)row * p.ldcb + nb, v, nv, p.vec);
-                    if (p.cf) store_f32_row(p.cf + (long long)g * p.cf_gs + (long long)row * p.ldcf + nb, v, nv, p.vec);
+                    if (p.cf && rvalid) store_f32_row(p.cf + (long long)g * p.cf_gs + (long long)row * p.ldcf + nb, v, nv, p.vec);
+                    if (tout) write_out(c, v);
+                    else if (p.cb && rvalid) store_bf16_row(p.cb + (long long)g * p.cb_gs + (long long)row * p.ldcb + nb, v, nv, p.vec);
                 } else if (EPI == EPI_WGRAD_D) {
                     // C[m = in][n = out] -> dW[in][out]: the thread owns (a piece of) a weight row
                     if (!rvalid) return;
@@ -355,24 +515,37 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                     if (!rvalid) return;
                     float* dst = p.dw + (long long)g * p.dw_gs + (long long)nb * p.lddw + row;
                     const int zr = p.zero_row_base + g - nb;
+                    if (p.accum) {
+                        float t[32];
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) t[j] = j < nv ? dst[(long long)j * p.lddw] : 0.f;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] += t[j];
+                    }
 #pragma unroll
                     for (int j = 0; j < 32; ++j)
-                        if (j < nv) {
-                            const float val = j == zr ? 0.f : v[j];
-                            float* d1 = dst + (long long)j * p.lddw;
-                            *d1 = p.accum ? *d1 + val : val;
-                        }
+                        if (j < nv) dst[(long long)j * p.lddw] = j == zr ? 0.f : v[j];
                 }
             };
 
+            if (tin) fetch_in(0);
             tc::mbar_wait(&tmem_full[wg], use & 1);
             tc::fence_after_thread_sync();
             float va[32], vb[32];
+            if (EPI == EPI_WGRAD_T && p.ones && nt == 0) {          // bias gradient of weight column `row` (uniform branch)
+                tc::tmem_ld_32x32(lane_addr + ONES_COL - 16, va);
+                tc::tmem_ld_wait(va);
+                if (rvalid) {
+                    float* d = p.db + (long long)g * p.db_gs + row;
+                    *d = p.accum ? *d + va[16] : va[16];
+                }
+            }
             tc::tmem_ld_32x32(lane_addr, va);
             for (int c = 0; c < nch; c += 2) {
                 tc::tmem_ld_wait(va);
                 if (c + 1 < nch) {
                     tc::tmem_ld_32x32(lane_addr + (c + 1) * 32, vb);
+                    if (tin) fetch_in(c + 1);              // buffer (c + 1) & 1 was last read before the barriers of chunk c - 1
                 } else {                                   // the whole accumulator sits in registers: hand it back
                     tc::fence_before_thread_sync();
                     __syncwarp();
@@ -383,6 +556,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                     tc::tmem_ld_wait(vb);
                     if (c + 2 < nch) {
                         tc::tmem_ld_32x32(lane_addr + (c + 2) * 32, va);
+                        if (tin) fetch_in(c + 2);
                     } else {
                         tc::fence_before_thread_sync();
                         __syncwarp();
@@ -393,6 +567,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             }
             if (EPI == EPI_SIGMOID_MSE) { dsq += (double)sq; dab += (double)ab; }
         }
+        if (tout && leader) tc::bulk_wait_all();           // every store has landed before the CTA gives up its shared memory
         if (EPI == EPI_SIGMOID_MSE) {
             dsq = pg_warp_sum_d(dsq);
             dab = pg_warp_sum_d(dab);
@@ -404,6 +579,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     }
     tc::fence_before_thread_sync();
     __syncthreads();
+    if (p.pair) tc::cluster_sync_all();                   // no CTA leaves while its peer may still signal its barriers
     if (warp == 2) {
         tc::fence_after_thread_sync();
         tc::tmem_dealloc(tmem_base, 512u);
@@ -524,8 +700,46 @@ int launch(pgmvae_ctx* ctx, cudaStream_t st, Bf16P& p, const Operand& A, const O
     p.a_bytes = A_BYTES;
     p.b_panels = (int)pg_cdiv(p.BN, 64);
     p.b_bytes = p.b_mn ? (unsigned)(p.b_panels * PANEL_BYTES) : (unsigned)pg_round_up(p.BN * 128, 1024);
+    // 2-CTA clusters with the shared operand multicast: the main loop is bound by L2 -> SM traffic (ncu: lts 69 %,
+    // tensor pipe 33 % with one CTA per tile), and a pair halves the traffic of the operand it shares.  Pair along M
+    // (neighbouring M tiles share B) or along N (neighbouring N tiles share A), whichever moves fewer bytes per CTA and
+    // k-block; an odd tile count costs a phantom tile, accepted up to 10 % of the work.
+    p.tiles_mp = (int)pg_cdiv(p.tiles_m, 2);
+    p.tiles_np = (int)pg_cdiv(p.tiles_n, 2);
+    p.pair = 0;
+    {
+        const double none = (double)p.a_bytes + p.b_bytes;
+        const double wm = 2.0 * p.tiles_mp / p.tiles_m, wn = 2.0 * p.tiles_np / p.tiles_n;
+        const double cm = wm <= 1.10 ? ((double)p.a_bytes + 0.5 * p.b_bytes) * wm : 1e30;
+        const double cn = wn <= 1.10 ? (0.5 * p.a_bytes + (double)p.b_bytes) * wn : 1e30;
+        if (std::min(cm, cn) < 0.95 * none) p.pair = cm <= cn ? 1 : 2;
+        if (p.total_tiles < 2 * ctx->sm_count) p.pair = 0;          // too little work to fill the machine with pairs anyway
+        if (const char* ev = getenv("PGMVAE_BF16_PAIR")) p.pair = atoi(ev) >= 0 && atoi(ev) <= 2 ? atoi(ev) : p.pair;
+        if (p.pair == 1 && !p.b_mn && (p.BN / 2) % 8) p.pair = 0;   // half tiles must keep whole 8-row swizzle atoms
+    }
+    p.total_ptiles = p.pair == 1 ? p.G * p.tiles_mp * p.tiles_n : (p.pair == 2 ? p.G * p.tiles_m * p.tiles_np : p.total_tiles);
+    // bf16 rows leave (and the epilogue's bf16 operand rows arrive) as staged tiles through TMA: a thread owns a row, so
+    // direct 16-byte accesses touch 32 different lines per warp instruction and the epilogue is bound by LSU wavefronts
+    EpiMaps em;
+    memset(&em, 0, sizeof(em));
+    const __nv_bfloat16* inp = EPI == EPI_SIGMOID_MSE ? p.yb : (EPI == EPI_DGRAD ? p.hb : nullptr);
+    const int ld_in = EPI == EPI_SIGMOID_MSE ? p.ldyb : p.ldhb;
+    const int64_t gs_in = EPI == EPI_SIGMOID_MSE ? 0 : p.hb_gs;
+    const bool epi_rows = EPI == EPI_FWD || EPI == EPI_SIGMOID_MSE || EPI == EPI_DGRAD;
+    p.in_shared = EPI == EPI_SIGMOID_MSE;
+    p.tma_out = epi_rows && p.cb && p.tiles_n <= MAX_NT_MAPS && al16(p.cb) && p.ldcb % 8 == 0 && p.cb_gs % 8 == 0 &&
+                getenv("PGMVAE_BF16_DIRECT_EPI") == nullptr;
+    p.tma_in = p.tma_out && inp && al16(inp) && ld_in % 8 == 0 && gs_in % 8 == 0;
+    for (int nt = 0; nt < p.tiles_n && p.tma_out; ++nt) {
+        const int n0 = nt * p.BN, ncols = std::min(p.BN, p.N - n0);
+        PG_TRY(tc::make_map(&em.out[nt], p.cb + n0, 2, (uint64_t)ncols, (uint64_t)p.M, (uint64_t)p.G, (uint64_t)p.ldcb,
+                            (uint64_t)p.cb_gs, 32, TM, false, true));
+        if (p.tma_in)
+            PG_TRY(tc::make_map(&em.in[nt], inp + n0, 2, (uint64_t)ncols, (uint64_t)p.M, (uint64_t)(p.in_shared ? 1 : p.G),
+                                (uint64_t)ld_in, (uint64_t)gs_in, 32, TM, false, true));
+    }
     const size_t stage = (size_t)A_BYTES + p.b_bytes;
-    const size_t fixed = 1024 + 256;
+    const size_t fixed = 1024 + 256 + (p.tma_out ? 2 * (size_t)STG_WG : 0) + (p.ones ? ONES_BYTES : 0);
     int stages = (int)((ctx->smem_optin - fixed) / stage);
     if (stages > MAX_STAGES) stages = MAX_STAGES;
     if (stages < 2) {
@@ -537,9 +751,11 @@ int launch(pgmvae_ctx* ctx, cudaStream_t st, Bf16P& p, const Operand& A, const O
     size_t smem = fixed + stages * stage;
     if (smem < (size_t)120 * 1024) smem = (size_t)120 * 1024;
     CUtensorMap mA, mB;
-    if (!p.a_mn) PG_TRY(tc::make_map(&mA, A.p, 2, (uint64_t)p.K, (uint64_t)p.M, (uint64_t)p.G, (uint64_t)A.ld, (uint64_t)A.gs, BK, TM));
+    // (a K-major operand shared by a pair is loaded in two half-height boxes, one per CTA)
+    const uint32_t a_box_rows = p.pair == 2 ? TM / 2 : TM, b_box_rows = (uint32_t)(p.pair == 1 ? p.BN / 2 : p.BN);
+    if (!p.a_mn) PG_TRY(tc::make_map(&mA, A.p, 2, (uint64_t)p.K, (uint64_t)p.M, (uint64_t)p.G, (uint64_t)A.ld, (uint64_t)A.gs, BK, a_box_rows));
     else PG_TRY(tc::make_map(&mA, A.p, 2, (uint64_t)p.M, (uint64_t)p.K, (uint64_t)p.G, (uint64_t)A.ld, (uint64_t)A.gs, 64, BK));
-    if (!p.b_mn) PG_TRY(tc::make_map(&mB, B.p, 2, (uint64_t)p.K, (uint64_t)p.N, (uint64_t)p.G, (uint64_t)B.ld, (uint64_t)B.gs, BK, (uint32_t)p.BN));
+    if (!p.b_mn) PG_TRY(tc::make_map(&mB, B.p, 2, (uint64_t)p.K, (uint64_t)p.N, (uint64_t)p.G, (uint64_t)B.ld, (uint64_t)B.gs, BK, b_box_rows));
     else PG_TRY(tc::make_map(&mB, B.p, 2, (uint64_t)p.N, (uint64_t)p.K, (uint64_t)p.G, (uint64_t)B.ld, (uint64_t)B.gs, 64, BK));
     static size_t configured[16] = {};
     const int dev = ctx->device & 15;
@@ -547,9 +763,22 @@ int launch(pgmvae_ctx* ctx, cudaStream_t st, Bf16P& p, const Operand& A, const O
         PG_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured[dev] = smem;
     }
-    const int grid = p.total_tiles < ctx->sm_count ? p.total_tiles : ctx->sm_count;
+    const int csize = p.pair ? 2 : 1;
+    const int nclusters = std::min(p.total_ptiles, ctx->sm_count / csize);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(nclusters * csize));
+    cfg.blockDim = dim3(THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)csize;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
     PG_KERNEL(ctx, st, name, bytes, 2.0 * p.G * (double)p.M * p.N * p.K);
-    gemm_bf16_kernel<EPI><<<grid, THREADS, smem, st>>>(mA, mB, p);
+    PG_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<EPI>, mA, mB, em, p));
     PG_LAUNCHED(ctx);
     return PGMVAE_OK;
 }
@@ -559,9 +788,9 @@ int launch(pgmvae_ctx* ctx, cudaStream_t st, Bf16P& p, const Operand& A, const O
 // ---- internal entry points (ops.cuh) ---------------------------------------------------------------------------
 int pg_bf16_fwd(pgmvae_ctx* ctx, cudaStream_t st, const __nv_bfloat16* x, int64_t x_gs, int ldx, const __nv_bfloat16* wt,
                 int64_t wt_gs, int ldwt, const float* bias, int64_t bias_gs, __nv_bfloat16* outb, int64_t outb_gs, int ldob,
-                float* outf, int64_t outf_gs, int ldof, int G, int B, int in, int out_dim, int act) {
+                float* outf, int64_t outf_gs, int ldof, int G, int B, int in, int out_dim, int act, int w_mn) {
     Bf16P p{};
-    p.G = G; p.M = B; p.N = out_dim; p.K = in;
+    p.G = G; p.M = B; p.N = out_dim; p.K = in; p.b_mn = w_mn ? 1 : 0;
     p.cb = outb; p.cb_gs = outb_gs; p.ldcb = ldob; p.cf = outf; p.cf_gs = outf_gs; p.ldcf = ldof;
     p.bias = bias; p.bias_gs = bias_gs; p.act = act;
     p.vec = (!outb || (al16(outb) && ldob % 8 == 0 && outb_gs % 8 == 0)) &&
@@ -575,9 +804,10 @@ int pg_bf16_fwd(pgmvae_ctx* ctx, cudaStream_t st, const __nv_bfloat16* x, int64_
 int pg_bf16_fwd_sigmoid_mse(pgmvae_ctx* ctx, cudaStream_t st, const __nv_bfloat16* x, int64_t x_gs, int ldx,
                             const __nv_bfloat16* wt, int64_t wt_gs, int ldwt, const float* bias, int64_t bias_gs,
                             const __nv_bfloat16* yb, int ldyb, __nv_bfloat16* dpre, int64_t dpre_gs, int ldd, float* out_opt,
-                            int64_t out_gs, int ldo, double* acc2, int G, int g0, int B, int in, int V, float grad_scale) {
+                            int64_t out_gs, int ldo, double* acc2, int G, int g0, int B, int in, int V, float grad_scale,
+                            int w_mn) {
     Bf16P p{};
-    p.G = G; p.M = B; p.N = V; p.K = in;
+    p.G = G; p.M = B; p.N = V; p.K = in; p.b_mn = w_mn ? 1 : 0;
     p.cb = dpre; p.cb_gs = dpre_gs; p.ldcb = ldd; p.cf = out_opt; p.cf_gs = out_gs; p.ldcf = ldo;
     p.bias = bias; p.bias_gs = bias_gs; p.yb = yb; p.ldyb = ldyb; p.acc = acc2; p.gscale = grad_scale; p.g0 = g0;
     p.vec = (!dpre || (al16(dpre) && ldd % 8 == 0 && dpre_gs % 8 == 0)) && al16(yb) && ldyb % 8 == 0 &&
@@ -605,12 +835,15 @@ int pg_bf16_dgrad(pgmvae_ctx* ctx, cudaStream_t st, const __nv_bfloat16* dy, int
                                  (z ? 8.0 * G * B * in : 0.0));
 }
 
-// dW[in][out] (+)= X^T dY; the orientation that pads less.  db is NOT computed here (pg_bf16_colsum).
+// dW[in][out] (+)= X^T dY in the orientation that pads less, and db[out] (+)= column sums of dY (nullable): through
+// the ones-tile MMA of the transposed orientation where that applies, with the column-sum kernel otherwise.
 int pg_bf16_wgrad(pgmvae_ctx* ctx, cudaStream_t st, const __nv_bfloat16* x, int64_t x_gs, int ldx, const __nv_bfloat16* dy,
-                  int64_t dy_gs, int lddy, float* dw, int64_t dw_gs, int lddw, int G, int B, int in, int out_dim,
-                  int zero_row_base, int accumulate) {
+                  int64_t dy_gs, int lddy, float* dw, int64_t dw_gs, int lddw, float* db, int64_t db_gs, int G, int B, int in,
+                  int out_dim, int zero_row_base, int accumulate) {
     auto padded = [](int m, int n) { return (double)pg_round_up(m, TM) * (double)(pg_cdiv(n, pick_bn(n)) * (pick_bn(n) + 48)); };
-    bool direct = padded(in, out_dim) <= padded(out_dim, in);
+    // the transposed orientation gets the bias gradient for free (ones-tile MMA); the direct one pays a second pass over
+    // dY, worth ~133 padded tile elements per output column at the measured rates of the two kernels
+    bool direct = padded(in, out_dim) + (db ? 133.0 * out_dim : 0.0) < padded(out_dim, in);
     if (const char* ev = getenv("PGMVAE_WGRAD_ORIENT")) direct = ev[0] == 'd' ? true : (ev[0] == 't' ? false : direct);
     Bf16P p{};
     p.G = G; p.K = B; p.a_mn = 1; p.b_mn = 1;
@@ -621,10 +854,16 @@ int pg_bf16_wgrad(pgmvae_ctx* ctx, cudaStream_t st, const __nv_bfloat16* x, int6
     const double bytes = 2.0 * (xg * B * in + (double)G * B * out_dim) + 4.0 * G * (double)in * out_dim;
     if (direct) {
         p.M = in; p.N = out_dim;
-        return launch<EPI_WGRAD_D>(ctx, st, p, Operand{x, x_gs, ldx}, Operand{dy, dy_gs, lddy}, "dense_wgrad_bf16", bytes);
+        PG_TRY(launch<EPI_WGRAD_D>(ctx, st, p, Operand{x, x_gs, ldx}, Operand{dy, dy_gs, lddy}, "dense_wgrad_bf16", bytes));
+        if (db) PG_TRY(pg_bf16_colsum(ctx, st, dy, dy_gs, lddy, db, db_gs, G, B, out_dim, accumulate));
+        return PGMVAE_OK;
     }
     p.M = out_dim; p.N = in;
-    return launch<EPI_WGRAD_T>(ctx, st, p, Operand{dy, dy_gs, lddy}, Operand{x, x_gs, ldx}, "dense_wgrad_bf16", bytes);
+    p.ones = db != nullptr && pick_bn(in) <= ONES_COL - 16 + 16 && getenv("PGMVAE_WGRAD_NO_ONES") == nullptr;
+    p.db = db; p.db_gs = db_gs;
+    PG_TRY(launch<EPI_WGRAD_T>(ctx, st, p, Operand{dy, dy_gs, lddy}, Operand{x, x_gs, ldx}, "dense_wgrad_bf16", bytes));
+    if (db && !p.ones) PG_TRY(pg_bf16_colsum(ctx, st, dy, dy_gs, lddy, db, db_gs, G, B, out_dim, accumulate));
+    return PGMVAE_OK;
 }
 
 int pg_bf16_colsum(pgmvae_ctx* ctx, cudaStream_t st, const __nv_bfloat16* dy, int64_t dy_gs, int lddy, float* db, int64_t db_gs,

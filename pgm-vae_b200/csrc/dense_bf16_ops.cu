@@ -51,16 +51,17 @@ int pg_dense_fwd_bf16(pgmvae_ctx* ctx, cudaStream_t st, const float* x, int64_t 
                       int ldw, const float* bias, int64_t bias_gs, float* out, int64_t out_gs, int ldo, int G, int B, int in,
                       int out_dim, int act) {
     if (G <= 0 || B <= 0) return PGMVAE_OK;
-    const int pin = P8(in), xg = x_gs == 0 ? 1 : G;
-    const size_t nx = (size_t)xg * B * pin, nw = (size_t)G * out_dim * pin;
+    // the weights as the model keeps them: a bf16 copy in the stored [in][out] orientation, read MN-major
+    const int pin = P8(in), po = P8(out_dim), xg = x_gs == 0 ? 1 : G;
+    const size_t nx = (size_t)xg * B * pin, nw = (size_t)G * in * po;
     PG_TRY(ensure(ctx, pad256(nx * 2) + pad256(nw * 2)));
     Carver c{(uint8_t*)ctx->scratch_b};
     __nv_bfloat16* xb = c.take<__nv_bfloat16>(nx);
-    __nv_bfloat16* wt = c.take<__nv_bfloat16>(nw);
+    __nv_bfloat16* wc = c.take<__nv_bfloat16>(nw);
     PG_TRY(pg_f32_to_bf16(ctx, st, x, x_gs, ldx, xb, (int64_t)B * pin, pin, xg, B, in));
-    PG_TRY(pg_bf16_shadow(ctx, st, w, w_gs, ldw, in, out_dim, wt, (int64_t)out_dim * pin, pin, nullptr, 0, 0, G));
-    return pg_bf16_fwd(ctx, st, xb, x_gs == 0 ? 0 : (int64_t)B * pin, pin, wt, (int64_t)out_dim * pin, pin, bias, bias_gs, nullptr,
-                       0, 0, out, out_gs, ldo, G, B, in, out_dim, act);
+    PG_TRY(pg_bf16_shadow(ctx, st, w, w_gs, ldw, in, out_dim, nullptr, 0, 0, wc, (int64_t)in * po, po, G));
+    return pg_bf16_fwd(ctx, st, xb, x_gs == 0 ? 0 : (int64_t)B * pin, pin, wc, (int64_t)in * po, po, bias, bias_gs, nullptr,
+                       0, 0, out, out_gs, ldo, G, B, in, out_dim, act, 1);
 }
 
 int pg_dense_fwd_sigmoid_mse_bf16(pgmvae_ctx* ctx, cudaStream_t st, const float* x, int64_t x_gs, int ldx, const float* w,
@@ -69,7 +70,7 @@ int pg_dense_fwd_sigmoid_mse_bf16(pgmvae_ctx* ctx, cudaStream_t st, const float*
                                   int in, int V, float grad_scale) {
     if (G <= 0 || B <= 0) return PGMVAE_OK;
     const int pin = P8(in), pv = P8(V), xg = x_gs == 0 ? 1 : G;
-    const size_t nx = (size_t)xg * B * pin, nw = (size_t)G * V * pin, ny = (size_t)B * pv, nd = (size_t)G * B * pv;
+    const size_t nx = (size_t)xg * B * pin, nw = (size_t)G * in * pv, ny = (size_t)B * pv, nd = (size_t)G * B * pv;
     PG_TRY(ensure(ctx, pad256(nx * 2) + pad256(nw * 2) + pad256(ny * 2) + pad256(nd * 2)));
     Carver c{(uint8_t*)ctx->scratch_b};
     __nv_bfloat16* xb = c.take<__nv_bfloat16>(nx);
@@ -77,10 +78,10 @@ int pg_dense_fwd_sigmoid_mse_bf16(pgmvae_ctx* ctx, cudaStream_t st, const float*
     __nv_bfloat16* yb = c.take<__nv_bfloat16>(ny);
     __nv_bfloat16* db = c.take<__nv_bfloat16>(nd);
     PG_TRY(pg_f32_to_bf16(ctx, st, x, x_gs, ldx, xb, (int64_t)B * pin, pin, xg, B, in));
-    PG_TRY(pg_bf16_shadow(ctx, st, w, w_gs, ldw, in, V, wt, (int64_t)V * pin, pin, nullptr, 0, 0, G));
+    PG_TRY(pg_bf16_shadow(ctx, st, w, w_gs, ldw, in, V, nullptr, 0, 0, wt, (int64_t)in * pv, pv, G));
     PG_TRY(pg_f32_to_bf16(ctx, st, y, 0, ldy, yb, 0, pv, 1, B, V));
-    PG_TRY(pg_bf16_fwd_sigmoid_mse(ctx, st, xb, x_gs == 0 ? 0 : (int64_t)B * pin, pin, wt, (int64_t)V * pin, pin, bias, bias_gs, yb,
-                                   pv, db, (int64_t)B * pv, pv, out_opt, dpre_gs, ldd, acc2, G, g0, B, in, V, grad_scale));
+    PG_TRY(pg_bf16_fwd_sigmoid_mse(ctx, st, xb, x_gs == 0 ? 0 : (int64_t)B * pin, pin, wt, (int64_t)in * pv, pv, bias, bias_gs, yb,
+                                   pv, db, (int64_t)B * pv, pv, out_opt, dpre_gs, ldd, acc2, G, g0, B, in, V, grad_scale, 1));
     dim3 grid((unsigned)std::min<int64_t>(pg_cdiv((int64_t)B * V, 1024), 2048), (unsigned)G);
     bf16_to_f32_kernel<<<grid, 256, 0, st>>>(db, (long long)B * pv, pv, dpre, dpre_gs, ldd, B, V);
     PG_LAUNCHED(ctx);
@@ -117,8 +118,6 @@ int pg_dense_wgrad_bf16(pgmvae_ctx* ctx, cudaStream_t st, const float* x, int64_
     PG_TRY(pg_f32_to_bf16(ctx, st, x, x_gs, ldx, xb, (int64_t)B * pin, pin, xg, B, in));
     PG_TRY(pg_f32_to_bf16(ctx, st, dy, dy_gs, lddy, dyb, (int64_t)B * po, po, G, B, out_dim));
     // the operator ABI accumulates into dw / db (+=)
-    PG_TRY(pg_bf16_wgrad(ctx, st, xb, x_gs == 0 ? 0 : (int64_t)B * pin, pin, dyb, (int64_t)B * po, po, dw, dw_gs, lddw, G, B, in,
-                         out_dim, zero_row_base, 1));
-    if (db) PG_TRY(pg_bf16_colsum(ctx, st, dyb, (int64_t)B * po, po, db, db_gs, G, B, out_dim, 1));
-    return PGMVAE_OK;
+    return pg_bf16_wgrad(ctx, st, xb, x_gs == 0 ? 0 : (int64_t)B * pin, pin, dyb, (int64_t)B * po, po, dw, dw_gs, lddw, db, db_gs, G,
+                         B, in, out_dim, zero_row_base, 1);
 }

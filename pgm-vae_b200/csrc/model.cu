@@ -195,16 +195,15 @@ struct pgmvae_model {
     cudaStream_t ema_stream = nullptr;
     cudaEvent_t ev_ema_fork = nullptr, ev_ema = nullptr;
     // bf16 tensor-core mode (csrc/dense_bf16.cu): networks too wide for the chain kernels (cfg3).  Operands live in
-    // bf16: the data matrix, every activation / pre-activation gradient of the current variable group, and two
-    // shadows of the weights (wt: transposed [V][out][in] for the forward GEMMs, wc: as stored [V][in][out] for
-    // the dgrad GEMMs), refreshed from the fp32 master weights whenever those change.
+    // bf16: the data matrix, every activation / pre-activation gradient of the current variable group, and a bf16
+    // mirror of the weights in the stored [V][in][out] orientation (K-major operand of the dgrad GEMMs, MN-major
+    // operand of the forward GEMMs), written by the Adam kernel together with the fp32 master weights.
     bool bf16 = false, shadow_dirty = true;
     __nv_bfloat16* yb = nullptr;            // [max_batch][Vp]
     __nv_bfloat16* Hb[10] = {};             // activations (layer 4 = the latent stays fp32 in H[4])
     __nv_bfloat16* Gb[10] = {};             // d(loss)/d(pre-activation)
     __nv_bfloat16* stb = nullptr;           // straight-through output of the VQ layer
-    __nv_bfloat16* wt[10] = {};
-    __nv_bfloat16* wc[10] = {};
+    __nv_bfloat16* wb = nullptr;            // bf16 mirror of the dense parameters, same offsets as `params`
     __nv_bfloat16* cnt_yb = nullptr;
 
     float* E() const { return params + e_off; }
@@ -360,14 +359,11 @@ int upload_batch(pgmvae_model* m, const uint8_t* y, int on_device, int B, const 
     return pgmvae_y_to_f32(m->ctx, st, *y_dev, m->V, m->yf, m->Vp, B, m->V);
 }
 
-// bf16 shadows of the weights, rebuilt from the fp32 master copy when it has changed (Adam, init, set_tensor)
+// bf16 mirror of the weights, rebuilt from the fp32 master copy when that changed outside the optimiser (init,
+// set_tensor); the Adam kernel keeps it current during training
 int refresh_shadows(pgmvae_model* m) {
     if (!m->bf16 || !m->shadow_dirty) return PGMVAE_OK;
-    for (int l = 0; l < 10; ++l) {
-        const Layer& L = m->L[l];
-        PG_TRY(pg_bf16_shadow(m->ctx, m->ctx->stream, m->params + L.w_off, (int64_t)L.pin * L.pout, L.pout, L.in, L.out, m->wt[l],
-                              (int64_t)L.pout * L.pin, L.pin, m->wc[l], (int64_t)L.pin * L.pout, L.pout, m->V));
-    }
+    PG_TRY(pg_flat_to_bf16(m->ctx, m->ctx->stream, m->params, m->wb, (int64_t)m->n_dense));
     m->shadow_dirty = false;
     return PGMVAE_OK;
 }
@@ -474,9 +470,9 @@ int bf16_forward_layers(pgmvae_model* m, int g0, int Gn, int B, int l0, int l1, 
         const __nv_bfloat16* x = l == 0 ? yb : (l == 5 ? m->stb : m->Hb[l - 1]);
         const int ldx = l == 0 ? m->Vp : (l == 5 ? m->Dp : m->L[l - 1].pout);
         const int64_t x_gs = l == 0 ? 0 : MB * ldx;
-        PG_TRY(pg_bf16_fwd(ctx, st, x, x_gs, ldx, m->wt[l] + (size_t)g0 * L.pout * L.pin, (int64_t)L.pout * L.pin, L.pin,
+        PG_TRY(pg_bf16_fwd(ctx, st, x, x_gs, ldx, m->wb + L.w_off + (size_t)g0 * L.pin * L.pout, (int64_t)L.pin * L.pout, L.pout,
                            m->params + L.b_off + (size_t)g0 * L.pout, L.pout, l == 4 ? nullptr : m->Hb[l], MB * L.pout, L.pout,
-                           l == 4 ? m->H[4] : nullptr, MB * L.pout, L.pout, Gn, B, L.in, L.out, L.act));
+                           l == 4 ? m->H[4] : nullptr, MB * L.pout, L.pout, Gn, B, L.in, L.out, L.act, 1));
     }
     return PGMVAE_OK;
 }
@@ -572,6 +568,10 @@ int pgmvae_model_create(pgmvae_ctx* ctx, const int* units4, int nvar, int dim, i
     size_t budget = (size_t)12 << 30;
     if (const char* ev = getenv("PGMVAE_WS_GB")) budget = atof(ev) > 0.0 ? (size_t)(atof(ev) * (double)(1ull << 30)) : budget;
     size_t vg = budget / (per_vb * (size_t)max_batch);
+    // one group = one SM count of variables when the budget allows more: every layer's tile count is then a whole
+    // number of waves of the persistent GEMMs, and under data parallelism more (smaller) groups leave less of the
+    // gradient exchange exposed behind the last one
+    if (vg > (size_t)ctx->sm_count) vg = ctx->sm_count;
     if (const char* ev = getenv("PGMVAE_GROUP_VARS")) vg = atoi(ev) > 0 ? (size_t)atoi(ev) : vg;
     if (vg < 1) vg = 1;
     if (vg > (size_t)nvar) vg = nvar;
@@ -582,9 +582,8 @@ int pgmvae_model_create(pgmvae_ctx* ctx, const int* units4, int nvar, int dim, i
         for (int l = 0; l < 10; ++l) {
             if (l < 9 && l != 4) A((void**)&m->Hb[l], vg * max_batch * m->L[l].pout * 2);
             A((void**)&m->Gb[l], vg * max_batch * m->L[l].pout * 2);
-            A((void**)&m->wt[l], (size_t)nvar * m->L[l].pout * m->L[l].pin * 2);
-            if (l > 0) A((void**)&m->wc[l], (size_t)nvar * m->L[l].pin * m->L[l].pout * 2);
         }
+        A((void**)&m->wb, m->n_dense * 2);
         A((void**)&m->H[4], vg * max_batch * m->Dp * 4);
         A((void**)&m->stb, vg * max_batch * m->Dp * 2);
     } else {
@@ -1017,10 +1016,10 @@ int run_step(pgmvae_model* m, const uint8_t* y, int y_on_device, int B, int glob
         {   // fd9 + loss + d(loss)/d(pre-activation)
             const Layer& L = m->L[9];
             PG_TRY(pg_bf16_fwd_sigmoid_mse(ctx, st, m->Hb[8], MB * m->L[8].pout, m->L[8].pout,
-                                           m->wt[9] + (size_t)g0 * L.pout * L.pin, (int64_t)L.pout * L.pin, L.pin,
+                                           m->wb + L.w_off + (size_t)g0 * L.pin * L.pout, (int64_t)L.pin * L.pout, L.pout,
                                            m->params + L.b_off + (size_t)g0 * L.pout, L.pout, m->yb, m->Vp, m->Gb[9], MB * L.pout,
                                            L.pout, out_dev ? out_dev + (size_t)g0 * MB * L.pout : nullptr, MB * L.pout, L.pout,
-                                           m->acc, Gn, g0, B, L.in, V, gscale));
+                                           m->acc, Gn, g0, B, L.in, V, gscale, 1));
         }
         for (int l = (flags & STEP_FWD_ONLY) ? -1 : 9; l >= 0; --l) {
             const Layer& L = m->L[l];
@@ -1028,14 +1027,12 @@ int run_step(pgmvae_model* m, const uint8_t* y, int y_on_device, int B, int glob
             const int ldx = l == 0 ? m->Vp : (l == 5 ? Dp : m->L[l - 1].pout);
             const int64_t x_gs = l == 0 ? 0 : MB * ldx;
             PG_TRY(pg_bf16_wgrad(ctx, st, x, x_gs, ldx, m->Gb[l], MB * L.pout, L.pout,
-                                 m->grads + L.w_off + (size_t)g0 * L.pin * L.pout, (int64_t)L.pin * L.pout, L.pout, Gn, B, L.in,
-                                 L.out, l == 0 ? g0 : -1, 0));
-            PG_TRY(pg_bf16_colsum(ctx, st, m->Gb[l], MB * L.pout, L.pout, m->grads + L.b_off + (size_t)g0 * L.pout, L.pout, Gn, B,
-                                  L.out, 0));
+                                 m->grads + L.w_off + (size_t)g0 * L.pin * L.pout, (int64_t)L.pin * L.pout, L.pout,
+                                 m->grads + L.b_off + (size_t)g0 * L.pout, L.pout, Gn, B, L.in, L.out, l == 0 ? g0 : -1, 0));
             if (l > 0) {
                 const Layer& P = m->L[l - 1];
                 const bool vqb = (l == 5);
-                PG_TRY(pg_bf16_dgrad(ctx, st, m->Gb[l], MB * L.pout, L.pout, m->wc[l] + (size_t)g0 * L.pin * L.pout,
+                PG_TRY(pg_bf16_dgrad(ctx, st, m->Gb[l], MB * L.pout, L.pout, m->wb + L.w_off + (size_t)g0 * L.pin * L.pout,
                                      (int64_t)L.pin * L.pout, L.pout, vqb ? nullptr : m->Hb[l - 1], MB * P.pout, P.pout,
                                      vqb ? m->H[4] : nullptr, MB * P.pout, P.pout, vqb ? m->H[4] : nullptr, vqb ? m->q : nullptr,
                                      zgs, Dp, cscale, m->Gb[l - 1], MB * P.pout, P.pout, nullptr, 0, 0, Gn, B, L.in, L.out,
@@ -1139,10 +1136,10 @@ int run_step(pgmvae_model* m, const uint8_t* y, int y_on_device, int B, int glob
             p2p_sum_adam_kernel<<<blocks, 256, 0, st>>>(a);
             PG_LAUNCHED(ctx);
         } else {
-            PG_TRY(pgmvae_adam_step(ctx, st, m->params, m->grads, m->adam_m, m->adam_v, (int64_t)trainable, alpha, b1, b2,
-                                    1e-7));
+            PG_TRY(pg_adam_step_shadow(ctx, st, m->params, m->grads, m->adam_m, m->adam_v, (int64_t)trainable, alpha, b1, b2,
+                                       1e-7, m->bf16 ? m->wb : nullptr, (int64_t)m->n_dense));
         }
-        m->shadow_dirty = true;
+        if (use_p2p) m->shadow_dirty = true;          // (the peer-to-peer kernel does not write the bf16 mirror)
     }
     PG_TRY(ema_update(st));
     if (ema_side) PG_CUDA(cudaStreamWaitEvent(st, m->ev_ema, 0));       // later work sees the new codebook

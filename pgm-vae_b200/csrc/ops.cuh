@@ -103,23 +103,24 @@ int pg_chain_launch(pgmvae_ctx* ctx, cudaStream_t st, const PgChainArgs& a);
 bool pg_chain_supported(const int* pin, const int* pout, int nlayers, int Vp, int Dp, int K, size_t smem_optin);
 
 // bf16 tensor-core grouped GEMMs (dense_bf16.cu): persistent tcgen05 kernels on bf16 copies of the operands.
-//   x / dy / h: row-major bf16 activations [G][B][ld];  wt: transposed weight shadow [G][out][ld(in)];
+//   x / dy / h: row-major bf16 activations [G][B][ld];  wt: transposed weight shadow [G][out][ld(in)], or with
+//   w_mn = 1 the shadow AS STORED [G][in][ld(out)] read as an MN-major operand (no transposed copy needed);
 //   w: weight shadow as stored [G][in][ld(out)];  outputs in bf16 and / or fp32 (nullable)
 int pg_bf16_fwd(pgmvae_ctx* ctx, cudaStream_t st, const __nv_bfloat16* x, int64_t x_gs, int ldx, const __nv_bfloat16* wt,
                 int64_t wt_gs, int ldwt, const float* bias, int64_t bias_gs, __nv_bfloat16* outb, int64_t outb_gs, int ldob,
-                float* outf, int64_t outf_gs, int ldof, int G, int B, int in, int out_dim, int act);
+                float* outf, int64_t outf_gs, int ldof, int G, int B, int in, int out_dim, int act, int w_mn = 0);
 int pg_bf16_fwd_sigmoid_mse(pgmvae_ctx* ctx, cudaStream_t st, const __nv_bfloat16* x, int64_t x_gs, int ldx,
                             const __nv_bfloat16* wt, int64_t wt_gs, int ldwt, const float* bias, int64_t bias_gs,
                             const __nv_bfloat16* yb, int ldyb, __nv_bfloat16* dpre, int64_t dpre_gs, int ldd, float* out_opt,
-                            int64_t out_gs, int ldo, double* acc2, int G, int g0, int B, int in, int V, float grad_scale);
+                            int64_t out_gs, int ldo, double* acc2, int G, int g0, int B, int in, int V, float grad_scale, int w_mn = 0);
 int pg_bf16_dgrad(pgmvae_ctx* ctx, cudaStream_t st, const __nv_bfloat16* dy, int64_t dy_gs, int lddy, const __nv_bfloat16* w,
                   int64_t w_gs, int ldw, const __nv_bfloat16* hb, int64_t hb_gs, int ldhb, const float* hf, int64_t hf_gs,
                   int ldhf, const float* z, const float* q, int64_t zq_gs, int ldzq, float cscale, __nv_bfloat16* dxb,
                   int64_t dxb_gs, int lddxb, float* dxf, int64_t dxf_gs, int lddxf, int G, int B, int in, int out_dim,
                   int act_below);
 int pg_bf16_wgrad(pgmvae_ctx* ctx, cudaStream_t st, const __nv_bfloat16* x, int64_t x_gs, int ldx, const __nv_bfloat16* dy,
-                  int64_t dy_gs, int lddy, float* dw, int64_t dw_gs, int lddw, int G, int B, int in, int out_dim,
-                  int zero_row_base, int accumulate);
+                  int64_t dy_gs, int lddy, float* dw, int64_t dw_gs, int lddw, float* db, int64_t db_gs, int G, int B, int in,
+                  int out_dim, int zero_row_base, int accumulate);
 int pg_bf16_colsum(pgmvae_ctx* ctx, cudaStream_t st, const __nv_bfloat16* dy, int64_t dy_gs, int lddy, float* db, int64_t db_gs,
                    int G, int B, int N, int accumulate);
 // operator-level wrappers on fp32 tensors (dense_bf16_ops.cu): same signatures as the tf32 / fp32 flavours
@@ -141,4 +142,7 @@ int pg_f32_to_bf16(pgmvae_ctx* ctx, cudaStream_t st, const float* src, int64_t s
                    int ldd, int G, int rows, int cols);
 int pg_bf16_shadow(pgmvae_ctx* ctx, cudaStream_t st, const float* w, int64_t w_gs, int lds, int rows, int cols,
                    __nv_bfloat16* wt, int64_t t_gs, int ldt, __nv_bfloat16* wc, int64_t c_gs, int ldc, int G);
+int pg_flat_to_bf16(pgmvae_ctx* ctx, cudaStream_t st, const float* src, __nv_bfloat16* dst, int64_t n);
+int pg_adam_step_shadow(pgmvae_ctx* ctx, cudaStream_t stream, float* p, const float* g, float* m, float* v, int64_t n,
+                        float alpha, double b1, double b2, double eps, __nv_bfloat16* wb, int64_t nwb);
 int pg_y_to_bf16(pgmvae_ctx* ctx, cudaStream_t st, const uint8_t* y, int ldy, __nv_bfloat16* out, int ld, int B, int V);

@@ -4,7 +4,10 @@
 //   pll_reduce  float64 log-likelihood reduction      reference core/model.py:93-96
 //   adam_step   Keras Adam (ResourceApplyAdam form)   reference run.py:60
 //   y_to_f32    uint8 data matrix -> fp32 operand     replaces make_xs, reference run.py:46-50
+#include <cuda_bf16.h>
+
 #include "common.cuh"
+#include "ops.cuh"
 
 namespace {
 
@@ -90,9 +93,12 @@ __global__ void __launch_bounds__(256) pll_reduce_kernel(const unsigned long lon
     }
 }
 
+// wb (optional): bf16 mirror of the first nwb parameters (the operand copy of the bf16 tensor-core path), written
+// with the updated values so that no separate conversion pass re-reads the weights
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g,
                                                    float* __restrict__ m, float* __restrict__ v, long long n,
-                                                   float alpha, float omb1, float omb2, float eps) {
+                                                   float alpha, float omb1, float omb2, float eps,
+                                                   __nv_bfloat16* __restrict__ wb, long long nwb) {
     const long long n4 = n >> 2;
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
@@ -109,6 +115,10 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
         reinterpret_cast<float4*>(p)[i] = pp;
         reinterpret_cast<float4*>(m)[i] = mm;
         reinterpret_cast<float4*>(v)[i] = vv;
+        if (wb && (i << 2) + 4 <= nwb) {
+            const __nv_bfloat162 lo = __floats2bfloat162_rn(pp.x, pp.y), hi = __floats2bfloat162_rn(pp.z, pp.w);
+            reinterpret_cast<uint2*>(wb)[i] = make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
+        }
     }
     for (long long i = (n4 << 2) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         float mm = m[i], vv = v[i];
@@ -118,7 +128,20 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
         p[i] -= (mm * alpha) / (sqrtf(vv) + eps);
         m[i] = mm;
         v[i] = vv;
+        if (wb && i < nwb) wb[i] = __float2bfloat16_rn(p[i]);
     }
+}
+
+__global__ void __launch_bounds__(256) flat_to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long n) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long n4 = n >> 2;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        const float4 t = reinterpret_cast<const float4*>(src)[i];
+        const __nv_bfloat162 lo = __floats2bfloat162_rn(t.x, t.y), hi = __floats2bfloat162_rn(t.z, t.w);
+        reinterpret_cast<uint2*>(dst)[i] = make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
+    }
+    for (long long i = (n4 << 2) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        dst[i] = __float2bfloat16_rn(src[i]);
 }
 
 __global__ void y_to_f32_kernel(const uint8_t* __restrict__ y, int ldy, float* __restrict__ out, int ld, int B, int V) {
@@ -193,18 +216,37 @@ int pgmvae_pll_reduce(pgmvae_ctx* ctx, void* stream, const unsigned long long* n
 
 int pgmvae_adam_step(pgmvae_ctx* ctx, void* stream, float* p, const float* g, float* m, float* v, int64_t n,
                      float alpha, double b1, double b2, double eps) {
+    return pg_adam_step_shadow(ctx, pg_stream(ctx, stream), p, g, m, v, n, alpha, b1, b2, eps, nullptr, 0);
+}
+
+}  // extern "C"
+
+int pg_flat_to_bf16(pgmvae_ctx* ctx, cudaStream_t st, const float* src, __nv_bfloat16* dst, int64_t n) {
+    if (n <= 0) return PGMVAE_OK;
+    int blocks = (int)std::min<int64_t>(pg_cdiv(n, 256 * 4 * 4), (int64_t)ctx->sm_count * 8);
+    if (blocks < 1) blocks = 1;
+    PG_KERNEL(ctx, st, "weights_to_bf16", 6.0 * n, 0.0);
+    flat_to_bf16_kernel<<<blocks, 256, 0, st>>>(src, dst, n);
+    PG_LAUNCHED(ctx);
+    return PGMVAE_OK;
+}
+
+int pg_adam_step_shadow(pgmvae_ctx* ctx, cudaStream_t stream, float* p, const float* g, float* m, float* v, int64_t n,
+                        float alpha, double b1, double b2, double eps, __nv_bfloat16* wb, int64_t nwb) {
     PG_CHECK_ARG(ctx && p && g && m && v && n >= 0);
     PG_CHECK_ARG(((uintptr_t)p & 15) == 0 && ((uintptr_t)g & 15) == 0 && ((uintptr_t)m & 15) == 0 &&
                  ((uintptr_t)v & 15) == 0);
     if (n == 0) return PGMVAE_OK;
     int blocks = (int)std::min<int64_t>(pg_cdiv(n, 256 * 4 * 4), (int64_t)ctx->sm_count * 8);
     if (blocks < 1) blocks = 1;
-    PG_KERNEL(ctx, pg_stream(ctx, stream), "adam", 28.0 * n, 10.0 * n);
-    adam_kernel<<<blocks, 256, 0, pg_stream(ctx, stream)>>>(p, g, m, v, n, alpha, (float)(1.0 - b1), (float)(1.0 - b2),
-                                                            (float)eps);
+    PG_KERNEL(ctx, stream, "adam", 28.0 * n + (wb ? 2.0 * nwb : 0.0), 10.0 * n);
+    adam_kernel<<<blocks, 256, 0, stream>>>(p, g, m, v, n, alpha, (float)(1.0 - b1), (float)(1.0 - b2), (float)eps, wb,
+                                            (long long)nwb);
     PG_LAUNCHED(ctx);
     return PGMVAE_OK;
 }
+
+extern "C" {
 
 int pgmvae_y_to_f32(pgmvae_ctx* ctx, void* stream, const uint8_t* y, int ldy, float* out, int ld, int B, int V) {
     PG_CHECK_ARG(ctx && y && out && ld >= V && ldy >= V && B >= 0);

@@ -30,8 +30,9 @@ inline EncodeTiledFn encode_fn() {
 // and group stride gs in ELEMENTS (gs == 0 = one shared matrix); box = [1][box_rows][box_cols]
 // with box_cols * esize = 128 bytes, 128-byte swizzle (16-byte atoms; atom32 = 32-byte atoms, the
 // only layout tcgen05 accepts for MN-major 32-bit operands), out-of-bounds elements read as zero.
+//   sw64 = true: 64-byte swizzle (box_cols * esize = 64 bytes; the epilogue staging tiles of dense_bf16.cu)
 inline int make_map(CUtensorMap* map, const void* base, int esize, uint64_t cols, uint64_t rows, uint64_t groups,
-                    uint64_t ld, uint64_t gs, uint32_t box_cols, uint32_t box_rows, bool atom32 = false) {
+                    uint64_t ld, uint64_t gs, uint32_t box_cols, uint32_t box_rows, bool atom32 = false, bool sw64 = false) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) {
         pgmvae_set_error("cuTensorMapEncodeTiled unavailable");
@@ -49,7 +50,7 @@ inline int make_map(CUtensorMap* map, const void* base, int esize, uint64_t cols
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = fn(map, esize == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, (void*)base,
                     dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                    atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                    sw64 ? CU_TENSOR_MAP_SWIZZLE_64B : (atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B),
                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         pgmvae_set_error("cuTensorMapEncodeTiled failed (%d): cols %llu rows %llu groups %llu ld %llu gs %llu", (int)r,
@@ -137,6 +138,51 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m
             smem_u32(smem_dst)),
         "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
+}
+
+// The same load delivered to the same shared-memory offset of EVERY CTA of the cluster named in cta_mask; each
+// destination CTA's mbarrier (same offset) receives the complete_tx.  One L2 read feeds several SMs.
+__device__ __forceinline__ void tma_load_3d_mc(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
+                                               int c2, uint16_t cta_mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, "
+        "%4, %5}], [%2], %6;" ::"r"(smem_u32(smem_dst)),
+        "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "h"(cta_mask)
+        : "memory");
+}
+// arrive (once all previously issued MMAs of this thread have completed) on the mbarrier at this offset in every CTA
+// of cta_mask: a shared-memory stage that peers multicast into is free when the MMAs of ALL of them have read it
+__device__ __forceinline__ void mma_commit_mc(uint64_t* bar, uint16_t cta_mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                     smem_u32(bar)),
+                 "h"(cta_mask)
+                 : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {      // every thread of every CTA of the cluster
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+// shared -> global tile store (bulk async group); out-of-bounds rows / columns of the box are clipped
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* smem_src, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"((uint64_t)map),
+                 "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all committed bulk stores of this thread have finished READING their shared-memory source
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// generic-proxy writes to shared memory become visible to the async proxy (TMA store source)
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// named barrier among `count` threads (count a multiple of 32); id 0 is __syncthreads
+__device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t count) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
 }
 
 // plain (non-tensor) bulk copy global -> shared, completing on an mbarrier; 16-byte granularity
