@@ -69,6 +69,11 @@ int pgmvae_ctx_sync(pgmvae_ctx* ctx);
 void* pgmvae_ctx_stream(pgmvae_ctx* ctx);
 int pgmvae_ctx_set_precision(pgmvae_ctx* ctx, int prec);
 int pgmvae_ctx_get_precision(pgmvae_ctx* ctx);
+/* Leave n SMs to other work (the NCCL kernels of the data-parallel exchange): the persistent kernels of the
+ * library size their grids to the remaining SMs.  They assign tiles statically, one CTA per SM, so a CTA that
+ * cannot be placed because a communication kernel holds its SM would start only when that kernel ends --
+ * the overlap of exchange and compute needs the room to exist.  n = 0 restores the whole device. */
+int pgmvae_ctx_reserve_sms(pgmvae_ctx* ctx, int n);
 /* number of library kernels launched through this context since creation */
 int64_t pgmvae_ctx_launch_count(pgmvae_ctx* ctx);
 
@@ -298,6 +303,13 @@ int pgmvae_model_count(pgmvae_model* m, const uint8_t* y, int y_on_device, int64
  * PLL scalar crosses ranks (north_star; core/model.py:91-96 is a sum over variables). */
 int pgmvae_model_count_vars(pgmvae_model* m, const uint8_t* y, int y_on_device, int64_t N, int v0, int v1,
                             unsigned long long* n1_host, unsigned long long* n0_host);
+/* The same as a stream of chunks, for data sets larger than host or device memory (run.py:53: the author's TODO):
+ * _begin zeroes the device counters, every _add enqueues the copy (host pointers: cudaMemcpyAsync, truly asynchronous
+ * from pinned memory) and the kernels of one chunk and returns without waiting, _end downloads n1 / n0.  The caller
+ * keeps a chunk's host buffer alive until pgmvae_ctx_sync or _end. */
+int pgmvae_model_count_begin(pgmvae_model* m);
+int pgmvae_model_count_add(pgmvae_model* m, const uint8_t* y, int y_on_device, int64_t N, int v0, int v1);
+int pgmvae_model_count_end(pgmvae_model* m, int v0, int v1, unsigned long long* n1_host, unsigned long long* n0_host);
 /* arithmetic of the model's GEMM-shaped kernels, fixed at creation: 0 = fp32 CUDA cores, 1 = tf32 tcgen05
  * (per-layer or chain kernels), 2 = bf16 tcgen05 (wide networks under PGMVAE_PREC_BF16) */
 int pgmvae_model_arithmetic(pgmvae_model* m);

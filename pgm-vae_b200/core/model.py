@@ -243,10 +243,15 @@ class VqVAE:
         self._ensure_capacity(B)
         L = _ffi.lib()
         if code_only:
-            idx = _ffi.DeviceArray(self.ctx, (self.nvar, B), np.int32, zero=False)
-            _ffi.check(L.pgmvae_model_encode(self._h, y.ctypes.data, 0, B, idx.ptr))
             self.losses = [0.0]
-            return np.eye(self.k, dtype=np.float32)[idx.numpy()]           # one-hot [V,B,K]
+            idx = self.encode(y)
+            if idx.size * self.k * 4 > (2 << 30):
+                raise MemoryError(f"code_only=True returns the reference's one-hot tensor [V,B,K] = {idx.shape + (self.k,)} float32 "
+                                  f"({idx.size * self.k * 4 / 2**30:.1f} GiB); use VqVAE.encode(y) for the codes [V,B] (count / cpt / "
+                                  f"pseudo_log_likelihood never build the one-hot tensor)")
+            out = np.zeros(idx.shape + (self.k,), dtype=np.float32)           # one-hot [V,B,K] (core/quantizer.py:139,159)
+            np.put_along_axis(out, idx[..., None].astype(np.int64), 1.0, axis=-1)
+            return out
         Vp = (self.nvar + 7) // 8 * 8
         out = _ffi.DeviceArray(self.ctx, (self.nvar, self.max_batch, Vp), np.float32, zero=False)
         met = (C.c_double * 4)()
@@ -259,6 +264,16 @@ class VqVAE:
         keep = ~np.eye(V, dtype=bool)
         rec = o.transpose(1, 0, 2)[:, keep].reshape(B, V, V - 1)            # drop column v of net v
         return np.ascontiguousarray(rec)
+
+    def encode(self, inputs) -> np.ndarray:
+        """Codes of every variable's latent, int32 [V,B]: the encoder fd0..fd4 + VQ assignment (what code_only=True
+        computes, core/model.py:48, without materialising the one-hot tensor)."""
+        y = to_y(inputs)
+        B = y.shape[0]
+        self._ensure_capacity(B)
+        idx = _ffi.DeviceArray(self.ctx, (self.nvar, B), np.int32, zero=False)
+        _ffi.check(_ffi.lib().pgmvae_model_encode(self._h, y.ctypes.data, 0, B, idx.ptr))
+        return idx.numpy()
 
     def _call_fts(self, inputs, code_only, fts):
         """Sub-net path (core/model.py:41, ``fts`` branches of every layer): inputs [F,B,V-1]."""
@@ -374,6 +389,49 @@ class VqVAE:
         if self.comm is not None and self.comm.nranks > 1:
             n1, n0 = self.comm.allreduce_u64(n1), self.comm.allreduce_u64(n0)
         return n1.astype(np.float64), n0.astype(np.float64)
+
+    def count_stream(self, chunks, rows_per_chunk: int = 32768, var_range=None):
+        """``count`` over an iterator of chunks y [n_i, V] (``pgmvae.data.iter_binary_csv`` / ``iter_array`` / any
+        generator) for data sets that fit neither host nor device memory (run.py:53, the author's TODO).  A background
+        thread reads / parses the next chunks into pinned host buffers while the device works on the current one;
+        counts accumulate on the device and come back once.  Returns (n1, n0, number of samples)."""
+        from pgmvae.data import PinnedPrefetcher
+        v0, v1 = (0, self.nvar) if var_range is None else (int(var_range[0]), int(var_range[1]))
+        L = _ffi.lib()
+        n1 = np.zeros((self.nvar, self.k), dtype=np.uint64)
+        n0 = np.zeros((self.nvar, self.k), dtype=np.uint64)
+        pf = PinnedPrefetcher(self.ctx, chunks, int(rows_per_chunk), self.nvar)
+        total, in_flight = 0, []
+        try:
+            _ffi.check(L.pgmvae_model_count_begin(self._h))
+            for buf, rows in pf:
+                _ffi.check(L.pgmvae_model_count_add(self._h, buf.ctypes.data, 0, rows, v0, v1))      # asynchronous
+                total += rows
+                in_flight.append(buf)
+                if len(in_flight) >= 2:              # the chunk before the one just enqueued has been consumed
+                    self.ctx.sync()
+                    for b in in_flight:
+                        pf.release(b)
+                    in_flight = []
+            _ffi.check(L.pgmvae_model_count_end(self._h, v0, v1, n1.ctypes.data, n0.ctypes.data))
+        finally:
+            self.ctx.sync()
+            pf.close()
+        if var_range is None and self.comm is not None and self.comm.nranks > 1:
+            n1, n0 = self.comm.allreduce_u64(n1), self.comm.allreduce_u64(n0)
+            total = int(self.comm.allreduce_u64(np.array([total], np.uint64))[0])
+        return n1.astype(np.float64), n0.astype(np.float64), total
+
+    def pseudo_log_likelihood_stream(self, chunks, rows_per_chunk: int = 32768):
+        """``pseudo_log_likelihood`` over an iterator of chunks (see ``count_stream``); ``self.dist`` must hold the CPT."""
+        n1, n0, n = self.count_stream(chunks, rows_per_chunk)
+        ctx, L = self.ctx, _ffi.lib()
+        d1 = _ffi.DeviceArray.from_numpy(ctx, n1.astype(np.uint64))
+        d0 = _ffi.DeviceArray.from_numpy(ctx, n0.astype(np.uint64))
+        dd = _ffi.DeviceArray.from_numpy(ctx, np.ascontiguousarray(self.dist, dtype=np.float64))
+        out = _ffi.DeviceArray(ctx, (1,), np.float64)
+        _ffi.check(L.pgmvae_pll_reduce(ctx.h, None, d1.ptr, d0.ptr, dd.ptr, self.nvar * self.k, out.ptr))
+        return float(out.numpy()[0]) / max(n, 1)
 
     def cpt(self, x, y=None, shard="samples"):
         """p(y=1 | code=k) with additive smoothing (reference core/model.py:85-88).  shard="variables": every rank

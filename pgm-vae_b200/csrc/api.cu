@@ -116,7 +116,7 @@ int pgmvae_ctx_create(int device, pgmvae_ctx** out) {
     }
     pgmvae_ctx* c = new pgmvae_ctx();
     c->device = device;
-    c->sm_count = prop.multiProcessorCount;
+    c->sm_count = c->sm_total = prop.multiProcessorCount;
     c->smem_optin = prop.sharedMemPerBlockOptin;
     PG_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     PG_CUDA(cudaEventCreate(&c->ev0));
@@ -154,6 +154,14 @@ int pgmvae_ctx_set_precision(pgmvae_ctx* ctx, int prec) {
     return PGMVAE_OK;
 }
 int pgmvae_ctx_get_precision(pgmvae_ctx* ctx) { return ctx ? ctx->precision : -1; }
+
+int pgmvae_ctx_reserve_sms(pgmvae_ctx* ctx, int n) {
+    PG_CHECK_ARG(ctx && n >= 0 && n < ctx->sm_total - 1);
+    int left = ctx->sm_total - n;
+    left -= left & 1;                        // whole 2-CTA clusters
+    ctx->sm_count = left;
+    return PGMVAE_OK;
+}
 int64_t pgmvae_ctx_launch_count(pgmvae_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 int pgmvae_malloc(pgmvae_ctx* ctx, size_t bytes, void** dptr) {

@@ -666,10 +666,10 @@ int pg_chain_launch(pgmvae_ctx* ctx, cudaStream_t st, const PgChainArgs& a) {
          chain_kernel<true, PG_CHAIN_TRAIN>}};
     if (a.mode < 0 || a.mode > 3) return PGMVAE_EINVAL;
     const KernelT kern = kernels[exact][a.mode];
-    static size_t configured[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
-    if (smem > configured[exact][a.mode]) {
+    static size_t configured[16][2][4] = {};          // per device: the attribute is set per device
+    if (smem > configured[ctx->device & 15][exact][a.mode]) {
         PG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured[exact][a.mode] = smem;
+        configured[ctx->device & 15][exact][a.mode] = smem;
     }
     const int items = a.G * p.tiles_m;
     const int grid = std::min(items, ctx->sm_count);        // one CTA per SM, nch chains in flight each

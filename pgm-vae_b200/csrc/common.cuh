@@ -21,7 +21,8 @@ struct pgmvae_ctx {
     bool prof_open = false;
     std::vector<pg_prof_rec> prof;
     int device = 0;
-    int sm_count = 148;
+    int sm_count = 148;           // SMs the library's persistent kernels may fill (device SMs minus the reserved ones)
+    int sm_total = 148;
     int precision = PGMVAE_PREC_FP32;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;

@@ -389,10 +389,10 @@ template <int EPI>
 int launch_tc(pgmvae_ctx* ctx, cudaStream_t st, DenseTcP& p, const CUtensorMap& mapA, const CUtensorMap& mapB, int G,
               const char* name, double bytes) {
     const size_t smem = configure_tc<EPI>(p);
-    static size_t configured = 0;
-    if (smem > configured) {
+    static size_t configured[16] = {};          // per device: the attribute is set per device
+    if (smem > configured[ctx->device & 15]) {
         PG_CUDA(cudaFuncSetAttribute(dense_tc_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
+        configured[ctx->device & 15] = smem;
     }
     dim3 grid((unsigned)pg_cdiv(p.N, p.BN), (unsigned)pg_cdiv(p.M, TM), (unsigned)(G * p.S));
     if (grid.y > 65535u || grid.z > 65535u) {
@@ -579,10 +579,10 @@ int pg_dense_wgrad_multi_tc(pgmvae_ctx* ctx, cudaStream_t st, const PgWgradProbl
         pgmvae_set_error("wgrad (multi): grid too large");
         return PGMVAE_EINVAL;
     }
-    static size_t configured = 0;
-    if (smem > configured) {
+    static size_t configured[16] = {};          // per device: the attribute is set per device
+    if (smem > configured[ctx->device & 15]) {
         PG_CUDA(cudaFuncSetAttribute(wgrad_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
+        configured[ctx->device & 15] = smem;
     }
     PG_KERNEL(ctx, st, "dense_wgrad_multi_tc", bytes, flops);
     wgrad_multi_kernel<<<(unsigned)total, 128, smem, st>>>(P);

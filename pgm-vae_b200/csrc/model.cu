@@ -1201,14 +1201,29 @@ int pgmvae_model_count(pgmvae_model* m, const uint8_t* y, int y_on_device, int64
 int pgmvae_model_count_vars(pgmvae_model* m, const uint8_t* y, int y_on_device, int64_t N, int v0, int v1,
                             unsigned long long* n1_host, unsigned long long* n0_host) {
     PG_CHECK_ARG(m && y && n1_host && n0_host && N >= 0);
-    PG_CHECK_ARG(v0 >= 0 && v0 <= v1 && v1 <= m->V);
-    pgmvae_ctx* ctx = m->ctx;
-    cudaStream_t st = ctx->stream;
-    PG_CUDA(cudaSetDevice(ctx->device));
+    PG_TRY(pgmvae_model_count_begin(m));
+    PG_TRY(pgmvae_model_count_add(m, y, y_on_device, N, v0, v1));
+    return pgmvae_model_count_end(m, v0, v1, n1_host, n0_host);
+}
+
+int pgmvae_model_count_begin(pgmvae_model* m) {
+    PG_CHECK_ARG(m != nullptr);
+    PG_TRY(p2p_check(m));
+    cudaStream_t st = m->ctx->stream;
+    PG_CUDA(cudaSetDevice(m->ctx->device));
     const size_t cs = (size_t)m->V * m->K;
     PG_TRY(refresh_shadows(m));
     PG_CUDA(cudaMemsetAsync(m->n1, 0, cs * 8, st));
     PG_CUDA(cudaMemsetAsync(m->n0, 0, cs * 8, st));
+    return PGMVAE_OK;
+}
+
+int pgmvae_model_count_add(pgmvae_model* m, const uint8_t* y, int y_on_device, int64_t N, int v0, int v1) {
+    PG_CHECK_ARG(m && y && N >= 0);
+    PG_CHECK_ARG(v0 >= 0 && v0 <= v1 && v1 <= m->V);
+    pgmvae_ctx* ctx = m->ctx;
+    cudaStream_t st = ctx->stream;
+    PG_CUDA(cudaSetDevice(ctx->device));
     if (use_chain(m) && m->Vg >= m->V && N > m->max_batch && v0 == 0 && v1 == m->V) {
         // slabs of up to 32768 samples per launch: 86 tile triples per variable instead of 11, so the items divide
         // evenly over the SMs, and an eighth of the launches
@@ -1228,7 +1243,7 @@ int pgmvae_model_count_vars(pgmvae_model* m, const uint8_t* y, int y_on_device, 
             PG_TRY(pgmvae_y_to_f32(ctx, st, y_dev, m->V, m->cnt_yf, m->Vp, B, m->V));
             PG_TRY(chain_encode(m, 0, m->V, B, y_dev, m->n1, m->n0, m->cnt_yf));
         }
-        N = 0;                                                   // (the loop below has nothing left to do)
+        return PGMVAE_OK;
     }
     for (int64_t s = 0; s < N; s += m->max_batch) {
         const int B = (int)std::min<int64_t>(m->max_batch, N - s);
@@ -1245,6 +1260,12 @@ int pgmvae_model_count_vars(pgmvae_model* m, const uint8_t* y, int y_on_device, 
                                     m->n0 + (size_t)g0 * m->K, Gn, B, m->K));
         }
     }
+    return PGMVAE_OK;
+}
+
+int pgmvae_model_count_end(pgmvae_model* m, int v0, int v1, unsigned long long* n1_host, unsigned long long* n0_host) {
+    PG_CHECK_ARG(m && n1_host && n0_host && v0 >= 0 && v0 <= v1 && v1 <= m->V);
+    cudaStream_t st = m->ctx->stream;
     const size_t lo = (size_t)v0 * m->K, cnt = (size_t)(v1 - v0) * m->K;
     if (cnt) {
         PG_CUDA(cudaMemcpyAsync(n1_host + lo, m->n1 + lo, cnt * 8, cudaMemcpyDeviceToHost, st));

@@ -177,10 +177,10 @@ int pgmvae_pll_count(pgmvae_ctx* ctx, void* stream, const int32_t* idx, int64_t 
     int rows_per_cta = pg_round_up((int)pg_cdiv(B, splits), PLL_TILE);
     if (rows_per_cta > 32768) rows_per_cta = 32768;
     splits = (int)pg_cdiv(B, rows_per_cta);
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
+    static size_t configured[16] = {};          // per device: the attribute is set per device
+    if (smem > 48 * 1024 && smem > configured[ctx->device & 15]) {
         PG_CUDA(cudaFuncSetAttribute(pll_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
+        configured[ctx->device & 15] = smem;
     }
     dim3 grid((unsigned)splits, (unsigned)vtiles);
     PG_KERNEL(ctx, pg_stream(ctx, stream), "pll_count", (double)G * B * 5.0 + 2.0 * G * K * 8.0, (double)G * B);

@@ -428,10 +428,10 @@ int pg_vq_assign_fp32(pgmvae_ctx* ctx, cudaStream_t st, const float* z, int64_t 
         pgmvae_set_error("vq_assign: embedding dim %d too large for the fp32 kernel", D);
         return PGMVAE_EINVAL;
     }
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
+    static size_t configured[16] = {};          // per device: the attribute is set per device
+    if (smem > 48 * 1024 && smem > configured[ctx->device & 15]) {
         PG_CUDA(cudaFuncSetAttribute(vq_assign_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
+        configured[ctx->device & 15] = smem;
     }
     dim3 grid((unsigned)pg_cdiv(B, VQ_ROWS), (unsigned)G);
     PG_KERNEL(ctx, st, "vq_assign_fp32", 4.0 * ((double)G * B * D + (double)G * K * D + (double)G * B),
@@ -460,11 +460,11 @@ static int scatter_launch(pgmvae_ctx* ctx, cudaStream_t st, const float* z, cons
     PG_KERNEL(ctx, st, MODE == 0 ? "ema_stats_scatter" : "vq_codebook_grad_scatter",
               (double)G * B * (4.0 * D * (MODE == 1 ? 2 : 1) + 4.0) + 4.0 * G * K * (D + 1.0), (double)G * B * D);
     if (use_smem) {
-        static size_t configured[2] = {0, 0};
-        if (smem > 48 * 1024 && smem > configured[MODE]) {
+        static size_t configured[16][2] = {};          // per device
+        if (smem > 48 * 1024 && smem > configured[ctx->device & 15][MODE]) {
             PG_CUDA(cudaFuncSetAttribute(scatter_rows_kernel<MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)smem));
-            configured[MODE] = smem;
+            configured[ctx->device & 15][MODE] = smem;
         }
         scatter_rows_kernel<MODE, true><<<grid, 256, smem, st>>>(z, q, z_gs, ldz, idx, idx_gs, cnt, c_gs, acc, a_gs,
                                                                  lda, scale, B, D, K, rows);

@@ -419,10 +419,10 @@ bool pg_vq_assign_tc_supported(int prec, int D, int K, int ldz, int lde, const f
 
 static int launch_vq_tc(pgmvae_ctx* ctx, cudaStream_t st, const CUtensorMap& mapZ, const CUtensorMap& mapE,
                         const VqTcParams& p, size_t smem, int grid) {
-    static size_t configured = 0;
-    if (smem > configured) {
+    static size_t configured[16] = {};          // per device: the attribute is set per device
+    if (smem > configured[ctx->device & 15]) {
         PG_CUDA(cudaFuncSetAttribute(vq_assign_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
+        configured[ctx->device & 15] = smem;
     }
     vq_assign_tc_kernel<<<grid, 128 + EPI_THREADS, smem, st>>>(mapZ, mapE, p);
     return PGMVAE_OK;

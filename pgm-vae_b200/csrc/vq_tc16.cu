@@ -544,10 +544,10 @@ int launch16(pgmvae_ctx* ctx, cudaStream_t st, const CUtensorMap& mapE, Vq16P& p
         pgmvae_set_error("vq_assign (fp16 tensor core): shared memory %zu exceeds %zu", smem, ctx->smem_optin);
         return PGMVAE_EINVAL;
     }
-    static size_t configured = 0;
-    if (smem > configured) {
+    static size_t configured[16] = {};          // per device: the attribute is set per device
+    if (smem > configured[ctx->device & 15]) {
         PG_CUDA(cudaFuncSetAttribute(vq_assign_f16_kernel<SUB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
+        configured[ctx->device & 15] = smem;
     }
     const int items = p.G * p.tiles_m;
     const int grid = items < ctx->sm_count ? items : ctx->sm_count;

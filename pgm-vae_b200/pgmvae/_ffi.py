@@ -93,6 +93,7 @@ SIGNATURES = {
     "pgmvae_model_p2p_export": (_i, [_vp, _vp]),
     "pgmvae_model_p2p_import": (_i, [_vp, _i, _i, _vp]),
     "pgmvae_model_p2p_disable": (_i, [_vp]),
+    "pgmvae_ctx_reserve_sms": (_i, [_vp, _i]),
     "pgmvae_device_can_access_peer": (_i, [_i, _i, _vp]),
     "pgmvae_model_train_step": (_i, [_vp, _vp, _i, _i, _i, _f, _vp, _i, _vp]),
     "pgmvae_model_forward": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
@@ -100,6 +101,9 @@ SIGNATURES = {
     "pgmvae_model_count": (_i, [_vp, _vp, _i, _i64, _vp, _vp]),
     "pgmvae_model_count_vars": (_i, [_vp, _vp, _i, _i64, _i, _i, _vp, _vp]),
     "pgmvae_model_arithmetic": (_i, [_vp]),
+    "pgmvae_model_count_begin": (_i, [_vp]),
+    "pgmvae_model_count_add": (_i, [_vp, _vp, _i, _i64, _i, _i]),
+    "pgmvae_model_count_end": (_i, [_vp, _i, _i, _vp, _vp]),
     "pgmvae_model_device_bytes": (_i64, [_vp]),
     "pgmvae_model_group_size": (_i, [_vp]),
     "pgmvae_comm_unique_id": (_i, [_vp]),
@@ -183,6 +187,10 @@ class Context:
 
     def get_precision(self) -> int:
         return int(lib().pgmvae_ctx_get_precision(self.h))
+
+    def reserve_sms(self, n: int):
+        """leave n SMs to the communication kernels (data parallel); see pgmvae_ctx_reserve_sms"""
+        check(lib().pgmvae_ctx_reserve_sms(self.h, int(n)))
 
     def profile_begin(self):
         check(lib().pgmvae_ctx_profile_begin(self.h))

@@ -101,6 +101,15 @@ def init_from_env(ctx: _ffi.Context = None):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group(backend="gloo", rank=rank, world_size=world)
     ctx = ctx or _ffi.get_context(int(os.environ.get("LOCAL_RANK", rank)))
+    # The library's persistent kernels fill the SMs they are given with one statically scheduled CTA each, so the
+    # NCCL kernels of the overlapped exchange get SMs of their own: NCCL is held to PGMVAE_COMM_SMS CTAs (default 8;
+    # the 9 GB gradient exchange of cfg3 needs ~160 GB/s to hide under a step) and the compute grids leave that many free.
+    comm_sms = int(os.environ.get("PGMVAE_COMM_SMS", "8"))
+    if comm_sms > 0:
+        os.environ.setdefault("NCCL_MAX_CTAS", str(comm_sms))
+        os.environ.setdefault("NCCL_MIN_CTAS", str(min(comm_sms, 4)))
     box = [Comm.unique_id() if rank == 0 else None]
     dist.broadcast_object_list(box, src=0)
-    return Comm(ctx, rank, world, box[0]), rank, world
+    comm = Comm(ctx, rank, world, box[0])
+    ctx.reserve_sms(max(comm_sms, 0))
+    return comm, rank, world

@@ -212,3 +212,80 @@ def test_gibbs_cmll_matches_oracle(ctx):
     got = m.conditional_marginal_log_likelihood(xt, 3, 10, 2, verbose=False, uniform=source())
     exp = om.conditional_marginal_log_likelihood(xt, 3, 10, 2, verbose=False, uniform=source())
     assert np.isfinite(got) and abs(got - exp) <= 2e-2 * abs(exp), (got, exp)
+
+
+def test_save_load_weights_round_trip(ctx, tmp_path):
+    """VqVAE.save_weights / load_weights (run.py:63 intent): every tensor in the reference layouts + Adam moments,
+    step counter and the EMA debias steps; a model restored from the file continues exactly like the original.
+    The path is used as given or with '.npz' appended (np.savez adds the suffix on its own)."""
+    from core.model import VqVAE, Adam
+    units, V, D, K, B = [15, 14, 13, 12], 16, 4, 32, 128
+    y = O.synthetic_binary(4 * B, V, seed=21)
+    a = VqVAE(units, V, D, K, cost=0.25, decay=0.99, ema=True, seed=3, max_batch=B)
+    a.compile(optimizer=Adam(lr=1e-3))
+    for s in range(2):
+        a.train_on_batch(np.ascontiguousarray(y[s * B:(s + 1) * B]))
+    path = str(tmp_path / "ckpt")                        # no suffix on purpose
+    a.save_weights(path)
+    assert (tmp_path / "ckpt.npz").exists()
+    b = VqVAE(units, V, D, K, cost=0.25, decay=0.99, ema=True, seed=99, max_batch=B)
+    b.compile(optimizer=Adam(lr=1e-3))
+    b.load_weights(path)
+    assert b._adam_t == a._adam_t == 2 and b._ema_steps == a._ema_steps == 2
+    for n in a.tensor_names():
+        np.testing.assert_array_equal(a._get_tensor(n), b._get_tensor(n), err_msg=n)
+    for s in range(2, 4):
+        ma = a.train_on_batch(np.ascontiguousarray(y[s * B:(s + 1) * B]))
+        mb = b.train_on_batch(np.ascontiguousarray(y[s * B:(s + 1) * B]))
+        assert ma == mb, (s, ma, mb)
+    for n in ("fd0.kernel", "fd9.bias", "vq.embeddings", "vq.ema_w", "vq.ema_cluster_size"):
+        np.testing.assert_array_equal(a._get_tensor(n), b._get_tensor(n), err_msg=n)
+
+
+def test_encode_equals_code_only_one_hot(ctx):
+    from core.model import VqVAE
+    units, V, D, K, B = [15, 14, 13, 12], 16, 4, 32, 77
+    y = O.synthetic_binary(B, V, seed=5)
+    m = VqVAE(units, V, D, K, seed=1, max_batch=B)
+    idx = m.encode(y)
+    oh = m(y, code_only=True)
+    assert oh.shape == (V, B, K) and np.array_equal(oh.argmax(-1), idx) and np.all(oh.sum(-1) == 1.0)
+
+
+def test_tf_crosscheck_export(ctx, tmp_path):
+    """tools/tf_crosscheck.py export: the file a TensorFlow install needs to run the unmodified reference on the same
+    weights and batches (the check mode itself needs TensorFlow and is not run here)."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = tmp_path / "case.npz"
+    r = subprocess.run([sys.executable, os.path.join(root, "pgm-vae_b200", "tools", "tf_crosscheck.py"), "export", str(out),
+                        "--steps", "2", "--eval", "500"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    z = np.load(out)
+    for k in ("init.fd0.kernel", "init.vq.embeddings", "final.fd9.bias", "final.vq.ema_w", "y_train", "metrics", "eval.idx",
+              "eval.n1", "eval.dist", "eval.pll"):
+        assert k in z.files, k
+    assert z["init.fd0.kernel"].shape == (16, 15, 15) and z["metrics"].shape == (2, 4) and z["eval.idx"].shape == (16, 500)
+
+
+def test_count_stream_equals_count(ctx, tmp_path):
+    """Stage 2 over a stream of chunks (a CSV file read in pieces by a background thread into pinned buffers, and an
+    in-memory iterator) equals stage 2 over the whole array: exactly, the counts are integers."""
+    from core.model import VqVAE
+    from pgmvae import data
+    units, V, D, K, B = [15, 14, 13, 12], 16, 4, 32, 256
+    y = O.synthetic_binary(5000, V, seed=8)
+    path = tmp_path / "toy.train.data"
+    with open(path, "w") as f:
+        for row in y:
+            f.write(",".join(str(int(t)) for t in row) + "\n")
+    chunks = list(data.iter_binary_csv(str(path), 700, nvar=V))
+    assert sum(len(c) for c in chunks) == len(y) and np.array_equal(np.concatenate(chunks), y)
+    m = VqVAE(units, V, D, K, seed=2, max_batch=B)
+    n1, n0 = m.count(y)
+    for it in (data.iter_binary_csv(str(path), 700, nvar=V), data.iter_array(y, 1234)):
+        s1, s0, n = m.count_stream(it, rows_per_chunk=512)
+        assert n == len(y) and np.array_equal(s1, n1) and np.array_equal(s0, n0)
+    m.dist = (n1 + 0.8) / (n1 + n0 + 1.6)
+    assert abs(m.pseudo_log_likelihood_stream(data.iter_array(y, 999), 512) - m.pseudo_log_likelihood(y)) < 1e-12

@@ -182,3 +182,14 @@ def test_gibbs_cmll_known_answer():
     from core.model import _gibbs_cmll
     assert _gibbs_cmll(lambda xs, fts: np.ones(xs.shape[:2], np.float32), x, 2, 3, 1,
                        lambda sh: np.zeros(sh, np.float32)) == got
+
+
+def test_tf_crosscheck_make_xs_matches_run_py():
+    """tools/tf_crosscheck.py builds the reference's leave-one-out inputs in numpy; same tensor as run.py:46-50."""
+    import importlib.util
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("tf_crosscheck", os.path.join(root, "pgm-vae_b200", "tools", "tf_crosscheck.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    y = O.synthetic_binary(9, 7, seed=3)
+    np.testing.assert_array_equal(mod.make_xs_np(y), O.make_xs(y).numpy())
