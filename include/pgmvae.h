@@ -310,6 +310,16 @@ int pgmvae_model_count_vars(pgmvae_model* m, const uint8_t* y, int y_on_device, 
 int pgmvae_model_count_begin(pgmvae_model* m);
 int pgmvae_model_count_add(pgmvae_model* m, const uint8_t* y, int y_on_device, int64_t N, int v0, int v1);
 int pgmvae_model_count_end(pgmvae_model* m, int v0, int v1, unsigned long long* n1_host, unsigned long long* n0_host);
+/* Sub-net path (reference `fts` branches: core/dense.py:104-105, core/quantizer.py:134, core/model.py:41-48): codes of the
+ * networks fts[f] on inputs x_exp [F][B][V] float32 (HOST; expanded over all V data columns, column fts[f] of block f is
+ * ignored), idx_host [F][B] int32.  The weights are read in place on the device through a per-group network index. */
+int pgmvae_model_fts_encode(pgmvae_model* m, const float* x_exp_host, const int32_t* fts_host, int F, int B,
+                            int32_t* idx_host);
+/* VqVAE.conditional_marginal_log_likelihood (core/model.py:110-148; run.py:74) with the block-Gibbs sampler resident on
+ * the device: x [B][V] uint8 and dist [V][K] float64 on the HOST; uniform_host (nullable) injects the U[0,1) draws
+ * [num_smp * p1][blocks][B] float32, otherwise a counter-based generator seeded with `seed` draws them on the device. */
+int pgmvae_model_gibbs_cmll(pgmvae_model* m, const uint8_t* x_host, int B, int p1, int num_smp, int burn_in,
+                            const double* dist_host, uint64_t seed, const float* uniform_host, double* cmll_out);
 /* arithmetic of the model's GEMM-shaped kernels, fixed at creation: 0 = fp32 CUDA cores, 1 = tf32 tcgen05
  * (per-layer or chain kernels), 2 = bf16 tcgen05 (wide networks under PGMVAE_PREC_BF16) */
 int pgmvae_model_arithmetic(pgmvae_model* m);

@@ -276,16 +276,32 @@ class VqVAE:
         return idx.numpy()
 
     def _call_fts(self, inputs, code_only, fts):
-        """Sub-net path (core/model.py:41, ``fts`` branches of every layer): inputs [F,B,V-1]."""
+        """Sub-net path (core/model.py:41, ``fts`` branches of every layer): inputs [F,B,V-1].  code_only (what
+        ``get_probability`` and the Gibbs sampler use) runs on the device against the model's weights in place
+        (``pgmvae_model_fts_encode``): one launch per layer for ALL selected networks, no weight copies."""
+        fts = np.asarray(fts, dtype=np.int32).reshape(-1)
+        if code_only:
+            x = _ffi.as_host_f32(inputs.numpy() if isinstance(inputs, _ffi.DeviceArray) else inputs)
+            F, B, vm1 = x.shape
+            if vm1 != self.nvar - 1 or F != len(fts):
+                raise ValueError(f"expected inputs [len(fts), B, V-1], got {x.shape}")
+            # expanded over all V data columns: net v ignores column v (its weight row is zero), so any value will do there
+            xe = np.zeros((F, B, self.nvar), np.float32)
+            for f, v in enumerate(fts):
+                xe[f, :, :v] = x[f, :, :v]
+                xe[f, :, v + 1:] = x[f, :, v:]
+            idx = np.empty((F, B), np.int32)
+            _ffi.check(_ffi.lib().pgmvae_model_fts_encode(self._h, xe.ctypes.data, np.ascontiguousarray(fts).ctypes.data, F, B,
+                                                          idx.ctypes.data))
+            self.losses = [0.0]
+            return idx
         x = inputs
         for i in range(5):
             x = self._layers[i](x, fts=fts)
-        x = self.vq_layer(x, training=None, code_only=code_only, fts=fts)
-        if not code_only:
-            for i in range(5, 10):
-                x = self._layers[i](x, fts=fts)
-            x = x.numpy()
-        return x
+        x = self.vq_layer(x, training=None, code_only=False, fts=fts)
+        for i in range(5, 10):
+            x = self._layers[i](x, fts=fts)
+        return x.numpy()
 
     # ---- training ------------------------------------------------------------------
     def compile(self, optimizer=None, loss="mse", metrics=None):
@@ -472,14 +488,28 @@ class VqVAE:
         prb = self.dist[fts].astype(np.float32)
         return np.take_along_axis(prb, enc_idx, axis=1)
 
-    def conditional_marginal_log_likelihood(self, x, p1, num_smp, burn_in, verbose=True, uniform=None):
+    def conditional_marginal_log_likelihood(self, x, p1, num_smp, burn_in, verbose=False, uniform=None, seed=None):
         """Conditional marginal log-likelihood by block Gibbs sampling (reference core/model.py:110-148; intended
-        call at run.py:74: ``p1=n_var//10, num_smp=3000, burn_in=150``).  Every sweep step evaluates the selected
-        sub-nets on the device (``get_probability`` -> fts path of every layer + VQ assignment); the sampler state
-        lives on the host.  ``uniform(shape)`` supplies the U[0,1) draws (default: numpy generator seeded by run.py's
-        ``np.random.seed``); the reference's tf.random stream cannot be reproduced without TensorFlow."""
-        uni = uniform if uniform is not None else (lambda shape: np.random.random_sample(shape).astype(np.float32))
-        return _gibbs_cmll(self.get_probability, to_y_float(x), p1, num_smp, burn_in, uni, verbose)
+        call at run.py:74: ``p1=n_var//10, num_smp=3000, burn_in=150``).  The sampler runs ON THE DEVICE
+        (``pgmvae_model_gibbs_cmll``): state, counters and the sub-net evaluation of every step stay in HBM, the host only
+        enqueues launches.  ``uniform(shape)`` injects the U[0,1) draws step by step (parity runs: the reference's
+        tf.random stream cannot be reproduced without TensorFlow); otherwise a counter-based generator on the device
+        is seeded with ``seed`` (default: drawn from numpy's global generator, which run.py seeds)."""
+        data = to_y(x)
+        B, V = data.shape
+        blocks = -(-V // int(p1))
+        steps = int(num_smp) * int(p1)
+        uni = None
+        if uniform is not None:
+            uni = np.ascontiguousarray(np.stack([np.asarray(uniform((blocks, B)), dtype=np.float32) for _ in range(steps)]))
+        if seed is None:
+            seed = int(np.random.randint(0, 2 ** 31 - 1))
+        out = C.c_double(0.0)
+        dist = np.ascontiguousarray(self.dist, dtype=np.float64)
+        _ffi.check(_ffi.lib().pgmvae_model_gibbs_cmll(self._h, data.ctypes.data, B, int(p1), int(num_smp), int(burn_in),
+                                                      dist.ctypes.data, C.c_uint64(seed),
+                                                      uni.ctypes.data if uni is not None else None, C.byref(out)))
+        return float(out.value)
 
     def device_bytes(self) -> int:
         return int(_ffi.lib().pgmvae_model_device_bytes(self._h))
@@ -513,35 +543,3 @@ class VqVAE:
 def to_y_float(x):
     """[B,V] data as float32 (accepts uint8 / float arrays)."""
     return np.ascontiguousarray(np.asarray(x), dtype=np.float32)
-
-
-def _gibbs_cmll(get_probability, x, p1, num_smp, burn_in, uniform, verbose=False):
-    """Block Gibbs sampler of the reference (core/model.py:110-148), framework-free.
-
-    get_probability(xs [F,B,V-1], fts [F]) -> p(y=1) [F,B];  uniform(shape) -> U[0,1) draws (the reference uses
-    tf.random.uniform, whose stream cannot be reproduced without TensorFlow; parity runs inject the draws).
-    Keeps the reference's quirks: the counter starts at i > burn_in * p1 (strict), every block sweeps its own
-    variables with period vol[b], and the last block's denominator is valid * p1 // vol[-1]."""
-    x = np.asarray(x, dtype=np.float32)
-    batch_size, dim = x.shape
-    blocks = int(np.ceil(dim / p1))                                        # :123
-    vol = np.array([p1] * (blocks - 1) + [dim - p1 * (blocks - 1)])        # :124
-    marker = np.arange(blocks) * p1                                        # :126
-    state = np.tile(x[None], (blocks, 1, 1))                               # :127
-    cnt = np.zeros_like(x)                                                 # :128
-    for i in range(num_smp * p1):                                          # :132
-        y = marker + np.mod(i, vol)                                        # :133
-        xs = np.stack([np.delete(state[b], y[b], axis=1) for b in range(blocks)])   # :134-136
-        prb = np.asarray(get_probability(xs, y), dtype=np.float32)         # :137
-        gibbs = (np.asarray(uniform((blocks, batch_size)), dtype=np.float32) < prb).astype(np.float32)   # :138
-        for b in range(blocks):
-            state[b, :, y[b]] = gibbs[b]                                   # :139
-            if i > burn_in * p1:
-                cnt[:, y[b]] += gibbs[b]                                   # :140-141
-        if verbose:
-            print(f"# of samples: {i // p1}, component: {y[0]}")
-    valid = num_smp - burn_in                                              # :146
-    valid_end = np.float32(valid * p1) // np.float32(vol[-1])              # :147
-    den = np.concatenate([np.full(dim - vol[-1], valid, np.float32), np.full(vol[-1], valid_end, np.float32)])
-    cmll = cnt / den[None, :]                                              # :148
-    return float(np.sum(x * np.log(cmll + 1e-5) + (1 - x) * np.log(1 - cmll + 1e-5)) / batch_size)   # :149

@@ -130,7 +130,6 @@ int pgmvae_ctx_destroy(pgmvae_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     if (ctx->scratch) cudaFree(ctx->scratch);
-    if (ctx->scratch_sort) cudaFree(ctx->scratch_sort);
     if (ctx->scratch_b) cudaFree(ctx->scratch_b);
     cudaEventDestroy(ctx->ev0);
     cudaEventDestroy(ctx->ev1);

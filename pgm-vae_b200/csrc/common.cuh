@@ -30,8 +30,6 @@ struct pgmvae_ctx {
     size_t smem_optin = 0;
     void* scratch = nullptr;      // grown on demand by the tensor-core kernels
     size_t scratch_bytes = 0;
-    void* scratch_sort = nullptr; // counting sort of the sorted scatter (vq.cu), grown on demand
-    size_t scratch_sort_bytes = 0;
     size_t vq_cnt_off = 0;
     void* scratch_b = nullptr;    // bf16 operand copies of the operator-level bf16 entry points (dense_bf16_ops.cu)
     size_t scratch_b_bytes = 0;

@@ -33,6 +33,9 @@ struct GemmP {
     const float* z; const float* q; long long zq_gs; int ldzq; float cscale;
     // EPI_WGRAD
     float* db; long long db_gs; int ones_row; int zero_row_base;
+    // weight indirection (reference core/dense.py:104-105, tf.gather(self.kernel, fts)): group g multiplies by the weights
+    // (and adds the bias) of network gidx[g]; null = identity
+    const int* gidx;
 };
 
 template <int ALAY, int BLAY, int EPI>
@@ -48,7 +51,8 @@ __global__ void __launch_bounds__(256) gemm_grouped_kernel(const GemmP p) {
     const int kbeg = s * p.kchunk;
     const int kend = min(p.K, kbeg + p.kchunk);
     const float* __restrict__ A = p.A + (long long)g * p.a_gs;
-    const float* __restrict__ Bm = p.B + (long long)g * p.b_gs;
+    const int wg = p.gidx ? __ldg(p.gidx + g) : g;
+    const float* __restrict__ Bm = p.B + (long long)wg * p.b_gs;
     const int Mext = p.M + ((EPI == EPI_WGRAD) ? p.ones_row : 0);
 
     float acc[8][4];
@@ -190,7 +194,7 @@ __global__ void __launch_bounds__(256) gemm_grouped_kernel(const GemmP p) {
         if (p.bias) {
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-                if (gn0 + j < p.N) bv[j] = __ldg(p.bias + (long long)g * p.bias_gs + gn0 + j);
+                if (gn0 + j < p.N) bv[j] = __ldg(p.bias + (long long)wg * p.bias_gs + gn0 + j);
         }
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -219,7 +223,7 @@ __global__ void __launch_bounds__(256) gemm_grouped_kernel(const GemmP p) {
         if (p.bias) {
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-                if (gn0 + j < p.N) bv[j] = __ldg(p.bias + (long long)g * p.bias_gs + gn0 + j);
+                if (gn0 + j < p.N) bv[j] = __ldg(p.bias + (long long)wg * p.bias_gs + gn0 + j);
         }
         float sq = 0.f, ab = 0.f;
 #pragma unroll
@@ -329,8 +333,9 @@ int launch(pgmvae_ctx* ctx, cudaStream_t st, GemmP& p, int G, int Mtiles_dim, co
 
 int pg_dense_fwd_fp32(pgmvae_ctx* ctx, cudaStream_t stream, const float* x, int64_t x_gs, int ldx,
                           const float* w, int64_t w_gs, int ldw, const float* bias, int64_t bias_gs,
-                          float* out, int64_t out_gs, int ldo, int G, int B, int in, int out_dim, int act) {
+                          float* out, int64_t out_gs, int ldo, int G, int B, int in, int out_dim, int act, const int* gidx) {
     GemmP p{};
+    p.gidx = gidx;
     p.A = x; p.a_gs = x_gs; p.lda = ldx;
     p.B = w; p.b_gs = w_gs; p.ldb = ldw;
     p.C = out; p.c_gs = out_gs; p.ldc = ldo;

@@ -503,6 +503,26 @@ int encode_group(pgmvae_model* m, int g0, int Gn, int B, const __nv_bfloat16* yb
 
 }  // namespace
 
+// read-only view for gibbs.cu (the sub-net path reads the weights in place)
+struct PgModelView {
+    pgmvae_ctx* ctx;
+    int V, Vp, D, Dp, K;
+    const float* params;
+    const float* E;
+    struct { int in, out, pin, pout; size_t w_off, b_off; } L[5];
+};
+int pg_model_view(pgmvae_model* m, PgModelView* v) {
+    PG_CHECK_ARG(m && v);
+    PG_TRY(p2p_check(m));
+    v->ctx = m->ctx; v->V = m->V; v->Vp = m->Vp; v->D = m->D; v->Dp = m->Dp; v->K = m->K;
+    v->params = m->params; v->E = m->E();
+    for (int l = 0; l < 5; ++l) {
+        v->L[l].in = m->L[l].in; v->L[l].out = m->L[l].out; v->L[l].pin = m->L[l].pin; v->L[l].pout = m->L[l].pout;
+        v->L[l].w_off = m->L[l].w_off; v->L[l].b_off = m->L[l].b_off;
+    }
+    return PGMVAE_OK;
+}
+
 extern "C" {
 
 int pgmvae_model_create(pgmvae_ctx* ctx, const int* units4, int nvar, int dim, int k, double cost, double decay,

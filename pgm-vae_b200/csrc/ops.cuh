@@ -7,7 +7,7 @@
 // exact-fp32 CUDA-core kernels (dense_simt.cu, vq.cu)
 int pg_dense_fwd_fp32(pgmvae_ctx* ctx, cudaStream_t st, const float* x, int64_t x_gs, int ldx, const float* w,
                       int64_t w_gs, int ldw, const float* bias, int64_t bias_gs, float* out, int64_t out_gs, int ldo,
-                      int G, int B, int in, int out_dim, int act);
+                      int G, int B, int in, int out_dim, int act, const int* gidx = nullptr);
 int pg_dense_fwd_sigmoid_mse_fp32(pgmvae_ctx* ctx, cudaStream_t st, const float* x, int64_t x_gs, int ldx,
                                   const float* w, int64_t w_gs, int ldw, const float* bias, int64_t bias_gs,
                                   const float* y, int ldy, float* dpre, int64_t dpre_gs, int ldd, float* out_opt,
@@ -21,7 +21,7 @@ int pg_dense_wgrad_fp32(pgmvae_ctx* ctx, cudaStream_t st, const float* x, int64_
                         int B, int in, int out_dim, int zero_row_base);
 int pg_vq_assign_fp32(pgmvae_ctx* ctx, cudaStream_t st, const float* z, int64_t z_gs, int ldz, const float* e,
                       int64_t e_gs, int lde, int32_t* idx, int64_t idx_gs, float* best_opt, float* gap_opt, int G,
-                      int B, int D, int K);
+                      int B, int D, int K, const int* gidx = nullptr);
 
 // tcgen05 tensor-core kernels (vq_tc.cu, dense_tc.cu)
 bool pg_vq_assign_tc_supported(int prec, int D, int K, int ldz, int lde, const float* z, const float* e, int64_t z_gs,

@@ -21,7 +21,7 @@ constexpr int VQ_KC = 64;      // codes staged per chunk
 __global__ void __launch_bounds__(VQ_ROWS) vq_assign_kernel(
     const float* __restrict__ z, long long z_gs, int ldz, const float* __restrict__ e, long long e_gs, int lde,
     int32_t* __restrict__ idx, long long idx_gs, float* __restrict__ best_out, float* __restrict__ gap_out,
-    int B, int D, int K) {
+    int B, int D, int K, const int* __restrict__ gidx) {
     extern __shared__ __align__(16) float smem[];
     float* zs = smem;
     float* es = zs + (size_t)D * VQ_ROWS;
@@ -29,7 +29,7 @@ __global__ void __launch_bounds__(VQ_ROWS) vq_assign_kernel(
     const int g = blockIdx.y, t = threadIdx.x;
     const int b0 = blockIdx.x * VQ_ROWS;
     const float* zg = z + (long long)g * z_gs;
-    const float* eg = e + (long long)g * e_gs;
+    const float* eg = e + (long long)(gidx ? __ldg(gidx + g) : g) * e_gs;        // codebook of network gidx[g] (fts path)
 
     // stage the z tile transposed: zs[d][row]
     for (int i = t; i < VQ_ROWS * D; i += VQ_ROWS) {
@@ -182,128 +182,10 @@ __global__ void __launch_bounds__(256) scatter_rows_vec_kernel(
     }
 }
 
-// ---- sorted scatter (opt-in: PGMVAE_SCATTER_SORTED=1; written after the GPU budget of round 1 was spent, NOT yet run
-// on hardware).  The direct scatter above is bound by the reduction rate of L2 (one RED per 16 bytes of every row).
-// With many rows per code (cfg4: 512 on average) the rows are first ordered by code -- a counting sort of the row
-// indices, three light passes over idx -- and a warp then walks a run of the order, sums rows of the same code in
-// registers and issues one RED per code change: HBM reads of z (random 16*LPR-byte rows) become the bound.
-__global__ void __launch_bounds__(256) sc_hist_kernel(const int32_t* __restrict__ idx, long long idx_gs, int B, int K,
-                                                      int* __restrict__ hist) {
-    const int g = blockIdx.y;
-    const int32_t* ig = idx + (long long)g * idx_gs;
-    int* hg = hist + (long long)g * K;
-    for (long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x; b < B; b += (long long)gridDim.x * blockDim.x) {
-        const int k = ig[b];
-        if (k >= 0 && k < K) atomicAdd(&hg[k], 1);
-    }
-}
-// one CTA per variable: exclusive scan of the histogram -> first position of every code (cursor), counts += histogram
-__global__ void __launch_bounds__(1024) sc_scan_kernel(const int* __restrict__ hist, int* __restrict__ cursor,
-                                                       float* __restrict__ cnt, long long c_gs, int K) {
-    __shared__ int part[32];
-    __shared__ int carry_s;
-    const int g = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int* hg = hist + (long long)g * K;
-    int* cg = cursor + (long long)g * K;
-    if (threadIdx.x == 0) carry_s = 0;
-    __syncthreads();
-    for (int k0 = 0; k0 < K; k0 += 1024) {
-        const int k = k0 + threadIdx.x;
-        const int h = k < K ? hg[k] : 0;
-        int incl = h;                                           // inclusive scan inside the warp
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int t = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += t;
-        }
-        if (lane == 31) part[warp] = incl;
-        __syncthreads();
-        if (warp == 0) {
-            int p = part[lane];
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int t = __shfl_up_sync(0xffffffffu, p, o);
-                if (lane >= o) p += t;
-            }
-            part[lane] = p;                                     // inclusive over the warps
-        }
-        __syncthreads();
-        const int base = carry_s + (warp ? part[warp - 1] : 0);
-        if (k < K) {
-            cg[k] = base + incl - h;
-            if (cnt && h) cnt[(long long)g * c_gs + k] += (float)h;
-        }
-        __syncthreads();
-        if (threadIdx.x == 1023) carry_s = base + incl;
-        __syncthreads();
-    }
-}
-__global__ void __launch_bounds__(256) sc_fill_kernel(const int32_t* __restrict__ idx, long long idx_gs, int B, int K,
-                                                      int* __restrict__ cursor, int2* __restrict__ order) {
-    const int g = blockIdx.y;
-    const int32_t* ig = idx + (long long)g * idx_gs;
-    int* cg = cursor + (long long)g * K;
-    int2* og = order + (long long)g * B;
-    for (long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x; b < B; b += (long long)gridDim.x * blockDim.x) {
-        const int k = ig[b];
-        if (k >= 0 && k < K) og[atomicAdd(&cg[k], 1)] = make_int2((int)b, k);
-    }
-}
-// A warp walks RUN consecutive positions of the order, rpw = 32 / LPR rows per request (lane group `sub` takes
-// every rpw-th position), SCATTER_UNROLL requests in flight; rows of one code are summed in registers.
-template <int MODE>
-__global__ void __launch_bounds__(256) sc_sum_kernel(
-    const float* __restrict__ z, const float* __restrict__ q, long long z_gs, int ldz, const int2* __restrict__ order,
-    const int* __restrict__ total, float* __restrict__ acc, long long a_gs, int lda, float scale, int B, int K, int D4,
-    int LPR, int run) {
-    const int g = blockIdx.y;
-    const int lane = threadIdx.x & 31;
-    const int sub = lane / LPR, l = lane - sub * LPR;
-    const int rpw = 32 / LPR;
-    const long long warp_id = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
-    const float* zg = z + (long long)g * z_gs;
-    const float* qg = q ? q + (long long)g * z_gs : nullptr;
-    const int2* og = order + (long long)g * B;
-    float* ag = acc + (long long)g * a_gs;
-    const int n = total[(long long)g * K + K - 1];             // rows with a valid code = end of the last code's range
-    for (long long p0 = warp_id * run; p0 < n; p0 += nwarps * run) {
-        const long long p1 = p0 + run < n ? p0 + run : n;
-        float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
-        int cur = -1;
-        for (long long pb = p0 + sub; pb < p1; pb += (long long)rpw * SCATTER_UNROLL) {
-            float4 v[SCATTER_UNROLL];
-            int k[SCATTER_UNROLL];
-#pragma unroll
-            for (int u = 0; u < SCATTER_UNROLL; ++u) {
-                const long long pos = pb + (long long)u * rpw;
-                k[u] = -1;
-                if (pos < p1 && l < D4) {
-                    const int2 e = og[pos];
-                    k[u] = e.y;
-                    v[u] = *reinterpret_cast<const float4*>(zg + (long long)e.x * ldz + 4 * l);
-                    if (MODE == 1) {
-                        const float4 qq = *reinterpret_cast<const float4*>(qg + (long long)e.x * ldz + 4 * l);
-                        v[u] = make_float4(scale * (qq.x - v[u].x), scale * (qq.y - v[u].y), scale * (qq.z - v[u].z),
-                                           scale * (qq.w - v[u].w));
-                    }
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < SCATTER_UNROLL; ++u) {
-                if (k[u] < 0) continue;
-                if (k[u] != cur) {
-                    if (cur >= 0) red_add_v4(ag + (long long)cur * lda + 4 * l, sum);
-                    cur = k[u];
-                    sum = v[u];
-                } else {
-                    sum.x += v[u].x; sum.y += v[u].y; sum.z += v[u].z; sum.w += v[u].w;
-                }
-            }
-        }
-        if (cur >= 0) red_add_v4(ag + (long long)cur * lda + 4 * l, sum);
-    }
-}
+// (A counting sort of the rows by code in front of the scatter, so that runs of one code are summed in registers, was
+// built and measured in round 2 at the cfg4 shape: 2.67 TB/s against the 3.50 TB/s of the direct vector reductions
+// above -- the three extra passes over idx and the random 256-byte row reads cost more than the L2 reductions they
+// save -- and was removed again.)
 
 template <int MODE, bool SMEM>
 __global__ void __launch_bounds__(256) scatter_rows_kernel(
@@ -421,7 +303,7 @@ __global__ void __launch_bounds__(256) ema_apply_kernel(
 
 int pg_vq_assign_fp32(pgmvae_ctx* ctx, cudaStream_t st, const float* z, int64_t z_gs, int ldz, const float* e,
                       int64_t e_gs, int lde, int32_t* idx, int64_t idx_gs, float* best_opt, float* gap_opt, int G,
-                      int B, int D, int K) {
+                      int B, int D, int K, const int* gidx) {
     if (G <= 0 || B <= 0) return PGMVAE_OK;
     const size_t smem = ((size_t)D * VQ_ROWS + (size_t)D * VQ_KC + VQ_KC) * sizeof(float);
     if (smem > ctx->smem_optin) {
@@ -436,7 +318,7 @@ int pg_vq_assign_fp32(pgmvae_ctx* ctx, cudaStream_t st, const float* z, int64_t 
     dim3 grid((unsigned)pg_cdiv(B, VQ_ROWS), (unsigned)G);
     PG_KERNEL(ctx, st, "vq_assign_fp32", 4.0 * ((double)G * B * D + (double)G * K * D + (double)G * B),
               2.0 * G * B * (double)D * K);
-    vq_assign_kernel<<<grid, VQ_ROWS, smem, st>>>(z, z_gs, ldz, e, e_gs, lde, idx, idx_gs, best_opt, gap_opt, B, D, K);
+    vq_assign_kernel<<<grid, VQ_ROWS, smem, st>>>(z, z_gs, ldz, e, e_gs, lde, idx, idx_gs, best_opt, gap_opt, B, D, K, gidx);
     PG_LAUNCHED(ctx);
     return PGMVAE_OK;
 }
@@ -468,30 +350,6 @@ static int scatter_launch(pgmvae_ctx* ctx, cudaStream_t st, const float* z, cons
         }
         scatter_rows_kernel<MODE, true><<<grid, 256, smem, st>>>(z, q, z_gs, ldz, idx, idx_gs, cnt, c_gs, acc, a_gs,
                                                                  lda, scale, B, D, K, rows);
-    } else if (vec_ok && getenv("PGMVAE_SCATTER_SORTED") != nullptr && (int64_t)B >= 16 * (int64_t)K) {
-        // opt-in, see sc_*_kernel: order the rows by code, then sum runs in registers
-        int lpr = 1;
-        while (lpr < D / 4) lpr <<= 1;
-        const size_t need = ((size_t)2 * G * K) * sizeof(int) + (size_t)G * B * sizeof(int2) + 256;
-        if (ctx->scratch_sort_bytes < need) {
-            if (ctx->scratch_sort) { PG_CUDA(cudaStreamSynchronize(st)); PG_CUDA(cudaFree(ctx->scratch_sort)); }
-            ctx->scratch_sort = nullptr; ctx->scratch_sort_bytes = 0;
-            PG_CUDA(cudaMalloc(&ctx->scratch_sort, need));
-            ctx->scratch_sort_bytes = need;
-        }
-        int* hist = (int*)ctx->scratch_sort;
-        int* cursor = hist + (size_t)G * K;
-        int2* order = (int2*)(((uintptr_t)(cursor + (size_t)G * K) + 15) & ~(uintptr_t)15);
-        PG_CUDA(cudaMemsetAsync(hist, 0, (size_t)G * K * sizeof(int), st));
-        dim3 lgrid((unsigned)std::min<int64_t>(pg_cdiv(B, 256 * 8), ctx->sm_count * 8), (unsigned)G);
-        sc_hist_kernel<<<lgrid, 256, 0, st>>>(idx, idx_gs, B, K, hist);
-        sc_scan_kernel<<<G, 1024, 0, st>>>(hist, cursor, MODE == 0 ? cnt : nullptr, c_gs, K);
-        sc_fill_kernel<<<lgrid, 256, 0, st>>>(idx, idx_gs, B, K, cursor, order);
-        // after the fill, cursor[k] is the END of code k's range: cursor[K - 1] = number of rows with a valid code
-        dim3 sgrid((unsigned)(ctx->sm_count * 8), (unsigned)G);
-        sc_sum_kernel<MODE><<<sgrid, 256, 0, st>>>(z, q, z_gs, ldz, order, cursor, acc, a_gs, lda, scale, B, K, D / 4, lpr,
-                                                   256);
-        ctx->launches += 3;
     } else if (vec_ok) {
         int lpr = 1;
         while (lpr < D / 4) lpr <<= 1;                       // lanes per row: power of two >= D / 4

@@ -101,6 +101,8 @@ SIGNATURES = {
     "pgmvae_model_count": (_i, [_vp, _vp, _i, _i64, _vp, _vp]),
     "pgmvae_model_count_vars": (_i, [_vp, _vp, _i, _i64, _i, _i, _vp, _vp]),
     "pgmvae_model_arithmetic": (_i, [_vp]),
+    "pgmvae_model_fts_encode": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
+    "pgmvae_model_gibbs_cmll": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, C.c_uint64, _vp, _vp]),
     "pgmvae_model_count_begin": (_i, [_vp]),
     "pgmvae_model_count_add": (_i, [_vp, _vp, _i, _i64, _i, _i]),
     "pgmvae_model_count_end": (_i, [_vp, _i, _i, _vp, _vp]),

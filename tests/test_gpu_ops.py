@@ -178,27 +178,6 @@ def test_ema_stats_scatter(ctx, G, B, D, K):
     np.testing.assert_allclose(dw.numpy(), w.numpy().transpose(0, 2, 1), rtol=1e-4, atol=2e-4)
 
 
-@pytest.mark.skipif(os.environ.get("PGMVAE_TEST_EXPERIMENTAL") != "1",
-                    reason="sorted scatter: written after the GPU budget of round 1 was spent, not yet run on hardware")
-@pytest.mark.parametrize("G,B,D,K", [(1, 300000, 64, 8192), (2, 70000, 16, 2100), (1, 200000, 128, 4096)])
-def test_ema_stats_sorted_scatter(ctx, monkeypatch, G, B, D, K):
-    """PGMVAE_SCATTER_SORTED=1: counting sort of the rows by code + register sums per run (codebooks beyond shared
-    memory, >= 16 rows per code) against the oracle, incl. skewed usage and codes that never occur."""
-    from pgmvae import _ffi
-    monkeypatch.setenv("PGMVAE_SCATTER_SORTED", "1")
-    rng = np.random.default_rng(G + B)
-    z = rng.standard_normal((G, B, D)).astype(np.float32)
-    idx = rng.integers(0, K - 7, (G, B)).astype(np.int32)      # the last seven codes stay empty
-    idx[:, : B // 3] = idx[:, :1]
-    dz, di = _ffi.DeviceArray.from_numpy(ctx, z), _ffi.DeviceArray.from_numpy(ctx, idx)
-    cnt, dw = _ffi.DeviceArray(ctx, (G, K)), _ffi.DeviceArray(ctx, (G, K, D))
-    _ffi.check(_ffi.lib().pgmvae_ema_stats(ctx.h, None, dz.ptr, B * D, D, di.ptr, B, cnt.ptr, K, dw.ptr, K * D, D,
-                                           G, B, D, K))
-    c, w = O.ema_stats(z, idx, K)
-    np.testing.assert_array_equal(cnt.numpy(), c.numpy())
-    np.testing.assert_allclose(dw.numpy(), w.numpy().transpose(0, 2, 1), rtol=1e-4, atol=2e-3)
-
-
 @pytest.mark.parametrize("V,B,K", [(16, 1000, 32), (69, 5000, 128), (3, 7, 512), (40, 2049, 8)])
 def test_pll_count_cpt_reduce(ctx, V, B, K):
     from pgmvae import _ffi
