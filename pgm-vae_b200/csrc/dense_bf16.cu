@@ -56,7 +56,9 @@ enum { EPI_FWD = 0, EPI_SIGMOID_MSE = 1, EPI_DGRAD = 2, EPI_WGRAD_D = 3, EPI_WGR
 struct Bf16P {
     int G, M, N, K, BN, tiles_m, tiles_n, kblocks, stages, total_tiles;
     int a_mn, b_mn, a_shared, b_shared, b_panels;
-    int pair, total_ptiles, tiles_mp, tiles_np;           // 2-CTA clusters: 0 none, 1 pair along M (B multicast), 2 pair along N (A multicast)
+    int pair, total_ptiles, tiles_mp, tiles_np;           // 2-CTA clusters: 0 none, 1 pair along M (B multicast), 2 pair along N (A multicast),
+                                                          // 3 pair along M with ONE cta_group::2 MMA over both SMs (each holds half of B),
+                                                          // 4 cluster of 2 x 2 tiles: A multicast along N, B multicast along M
     unsigned a_bytes, b_bytes;
     int vec;                                              // rows allow 16-byte vector access
     int tma_out, tma_in, in_shared;                       // bf16 output / epilogue operand move through staged TMA tiles
@@ -163,13 +165,20 @@ constexpr int STG_WG = 3 * STG_TILE;   // per epilogue warpgroup: out | in[0] | 
 // neighbouring N tiles of one M tile (pair == 2: they share the A tile).  Tiles past the edge are phantoms: their
 // loads are zero-filled and nothing of them is stored, but they keep the pair in lock step.
 __device__ __forceinline__ void decode_tile(const Bf16P& p, int pt, int crank, int& g, int& mt, int& nt) {
-    if (p.pair == 1) {
+    if (p.pair == 1 || p.pair == 3) {
         const int per_g = p.tiles_mp * p.tiles_n;
         g = pt / per_g;
         const int r = pt - g * per_g;
         const int mtp = r / p.tiles_n;
         nt = r - mtp * p.tiles_n;
         mt = 2 * mtp + crank;
+    } else if (p.pair == 4) {
+        const int per_g = p.tiles_mp * p.tiles_np;
+        g = pt / per_g;
+        const int r = pt - g * per_g;
+        const int mtp = r / p.tiles_np;
+        mt = 2 * mtp + (crank >> 1);
+        nt = 2 * (r - mtp * p.tiles_np) + (crank & 1);
     } else if (p.pair == 2) {
         const int per_g = p.tiles_m * p.tiles_np;
         g = pt / per_g;
@@ -185,7 +194,9 @@ __device__ __forceinline__ void decode_tile(const Bf16P& p, int pt, int crank, i
     }
 }
 
-template <int EPI>
+// CTA2: the instantiation that contains the cta_group::2 instructions (pair == 3).  It is a separate kernel because a
+// kernel holding such instructions can only be launched as clusters of CTA pairs ("cluster misconfiguration" otherwise).
+template <int EPI, bool CTA2>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                  const __grid_constant__ EpiMaps em, const __grid_constant__ Bf16P p) {
@@ -211,19 +222,26 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < MAX_STAGES; ++s) {
-            tc::mbar_init(&full[s], 1);
-            tc::mbar_init(&empty[s], p.pair ? 2 : 1);      // pairs: a stage is free when BOTH CTAs' MMAs have read it
+            // multicast pairs: a stage is free when BOTH CTAs' MMAs have read it.  cta_group::2: the leader's full barrier
+            // collects the producers of both CTAs, and its one MMA stream frees the stage in both.
+            tc::mbar_init(&full[s], CTA2 ? 2 : 1);
+            tc::mbar_init(&empty[s], p.pair == 4 ? 3 : ((p.pair == 1 || p.pair == 2) ? 2 : 1));
         }
         for (int b = 0; b < 2; ++b) {
             tc::mbar_init(&tmem_full[b], 1);
-            tc::mbar_init(&tmem_empty[b], 4);      // one arrival per warp of the warpgroup
+            tc::mbar_init(&tmem_empty[b], CTA2 ? 8 : 4);      // one arrival per warp of the warpgroup (of both CTAs)
         }
         for (int b = 0; b < 4; ++b) tc::mbar_init(&in_full[b], 1);
         tc::fence_barrier_init();
     }
     if (warp == 2) {
-        tc::tmem_alloc(tmem_slot, 512u);
-        tc::tmem_relinquish();
+        if (CTA2) {
+            tc::tmem_alloc_2sm(tmem_slot, 512u);
+            tc::tmem_relinquish_2sm();
+        } else {
+            tc::tmem_alloc(tmem_slot, 512u);
+            tc::tmem_relinquish();
+        }
     }
     if (EPI == EPI_WGRAD_T && p.ones && warp == 3) {
         // B tile of ones: D2[m][0..16) += A[m][k] * 1 leaves sum_k A[m][k] -- the bias gradient when A = dY^T -- in
@@ -238,7 +256,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     tc::fence_after_thread_sync();
     const uint32_t tmem_base = *tmem_slot;
     const int crank = p.pair ? (int)tc::cluster_ctarank() : 0;
-    const int csize = p.pair ? 2 : 1;
+    const int csize = p.pair == 4 ? 4 : (p.pair ? 2 : 1);
+    // who shares which operand with this CTA (multicast masks over cluster ranks).  2 x 2 cluster: rank = 2 rm + rn
+    const int rm = p.pair == 4 ? crank >> 1 : (p.pair == 1 ? crank : 0);       // position along M = which half of B this CTA loads
+    const int rn = p.pair == 4 ? crank & 1 : (p.pair == 2 ? crank : 0);        // position along N = which half of A this CTA loads
+    const uint16_t a_mask = p.pair == 4 ? (uint16_t)(3u << (2 * rm)) : 3;      // CTAs with the same M tile
+    const uint16_t b_mask = p.pair == 4 ? (uint16_t)(5u << rn) : 3;            // CTAs with the same N tile
+    const bool share_a = p.pair == 2 || p.pair == 4, share_b = p.pair == 1 || p.pair == 4;
     const int cid = (int)blockIdx.x / csize, ncl = (int)gridDim.x / csize;
 
     if (warp == 0) {
@@ -247,8 +271,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         // pairs: this CTA loads ITS HALF of the shared operand and multicasts it into both CTAs (rows of a K-major
         // tile, 64-wide panels of an MN-major one); every CTA still receives -- and expects -- the whole stage
         const int a_rows_half = TM / 2, b_rows_half = p.BN / 2;
-        const int bp0 = p.pair == 1 ? (crank == 0 ? 0 : (p.b_panels + 1) / 2) : 0;
-        const int bp1 = p.pair == 1 ? (crank == 0 ? (p.b_panels + 1) / 2 : p.b_panels) : p.b_panels;
+        const int bp0 = share_b ? (rm == 0 ? 0 : (p.b_panels + 1) / 2) : 0;
+        const int bp1 = share_b ? (rm == 0 ? (p.b_panels + 1) / 2 : p.b_panels) : p.b_panels;
         uint32_t s = 0, ph = 0;
         for (int pt = cid; pt < p.total_ptiles; pt += ncl) {
             int g, mt, nt;
@@ -257,29 +281,55 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             const int ga = p.a_shared ? 0 : g, gb = p.b_shared ? 0 : g;
             for (int kb = 0; kb < p.kblocks; ++kb) {
                 tc::mbar_wait(&empty[s], ph ^ 1);
+                if (CTA2) {
+                    // cta_group::2: own A tile and own HALF of the B tile into own shared memory; the bytes of both CTAs
+                    // complete on the leader's barrier, which the leader arms for both
+                    if (tc::elect_one()) {
+                        if (crank == 0) tc::mbar_arrive_expect_tx(&full[s], 2 * stage_tx);
+                        else tc::mbar_arrive_cluster(&full[s], 0);
+                        uint8_t* a_dst = sA + (size_t)s * A_BYTES;
+                        uint8_t* b_dst = sB + (size_t)s * p.b_bytes;
+                        if (!p.a_mn) {
+                            tc::tma_load_3d_2sm(a_dst, &mapA, &full[s], kb * BK, m0, ga);
+                        } else {
+                            tc::tma_load_3d_2sm(a_dst, &mapA, &full[s], m0, kb * BK, ga);
+                            tc::tma_load_3d_2sm(a_dst + PANEL_BYTES, &mapA, &full[s], m0 + 64, kb * BK, ga);
+                        }
+                        const int nh = n0 + crank * (p.BN / 2);
+                        if (!p.b_mn) {
+                            tc::tma_load_3d_2sm(b_dst, &mapB, &full[s], kb * BK, nh, gb);             // [BN/2 n][64 k]
+                        } else {
+                            for (int pn = 0; pn < p.b_panels; ++pn)                                     // panels of the half
+                                tc::tma_load_3d_2sm(b_dst + (size_t)pn * PANEL_BYTES, &mapB, &full[s], nh + pn * 64, kb * BK, gb);
+                        }
+                    }
+                    __syncwarp();
+                    if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1; }
+                    continue;
+                }
                 if (tc::elect_one()) {
                     tc::mbar_arrive_expect_tx(&full[s], stage_tx);
                     uint8_t* a_dst = sA + (size_t)s * A_BYTES;
                     uint8_t* b_dst = sB + (size_t)s * p.b_bytes;
-                    if (p.pair == 2) {                     // A shared by the pair
+                    if (share_a) {                         // A shared along N: this CTA loads half rn for all of them
                         if (!p.a_mn)
-                            tc::tma_load_3d_mc(a_dst + crank * a_rows_half * 128, &mapA, &full[s], kb * BK, m0 + crank * a_rows_half,
-                                               ga, 3);
+                            tc::tma_load_3d_mc(a_dst + rn * a_rows_half * 128, &mapA, &full[s], kb * BK, m0 + rn * a_rows_half, ga,
+                                               a_mask);
                         else
-                            tc::tma_load_3d_mc(a_dst + crank * PANEL_BYTES, &mapA, &full[s], m0 + crank * 64, kb * BK, ga, 3);
+                            tc::tma_load_3d_mc(a_dst + rn * PANEL_BYTES, &mapA, &full[s], m0 + rn * 64, kb * BK, ga, a_mask);
                     } else if (!p.a_mn) {
                         tc::tma_load_3d(a_dst, &mapA, &full[s], kb * BK, m0, ga);                   // [128 m][64 k]
                     } else {
                         tc::tma_load_3d(a_dst, &mapA, &full[s], m0, kb * BK, ga);                   // 2 panels [64 k][64 m]
                         tc::tma_load_3d(a_dst + PANEL_BYTES, &mapA, &full[s], m0 + 64, kb * BK, ga);
                     }
-                    if (p.pair == 1) {                     // B shared by the pair
+                    if (share_b) {                         // B shared along M: this CTA loads half rm for all of them
                         if (!p.b_mn) {
-                            tc::tma_load_3d_mc(b_dst + crank * b_rows_half * 128, &mapB, &full[s], kb * BK, n0 + crank * b_rows_half,
-                                               gb, 3);
+                            tc::tma_load_3d_mc(b_dst + rm * b_rows_half * 128, &mapB, &full[s], kb * BK, n0 + rm * b_rows_half, gb,
+                                               b_mask);
                         } else {
                             for (int pn = bp0; pn < bp1; ++pn)
-                                tc::tma_load_3d_mc(b_dst + (size_t)pn * PANEL_BYTES, &mapB, &full[s], n0 + pn * 64, kb * BK, gb, 3);
+                                tc::tma_load_3d_mc(b_dst + (size_t)pn * PANEL_BYTES, &mapB, &full[s], n0 + pn * 64, kb * BK, gb, b_mask);
                         }
                     } else if (!p.b_mn) {
                         tc::tma_load_3d(b_dst, &mapB, &full[s], kb * BK, n0, gb);                   // [BN n][64 k]
@@ -294,7 +344,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         }
     } else if (warp == 1) {
         // ===================== MMA issuer (warp-uniform loop, one elected lane issues) =====================
-        const uint32_t idesc = tc::make_idesc(1, TM, p.BN, p.a_mn, p.b_mn);
+        const uint32_t idesc = tc::make_idesc(1, CTA2 ? 2 * TM : TM, p.BN, p.a_mn, p.b_mn);
         // K-major : rows of 128 B along k, 8-row atoms 1024 B apart (SBO); one MMA (k = 16) advances 32 B
         // MN-major: panels [64 k][128 B along m/n], 8-k atoms 1024 B apart (SBO), panels PANEL_BYTES apart
         //           (LBO); one MMA (k = 16) advances two atoms = 2048 B
@@ -304,10 +354,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                                     : tc::make_smem_desc(tc::smem_u32(sB), 16, 1024, 2);
         const uint32_t a_step = (p.a_mn ? 2048u : 32u) >> 4, b_step = (p.b_mn ? 2048u : 32u) >> 4;
         const uint32_t a_stage = (uint32_t)A_BYTES >> 4, b_stage = p.b_bytes >> 4;
-        const uint32_t idesc1 = tc::make_idesc(1, TM, 16, p.a_mn, 0);
+        const uint32_t idesc1 = tc::make_idesc(1, CTA2 ? 2 * TM : TM, 16, p.a_mn, 0);
         const uint64_t dOnes = tc::make_smem_desc(tc::smem_u32(sOnes), 16, 1024, 2);
         uint32_t s = 0, ph = 0, it = 0;
-        for (int pt = cid; pt < p.total_ptiles; pt += ncl, ++it) {
+        for (int pt = cid; pt < p.total_ptiles && !(CTA2 && crank != 0); pt += ncl, ++it) {     // cta_group::2: the leader issues for both
             const uint32_t buf = it & 1, use = it >> 1;
             int g, mt, nt;
             decode_tile(p, pt, crank, g, mt, nt);
@@ -318,6 +368,26 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             for (int kb = 0; kb < p.kblocks; ++kb) {
                 tc::mbar_wait(&full[s], ph);
                 tc::fence_after_thread_sync();
+                if (CTA2) {
+                    if (tc::elect_one()) {
+                        const uint64_t dA = dA0 + (uint64_t)(s * a_stage), dB = dB0 + (uint64_t)(s * b_stage);
+#pragma unroll
+                        for (int k4 = 0; k4 < 4; ++k4)
+                            tc::mma_f16_2sm(d_tmem, dA + (uint64_t)(k4 * a_step), dB + (uint64_t)(k4 * b_step), idesc,
+                                            (kb > 0 || k4 > 0) ? 1u : 0u);
+                        if (ones) {
+#pragma unroll
+                            for (int k4 = 0; k4 < 4; ++k4)
+                                tc::mma_f16_2sm(d_tmem + ONES_COL, dA + (uint64_t)(k4 * a_step), dOnes + (uint64_t)(k4 * 2), idesc1,
+                                                (kb > 0 || k4 > 0) ? 1u : 0u);
+                        }
+                        tc::mma_commit_2sm(&empty[s], 3);                                   // frees the stage in both CTAs
+                        if (kb == p.kblocks - 1) tc::mma_commit_2sm(&tmem_full[buf], 3);   // both CTAs' epilogues
+                    }
+                    __syncwarp();
+                    if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1; }
+                    continue;
+                }
                 if (tc::elect_one()) {
                     const uint64_t dA = dA0 + (uint64_t)(s * a_stage), dB = dB0 + (uint64_t)(s * b_stage);
 #pragma unroll
@@ -330,7 +400,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                             tc::mma_f16(d_tmem + ONES_COL, dA + (uint64_t)(k4 * a_step), dOnes + (uint64_t)(k4 * 2), idesc1,
                                         (kb > 0 || k4 > 0) ? 1u : 0u);
                     }
-                    if (p.pair) tc::mma_commit_mc(&empty[s], 3);
+                    if (p.pair) tc::mma_commit_mc(&empty[s], p.pair == 4 ? (uint16_t)(a_mask | b_mask) : (uint16_t)3);
                     else tc::mma_commit(&empty[s]);
                     if (kb == p.kblocks - 1) tc::mma_commit(&tmem_full[buf]);
                 }
@@ -353,6 +423,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         uint32_t in_uses[2] = {0u, 0u};
         const bool tin = p.tma_in != 0, tout = p.tma_out != 0;
         double dsq = 0.0, dab = 0.0;
+        // hand an accumulator buffer back to the MMA issuer: under cta_group::2 that is the leader CTA's warp 1 for both CTAs
+        auto release_acc = [&]() {
+            if (CTA2) tc::mbar_arrive_cluster(&tmem_empty[wg], 0);
+            else tc::mbar_arrive(&tmem_empty[wg]);
+        };
         uint32_t it = 0;
         for (int pt = cid; pt < p.total_ptiles; pt += ncl, ++it) {
             if ((int)(it & 1) != wg) continue;
@@ -365,11 +440,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             const int ncols = min(p.BN, p.N - n0);
             const int nch = (ncols + 31) >> 5;
             if (ncols <= 0) {                              // phantom N tile of a pair: nothing to store, hand the buffer back
-                tc::mbar_wait(&tmem_full[wg], use & 1);
+                tc::mbar_wait_parked(&tmem_full[wg], use & 1);      // parked: eight polling epilogue warps would take issue slots from the producer / MMA warps
                 tc::fence_after_thread_sync();
                 tc::fence_before_thread_sync();
                 __syncwarp();
-                if (lane == 0) tc::mbar_arrive(&tmem_empty[wg]);
+                if (lane == 0) release_acc();
                 continue;
             }
             const int gin = p.in_shared ? 0 : g;
@@ -529,7 +604,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             };
 
             if (tin) fetch_in(0);
-            tc::mbar_wait(&tmem_full[wg], use & 1);
+            tc::mbar_wait_parked(&tmem_full[wg], use & 1);      // parked: eight polling epilogue warps would take issue slots from the producer / MMA warps
             tc::fence_after_thread_sync();
             float va[32], vb[32];
             if (EPI == EPI_WGRAD_T && p.ones && nt == 0) {          // bias gradient of weight column `row` (uniform branch)
@@ -549,7 +624,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                 } else {                                   // the whole accumulator sits in registers: hand it back
                     tc::fence_before_thread_sync();
                     __syncwarp();
-                    if (lane == 0) tc::mbar_arrive(&tmem_empty[wg]);
+                    if (lane == 0) release_acc();
                 }
                 process(va, c);
                 if (c + 1 < nch) {
@@ -560,7 +635,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                     } else {
                         tc::fence_before_thread_sync();
                         __syncwarp();
-                        if (lane == 0) tc::mbar_arrive(&tmem_empty[wg]);
+                        if (lane == 0) release_acc();
                     }
                     process(vb, c + 1);
                 }
@@ -582,7 +657,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     if (p.pair) tc::cluster_sync_all();                   // no CTA leaves while its peer may still signal its barriers
     if (warp == 2) {
         tc::fence_after_thread_sync();
-        tc::tmem_dealloc(tmem_base, 512u);
+        if (CTA2) tc::tmem_dealloc_2sm(tmem_base, 512u);
+        else tc::tmem_dealloc(tmem_base, 512u);
     }
 }
 
@@ -714,10 +790,28 @@ int launch(pgmvae_ctx* ctx, cudaStream_t st, Bf16P& p, const Operand& A, const O
         const double cn = wn <= 1.10 ? (0.5 * p.a_bytes + (double)p.b_bytes) * wn : 1e30;
         if (std::min(cm, cn) < 0.95 * none) p.pair = cm <= cn ? 1 : 2;
         if (p.total_tiles < 2 * ctx->sm_count) p.pair = 0;          // too little work to fill the machine with pairs anyway
-        if (const char* ev = getenv("PGMVAE_BF16_PAIR")) p.pair = atoi(ev) >= 0 && atoi(ev) <= 2 ? atoi(ev) : p.pair;
-        if (p.pair == 1 && !p.b_mn && (p.BN / 2) % 8) p.pair = 0;   // half tiles must keep whole 8-row swizzle atoms
+        // pairs along M can go one step further: ONE cta_group::2 MMA over both SMs, each holding only ITS half of the
+        // B tile -- the shared-memory fill per SM and k-block drops from A + B to A + B / 2 as well (what bounds the
+        // multicast pair: every SM still receives the whole B tile)
+        if (p.pair == 1 && getenv("PGMVAE_BF16_2SM") != nullptr) p.pair = 3;        // opt-in: measured equal to the multicast pair
+        // clusters of 2 x 2 tiles share both operands (per CTA and k-block: A / 2 + B / 2 from L2) at the price of the SMs
+        // that clusters of four cannot use (132 of 148 on B200): for the L2-bound main loops with long K
+        {
+            const double w4 = wm * wn;
+            if (w4 <= 1.10 && p.kblocks >= 16 && p.total_tiles >= 4 * ctx->sm_count && getenv("PGMVAE_BF16_NO_QUAD") == nullptr &&
+                0.5 * none * w4 * (148.0 / 132.0) < 0.9 * std::min(std::min(cm, cn), none))
+                p.pair = 4;
+        }
+        if (const char* ev = getenv("PGMVAE_BF16_PAIR")) p.pair = atoi(ev) >= 0 && atoi(ev) <= 4 ? atoi(ev) : p.pair;
+        if ((p.pair == 1 || p.pair == 3 || p.pair == 4) && (p.BN / 2) % 8) p.pair = 0;   // half tiles keep whole 8-row swizzle atoms
     }
-    p.total_ptiles = p.pair == 1 ? p.G * p.tiles_mp * p.tiles_n : (p.pair == 2 ? p.G * p.tiles_m * p.tiles_np : p.total_tiles);
+    p.total_ptiles = (p.pair == 1 || p.pair == 3) ? p.G * p.tiles_mp * p.tiles_n
+                     : (p.pair == 2 ? p.G * p.tiles_m * p.tiles_np
+                                    : (p.pair == 4 ? p.G * p.tiles_mp * p.tiles_np : p.total_tiles));
+    if (p.pair == 3) {                       // this CTA's half of the B tile
+        p.b_panels = (int)pg_cdiv(p.BN / 2, 64);
+        p.b_bytes = p.b_mn ? (unsigned)(p.b_panels * PANEL_BYTES) : (unsigned)pg_round_up((p.BN / 2) * 128, 1024);
+    }
     // bf16 rows leave (and the epilogue's bf16 operand rows arrive) as staged tiles through TMA: a thread owns a row, so
     // direct 16-byte accesses touch 32 different lines per warp instruction and the epilogue is bound by LSU wavefronts
     EpiMaps em;
@@ -752,19 +846,21 @@ int launch(pgmvae_ctx* ctx, cudaStream_t st, Bf16P& p, const Operand& A, const O
     if (smem < (size_t)120 * 1024) smem = (size_t)120 * 1024;
     CUtensorMap mA, mB;
     // (a K-major operand shared by a pair is loaded in two half-height boxes, one per CTA)
-    const uint32_t a_box_rows = p.pair == 2 ? TM / 2 : TM, b_box_rows = (uint32_t)(p.pair == 1 ? p.BN / 2 : p.BN);
+    const uint32_t a_box_rows = (p.pair == 2 || p.pair == 4) ? TM / 2 : TM;
+    const uint32_t b_box_rows = (uint32_t)((p.pair == 1 || p.pair == 3 || p.pair == 4) ? p.BN / 2 : p.BN);
     if (!p.a_mn) PG_TRY(tc::make_map(&mA, A.p, 2, (uint64_t)p.K, (uint64_t)p.M, (uint64_t)p.G, (uint64_t)A.ld, (uint64_t)A.gs, BK, a_box_rows));
     else PG_TRY(tc::make_map(&mA, A.p, 2, (uint64_t)p.M, (uint64_t)p.K, (uint64_t)p.G, (uint64_t)A.ld, (uint64_t)A.gs, 64, BK));
     if (!p.b_mn) PG_TRY(tc::make_map(&mB, B.p, 2, (uint64_t)p.K, (uint64_t)p.N, (uint64_t)p.G, (uint64_t)B.ld, (uint64_t)B.gs, BK, b_box_rows));
     else PG_TRY(tc::make_map(&mB, B.p, 2, (uint64_t)p.N, (uint64_t)p.K, (uint64_t)p.G, (uint64_t)B.ld, (uint64_t)B.gs, 64, BK));
-    static size_t configured[16] = {};
-    const int dev = ctx->device & 15;
-    if (smem > configured[dev]) {
-        PG_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured[dev] = smem;
+    static size_t configured[16][2] = {};
+    const int dev = ctx->device & 15, two = p.pair == 3 ? 1 : 0;
+    if (smem > configured[dev][two]) {
+        if (two) PG_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<EPI, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        else PG_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<EPI, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured[dev][two] = smem;
     }
-    const int csize = p.pair ? 2 : 1;
-    const int nclusters = std::min(p.total_ptiles, ctx->sm_count / csize);
+    const int csize = p.pair == 4 ? 4 : (p.pair ? 2 : 1);
+    int nclusters = std::min(p.total_ptiles, ctx->sm_count / csize);
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)(nclusters * csize));
     cfg.blockDim = dim3(THREADS);
@@ -777,8 +873,23 @@ int launch(pgmvae_ctx* ctx, cudaStream_t st, Bf16P& p, const Operand& A, const O
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
+    if (csize == 4) {
+        // tiles are assigned statically: never launch more clusters than can be resident at once (clusters of four do
+        // not tile every GPC)
+        static int max_quads[16][5] = {};
+        int& mq = max_quads[dev][EPI];
+        if (mq == 0) {
+            int n = 0;
+            cudaError_t e = two ? cudaOccupancyMaxActiveClusters(&n, gemm_bf16_kernel<EPI, true>, &cfg)
+                                : cudaOccupancyMaxActiveClusters(&n, gemm_bf16_kernel<EPI, false>, &cfg);
+            mq = (e == cudaSuccess && n > 0) ? n : 30;
+        }
+        nclusters = std::min(nclusters, mq);
+        cfg.gridDim = dim3((unsigned)(nclusters * csize));
+    }
     PG_KERNEL(ctx, st, name, bytes, 2.0 * p.G * (double)p.M * p.N * p.K);
-    PG_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<EPI>, mA, mB, em, p));
+    if (two) PG_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<EPI, true>, mA, mB, em, p));
+    else PG_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<EPI, false>, mA, mB, em, p));
     PG_LAUNCHED(ctx);
     return PGMVAE_OK;
 }

@@ -123,6 +123,56 @@ __device__ __forceinline__ void scatter_row(const Vq16P& p, int g, const float* 
     atomicAdd(p.cnt + (long long)g * p.c_gs + k, 1.0f);
 }
 
+// EMA statistics of the 32 rows a warp has just decided, WARP-AGGREGATED (north_star (c)): lanes that chose the same
+// code are found with match.any, the whole warp sums the rows of one code -- lane l owns floats 2l, 2l+1 (+64, ...) of the
+// vector -- and issues ONE set of reductions per distinct code instead of one per row.  With a trained codebook the 32
+// rows mostly differ and the per-row 128-bit reductions (scatter_row) are cheaper, so the warp takes this path only
+// when at most 8 distinct codes are present (right after initialisation nearly all rows of a variable share a code:
+// 4096 rows x 16 reductions into the same 256 bytes serialise in L2).  code < 0: the lane has nothing to add.
+__device__ __forceinline__ void scatter_warp(const Vq16P& p, int g, const float* zr, int code, int lane) {
+    const unsigned full = 0xffffffffu;
+    const unsigned active = __ballot_sync(full, code >= 0);
+    if (!active) return;
+    const unsigned peers = __match_any_sync(full, code);
+    const bool lead = code >= 0 && (__ffs(peers) - 1) == lane;
+    const int ngroups = __popc(__ballot_sync(full, lead));
+    const bool pairs_ok = p.zvec && !(p.D & 1) && !(p.lddw & 1) && !(p.dw_gs & 1);
+    if (ngroups > 8 || !pairs_ok) {
+        if (code >= 0) scatter_row(p, g, zr, code);
+        return;
+    }
+    unsigned todo = __ballot_sync(full, lead);
+    while (todo) {
+        const int src = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const unsigned grp = __shfl_sync(full, peers, src);
+        const int k = __shfl_sync(full, code, src);
+        float2 acc[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};          // D <= 128: two float2 per lane
+        unsigned mm = grp;
+        while (mm) {
+            const int r = __ffs(mm) - 1;
+            mm &= mm - 1;
+            const float* row = reinterpret_cast<const float*>(__shfl_sync(full, (unsigned long long)zr, r));
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int d = 2 * lane + 64 * j;
+                if (d < p.D) {
+                    const float2 v = *reinterpret_cast<const float2*>(row + d);
+                    acc[j].x += v.x; acc[j].y += v.y;
+                }
+            }
+        }
+        float* dst = p.dw + (long long)g * p.dw_gs + (long long)k * p.lddw;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int d = 2 * lane + 64 * j;
+            if (d < p.D)
+                asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(dst + d), "f"(acc[j].x), "f"(acc[j].y) : "memory");
+        }
+        if (lane == 0) atomicAdd(p.cnt + (long long)g * p.c_gs + k, (float)__popc(grp));
+    }
+}
+
 // quantise one row with its decided code: q, straight-through output (bf16), returns sum_d (q - z)^2
 __device__ __forceinline__ float quantize_row(const Vq16P& p, int g, int row, const float* zr, int k) {
     const float* er = p.e + (long long)g * p.e_gs + (long long)k * p.lde;
@@ -393,6 +443,7 @@ vq_assign_f16_kernel(const __grid_constant__ CUtensorMap mapE, const Vq16P p) {
             }
             it += p.tiles_n;
 
+            int my_code = -1;                               // decided code of this lane's row (for the warp-aggregated scatter)
             if (valid) {
                 const long long o = (long long)g * p.idx_gs + row;
                 const float thr_f = runmax - margin;
@@ -443,7 +494,7 @@ vq_assign_f16_kernel(const __grid_constant__ CUtensorMap mapE, const Vq16P p) {
                         if (p.gap) p.gap[o] = nq > 1 ? second - best : margin_d;
                     }
                     p.idx[o] = bi;
-                    if (p.dw) scatter_row(p, g, zr, bi);
+                    my_code = bi;
                     if (p.q || p.stb || p.loss) qloss += (double)quantize_row(p, g, row, zr, bi);
                 } else {
                     p.idx[o] = 0;
@@ -451,6 +502,8 @@ vq_assign_f16_kernel(const __grid_constant__ CUtensorMap mapE, const Vq16P p) {
                     p.flag_list[slot] = make_int2(g, row);
                 }
             }
+            __syncwarp();
+            if (p.dw) scatter_warp(p, g, zr, my_code, lane);
         }
         if (p.loss) {
             qloss = pg_warp_sum_d(qloss);

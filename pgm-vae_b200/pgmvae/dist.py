@@ -101,10 +101,11 @@ def init_from_env(ctx: _ffi.Context = None):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group(backend="gloo", rank=rank, world_size=world)
     ctx = ctx or _ffi.get_context(int(os.environ.get("LOCAL_RANK", rank)))
-    # The library's persistent kernels fill the SMs they are given with one statically scheduled CTA each, so the
-    # NCCL kernels of the overlapped exchange get SMs of their own: NCCL is held to PGMVAE_COMM_SMS CTAs (default 8;
-    # the 9 GB gradient exchange of cfg3 needs ~160 GB/s to hide under a step) and the compute grids leave that many free.
-    comm_sms = int(os.environ.get("PGMVAE_COMM_SMS", "8"))
+    # The library's persistent kernels fill the SMs they are given with one statically scheduled CTA each; PGMVAE_COMM_SMS=n
+    # holds NCCL to n CTAs and leaves that many SMs out of the compute grids, so that the overlapped exchange has SMs of
+    # its own.  Measured on cfg3 (round 2): 117.8 vs 117.5 ms per step at 2 GPUs, 123.1 vs 122.0 ms at 8 with n = 8 vs 0 --
+    # the 6 % of compute given up is not won back, so the default is 0 (NCCL and the GEMMs share the machine).
+    comm_sms = int(os.environ.get("PGMVAE_COMM_SMS", "0"))
     if comm_sms > 0:
         os.environ.setdefault("NCCL_MAX_CTAS", str(comm_sms))
         os.environ.setdefault("NCCL_MIN_CTAS", str(min(comm_sms, 4)))

@@ -58,7 +58,7 @@ def _act(x, act):
     (4, 64, 16, 24, None), (69, 300, 20, 16, "selu"), (2, 1000, 400, 200, "selu"), (1, 333, 1556, 400, "selu"),
     (3, 4096, 64, 50, "selu"), (2, 700, 400, 1556, "sigmoid"), (150, 130, 40, 30, "selu"),
 ])
-@pytest.mark.parametrize("pair", [None, "1", "2"])
+@pytest.mark.parametrize("pair", [None, "1", "2", "3", "4"])
 def test_fatdense_forward_bf16(bf16, monkeypatch, V, B, fin, fout, act, pair):
     from core.dense import FatDense
     if pair:
@@ -81,7 +81,7 @@ def test_fatdense_forward_bf16(bf16, monkeypatch, V, B, fin, fout, act, pair):
 
 
 @pytest.mark.parametrize("G,B,fin,V,g0", [(3, 50, 12, 16, 2), (2, 300, 50, 69, 10), (2, 513, 400, 1556, 700), (5, 128, 20, 40, 35)])
-@pytest.mark.parametrize("pair", [None, "1", "2"])
+@pytest.mark.parametrize("pair", [None, "1", "2", "3", "4"])
 def test_fwd_sigmoid_mse_bf16(bf16, monkeypatch, G, B, fin, V, g0, pair):
     """fd9 + loss: sigmoid output, squared / absolute error sums with the leave-one-out column masked, and
     d(loss)/d(pre-activation) (stored in bf16 by the kernel)."""
@@ -117,11 +117,12 @@ def test_fwd_sigmoid_mse_bf16(bf16, monkeypatch, G, B, fin, V, g0, pair):
 
 @pytest.mark.parametrize("G,B,fin,fout", [(9, 33, 9, 8), (3, 7, 4, 6), (5, 64, 16, 15), (4, 300, 69, 50), (2, 4096, 50, 40),
                                           (2, 1000, 400, 200), (1, 513, 1556, 400), (2, 600, 400, 1556), (3, 256, 64, 50)])
-@pytest.mark.parametrize("orient,pair", [("auto", None), ("d", None), ("t", None), ("d", "1"), ("d", "2"), ("t", "1"), ("t", "2")])
+@pytest.mark.parametrize("orient,pair", [("auto", None), ("d", None), ("t", None), ("d", "1"), ("d", "2"), ("t", "1"), ("t", "2"), ("d", "3"), ("t", "3"), ("d", "4"), ("t", "4")])
 def test_dgrad_wgrad_operators_bf16(bf16, monkeypatch, G, B, fin, fout, orient, pair):
     """pgmvae_dense_dgrad / pgmvae_dense_wgrad on padded (multiple-of-8) layouts, both wgrad orientations, and with the
     2-CTA cluster schedule forced (pair 1: neighbouring M tiles share a multicast B tile; pair 2: neighbouring N tiles
-    share A; odd tile counts leave phantom tiles)."""
+    share A; pair 3: one cta_group::2 MMA over both SMs of the pair; pair 4: clusters of 2 x 2 tiles with both operands
+    multicast; odd tile counts leave phantom tiles)."""
     from pgmvae import _ffi
     L = _ffi.lib()
     if orient != "auto":
@@ -215,7 +216,7 @@ GEOMS = [
 ]
 
 
-@pytest.mark.parametrize("pair", [None, "1", "2"])
+@pytest.mark.parametrize("pair", [None, "1", "2", "3", "4"])
 @pytest.mark.parametrize("V,units,D,K,B,ema,gv", GEOMS)
 def test_bf16_model_gradients_vs_oracle(ctx, monkeypatch, V, units, D, K, B, ema, gv, pair):
     """One step of the bf16 model (multi-group where gv is set) against the fp32 oracle: losses at 1e-3 / 2e-3,

@@ -258,7 +258,7 @@ def test_save_load_weights_round_trip(ctx, tmp_path):
         ma = a.train_on_batch(np.ascontiguousarray(y[s * B:(s + 1) * B]))
         mb = b.train_on_batch(np.ascontiguousarray(y[s * B:(s + 1) * B]))
         for k in ma:         # (the loss accumulators are fp32 / fp64 atomics: the order of the additions is not fixed)
-            assert abs(ma[k] - mb[k]) <= 1e-9 * abs(ma[k]) + 1e-15, (s, k, ma, mb)
+            assert abs(ma[k] - mb[k]) <= 1e-6 * abs(ma[k]) + 1e-15, (s, k, ma, mb)
     for n in ("fd0.kernel", "fd9.bias", "vq.embeddings", "vq.ema_w", "vq.ema_cluster_size"):
         np.testing.assert_allclose(a._get_tensor(n), b._get_tensor(n), rtol=1e-5, atol=1e-9, err_msg=n)
 
