@@ -65,7 +65,7 @@ struct Bf16P {
     __nv_bfloat16* cb; long long cb_gs; int ldcb;         // bf16 output rows (may be null)
     float* cf; long long cf_gs; int ldcf;                 // fp32 output rows (may be null)
     const float* bias; long long bias_gs; int act;
-    const __nv_bfloat16* yb; int ldyb; double* acc; float gscale; int g0;      // SIGMOID_MSE
+    const uint32_t* ybits; int ldbits; double* acc; float gscale; int g0;      // SIGMOID_MSE: targets bit-packed, 32 columns per word
     const __nv_bfloat16* hb; long long hb_gs; int ldhb;   // DGRAD: activation below (bf16) ...
     const float* hf; long long hf_gs; int ldhf;           // ... or fp32
     const float* z; const float* q; long long zq_gs; int ldzq; float cscale;
@@ -205,7 +205,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     uint8_t* sA = smem;                                           // [stages][16 KB]
     uint8_t* sB = sA + (size_t)p.stages * A_BYTES;                // [stages][b_bytes]
     uint8_t* sStage = sB + (size_t)p.stages * p.b_bytes;          // [2 warpgroups][STG_WG] (only with tma_out / tma_in)
-    uint8_t* sOnes = sStage + ((p.tma_out || p.tma_in) ? 2 * STG_WG : 0);      // (only with p.ones)
+    uint8_t* sOnes = sStage + ((p.tma_out || p.tma_in || EPI == EPI_SIGMOID_MSE) ? 2 * STG_WG : 0);      // (only with p.ones)
     uint64_t* bars = reinterpret_cast<uint64_t*>(sOnes + (p.ones ? ONES_BYTES : 0));
     uint64_t* full = bars;                        // [MAX_STAGES]   TMA -> MMA
     uint64_t* empty = bars + MAX_STAGES;          // [MAX_STAGES]   MMA -> TMA
@@ -416,8 +416,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         const bool leader = rt == 0;                   // issues this warpgroup's TMA loads / stores
         const uint32_t lane_addr = tmem_base + ((uint32_t)(qd * 32) << 16) + wg * ACC_COLS;
         // staged chunk [128 rows][64 B], 64-byte swizzle: the 16-byte piece j of row r sits at piece j ^ ((r >> 1) & 3)
+        // per warpgroup: out | in[0] | in[1]; the MSE stage needs no operand tiles (its targets are bits) and uses the
+        // room for a second output tile and its target words: out[0] | out[1] | words
         uint8_t* sOut = sStage + (size_t)wg * STG_WG;
         uint8_t* sIn = sOut + STG_TILE;
+        uint32_t* sY = reinterpret_cast<uint32_t*>(sOut + 2 * STG_TILE) + rt * 9;       // 9 target words of this thread's row
         const uint32_t swz = (uint32_t)((rt >> 1) & 3);
         uint64_t* my_in_full = in_full + wg * 2;
         uint32_t in_uses[2] = {0u, 0u};
@@ -472,9 +475,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             };
             // the thread's 32 bf16 results of chunk c -> staging tile -> one TMA store per warpgroup
             auto write_out = [&](int c, const float (&v)[32]) {
-                if (leader) tc::bulk_wait_read();                  // the previous store has read the staging tile
+                uint8_t* tile = sOut + ((EPI == EPI_SIGMOID_MSE) ? (size_t)(c & 1) * STG_TILE : 0);
+                if (leader) {                                       // the store that last used this staging tile has read it
+                    if (EPI == EPI_SIGMOID_MSE) tc::bulk_wait_read1();
+                    else tc::bulk_wait_read();
+                }
                 tc::named_bar_sync(1 + wg, 128);
-                uint8_t* rowp = sOut + rt * 64;
+                uint8_t* rowp = tile + rt * 64;
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
                     *reinterpret_cast<uint4*>(rowp + ((j ^ swz) << 4)) =
@@ -483,7 +490,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                 tc::fence_proxy_async_smem();
                 tc::named_bar_sync(1 + wg, 128);
                 if (leader) {
-                    tc::tma_store_3d(&em.out[nt], sOut, c * 32, m0, g);
+                    tc::tma_store_3d(&em.out[nt], tile, c * 32, m0, g);
                     tc::bulk_commit();
                 }
             };
@@ -515,8 +522,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 #pragma unroll
                         for (int j = 0; j < 32; ++j) v[j] += t[j];
                     }
-                    if (tin) read_in(c, t);                                                 // targets (0 / 1)
-                    else load_bf16_row(p.yb + (long long)(rvalid ? row : 0) * p.ldyb + nb, t, nv, p.vec);
+                    // targets (0 / 1): bit j of `bits` belongs to column nb + j
+                    const uint32_t bits = (n0 & 31) ? __funnelshift_r(sY[c], sY[c + 1], n0 & 31) : sY[c];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) t[j] = (bits >> j) & 1u ? 1.0f : 0.0f;
                     const int self = rvalid ? p.g0 + g - nb : -1;                           // masked column of this net
                     const int nvr = rvalid ? nv : 0;                                        // rows past the batch count nothing
                     float o[32];
@@ -604,6 +613,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             };
 
             if (tin) fetch_in(0);
+            if (EPI == EPI_SIGMOID_MSE) {                  // this row's target words of the tile, long before they are needed
+                const uint32_t* yrow = p.ybits + (long long)(rvalid ? row : 0) * p.ldbits;
+                const int w0 = n0 >> 5;
+#pragma unroll
+                for (int i = 0; i < 9; ++i) sY[i] = w0 + i < p.ldbits ? __ldg(yrow + w0 + i) : 0u;
+            }
             tc::mbar_wait_parked(&tmem_full[wg], use & 1);      // parked: eight polling epilogue warps would take issue slots from the producer / MMA warps
             tc::fence_after_thread_sync();
             float va[32], vb[32];
@@ -704,6 +719,20 @@ __global__ void y_to_bf16_kernel(const uint8_t* __restrict__ y, int ldy, __nv_bf
     if (i >= (long long)B * ld) return;
     const int b = (int)(i / ld), c = (int)(i - (long long)b * ld);
     out[i] = __float2bfloat16_rn(c < V && y[(long long)b * ldy + c] != 0 ? 1.0f : 0.0f);
+}
+
+// targets of the MSE stage, bit-packed: word w of row b holds columns 32 w .. 32 w + 31 (columns >= V read as 0)
+template <class T>
+__global__ void to_bits_kernel(const T* __restrict__ y, int ldy, uint32_t* __restrict__ bits, int ldbits, int B, int V) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)B * ldbits) return;
+    const int b = (int)(i / ldbits), w = (int)(i - (long long)b * ldbits);
+    uint32_t word = 0u;
+    const T* row = y + (long long)b * ldy + 32 * w;
+#pragma unroll 8
+    for (int j = 0; j < 32; ++j)
+        if (32 * w + j < V && row[j] != (T)0) word |= 1u << j;
+    bits[i] = word;
 }
 
 // bias gradient: db[g][n] = sum_b dY[g][b][n]; one CTA per (64 columns, variable): 8 row groups x 32 column pairs
@@ -816,11 +845,11 @@ int launch(pgmvae_ctx* ctx, cudaStream_t st, Bf16P& p, const Operand& A, const O
     // direct 16-byte accesses touch 32 different lines per warp instruction and the epilogue is bound by LSU wavefronts
     EpiMaps em;
     memset(&em, 0, sizeof(em));
-    const __nv_bfloat16* inp = EPI == EPI_SIGMOID_MSE ? p.yb : (EPI == EPI_DGRAD ? p.hb : nullptr);
-    const int ld_in = EPI == EPI_SIGMOID_MSE ? p.ldyb : p.ldhb;
-    const int64_t gs_in = EPI == EPI_SIGMOID_MSE ? 0 : p.hb_gs;
+    const __nv_bfloat16* inp = EPI == EPI_DGRAD ? p.hb : nullptr;
+    const int ld_in = p.ldhb;
+    const int64_t gs_in = p.hb_gs;
     const bool epi_rows = EPI == EPI_FWD || EPI == EPI_SIGMOID_MSE || EPI == EPI_DGRAD;
-    p.in_shared = EPI == EPI_SIGMOID_MSE;
+    p.in_shared = 0;
     p.tma_out = epi_rows && p.cb && p.tiles_n <= MAX_NT_MAPS && al16(p.cb) && p.ldcb % 8 == 0 && p.cb_gs % 8 == 0 &&
                 getenv("PGMVAE_BF16_DIRECT_EPI") == nullptr;
     p.tma_in = p.tma_out && inp && al16(inp) && ld_in % 8 == 0 && gs_in % 8 == 0;
@@ -833,7 +862,8 @@ int launch(pgmvae_ctx* ctx, cudaStream_t st, Bf16P& p, const Operand& A, const O
                                 (uint64_t)ld_in, (uint64_t)gs_in, 32, TM, false, true));
     }
     const size_t stage = (size_t)A_BYTES + p.b_bytes;
-    const size_t fixed = 1024 + 256 + (p.tma_out ? 2 * (size_t)STG_WG : 0) + (p.ones ? ONES_BYTES : 0);
+    const bool staged = p.tma_out || EPI == EPI_SIGMOID_MSE;       // (the MSE stage keeps its target words there)
+    const size_t fixed = 1024 + 256 + (staged ? 2 * (size_t)STG_WG : 0) + (p.ones ? ONES_BYTES : 0);
     int stages = (int)((ctx->smem_optin - fixed) / stage);
     if (stages > MAX_STAGES) stages = MAX_STAGES;
     if (stages < 2) {
@@ -914,14 +944,14 @@ int pg_bf16_fwd(pgmvae_ctx* ctx, cudaStream_t st, const __nv_bfloat16* x, int64_
 
 int pg_bf16_fwd_sigmoid_mse(pgmvae_ctx* ctx, cudaStream_t st, const __nv_bfloat16* x, int64_t x_gs, int ldx,
                             const __nv_bfloat16* wt, int64_t wt_gs, int ldwt, const float* bias, int64_t bias_gs,
-                            const __nv_bfloat16* yb, int ldyb, __nv_bfloat16* dpre, int64_t dpre_gs, int ldd, float* out_opt,
+                            const uint32_t* ybits, int ldbits, __nv_bfloat16* dpre, int64_t dpre_gs, int ldd, float* out_opt,
                             int64_t out_gs, int ldo, double* acc2, int G, int g0, int B, int in, int V, float grad_scale,
                             int w_mn) {
     Bf16P p{};
     p.G = G; p.M = B; p.N = V; p.K = in; p.b_mn = w_mn ? 1 : 0;
     p.cb = dpre; p.cb_gs = dpre_gs; p.ldcb = ldd; p.cf = out_opt; p.cf_gs = out_gs; p.ldcf = ldo;
-    p.bias = bias; p.bias_gs = bias_gs; p.yb = yb; p.ldyb = ldyb; p.acc = acc2; p.gscale = grad_scale; p.g0 = g0;
-    p.vec = (!dpre || (al16(dpre) && ldd % 8 == 0 && dpre_gs % 8 == 0)) && al16(yb) && ldyb % 8 == 0 &&
+    p.bias = bias; p.bias_gs = bias_gs; p.ybits = ybits; p.ldbits = ldbits; p.acc = acc2; p.gscale = grad_scale; p.g0 = g0;
+    p.vec = (!dpre || (al16(dpre) && ldd % 8 == 0 && dpre_gs % 8 == 0)) &&
             (!out_opt || (al16(out_opt) && ldo % 4 == 0 && out_gs % 4 == 0)) && (!bias || (al16(bias) && bias_gs % 4 == 0));
     return launch<EPI_SIGMOID_MSE>(ctx, st, p, Operand{x, x_gs, ldx}, Operand{wt, wt_gs, ldwt}, "dense_fwd_sigmoid_mse_bf16",
                                    2.0 * ((double)G * B * in + (double)G * in * V + (double)B * V + (double)G * B * V) +
@@ -1018,6 +1048,23 @@ int pg_bf16_shadow(pgmvae_ctx* ctx, cudaStream_t st, const float* w, int64_t w_g
                                             t_gs, ldt, wc ? wc + (size_t)g0 * c_gs : nullptr, c_gs, ldc);
         PG_LAUNCHED(ctx);
     }
+    return PGMVAE_OK;
+}
+
+int pg_y_to_bits(pgmvae_ctx* ctx, cudaStream_t st, const uint8_t* y, int ldy, uint32_t* bits, int ldbits, int B, int V) {
+    if (B <= 0) return PGMVAE_OK;
+    const long long n = (long long)B * ldbits;
+    PG_KERNEL(ctx, st, "y_to_bits", (double)B * V + 4.0 * n, 0.0);
+    to_bits_kernel<uint8_t><<<(unsigned)pg_cdiv(n, 256), 256, 0, st>>>(y, ldy, bits, ldbits, B, V);
+    PG_LAUNCHED(ctx);
+    return PGMVAE_OK;
+}
+int pg_f32_to_bits(pgmvae_ctx* ctx, cudaStream_t st, const float* y, int ldy, uint32_t* bits, int ldbits, int B, int V) {
+    if (B <= 0) return PGMVAE_OK;
+    const long long n = (long long)B * ldbits;
+    PG_KERNEL(ctx, st, "y_to_bits", 4.0 * B * V + 4.0 * n, 0.0);
+    to_bits_kernel<float><<<(unsigned)pg_cdiv(n, 256), 256, 0, st>>>(y, ldy, bits, ldbits, B, V);
+    PG_LAUNCHED(ctx);
     return PGMVAE_OK;
 }
 

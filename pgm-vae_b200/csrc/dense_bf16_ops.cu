@@ -70,18 +70,19 @@ int pg_dense_fwd_sigmoid_mse_bf16(pgmvae_ctx* ctx, cudaStream_t st, const float*
                                   int in, int V, float grad_scale) {
     if (G <= 0 || B <= 0) return PGMVAE_OK;
     const int pin = P8(in), pv = P8(V), xg = x_gs == 0 ? 1 : G;
-    const size_t nx = (size_t)xg * B * pin, nw = (size_t)G * in * pv, ny = (size_t)B * pv, nd = (size_t)G * B * pv;
+    const int ldbits = pv / 32 + 2;
+    const size_t nx = (size_t)xg * B * pin, nw = (size_t)G * in * pv, ny = (size_t)B * ldbits * 2, nd = (size_t)G * B * pv;
     PG_TRY(ensure(ctx, pad256(nx * 2) + pad256(nw * 2) + pad256(ny * 2) + pad256(nd * 2)));
     Carver c{(uint8_t*)ctx->scratch_b};
     __nv_bfloat16* xb = c.take<__nv_bfloat16>(nx);
     __nv_bfloat16* wt = c.take<__nv_bfloat16>(nw);
-    __nv_bfloat16* yb = c.take<__nv_bfloat16>(ny);
+    uint32_t* yb = reinterpret_cast<uint32_t*>(c.take<__nv_bfloat16>(ny));
     __nv_bfloat16* db = c.take<__nv_bfloat16>(nd);
     PG_TRY(pg_f32_to_bf16(ctx, st, x, x_gs, ldx, xb, (int64_t)B * pin, pin, xg, B, in));
     PG_TRY(pg_bf16_shadow(ctx, st, w, w_gs, ldw, in, V, nullptr, 0, 0, wt, (int64_t)in * pv, pv, G));
-    PG_TRY(pg_f32_to_bf16(ctx, st, y, 0, ldy, yb, 0, pv, 1, B, V));
+    PG_TRY(pg_f32_to_bits(ctx, st, y, ldy, yb, ldbits, B, V));
     PG_TRY(pg_bf16_fwd_sigmoid_mse(ctx, st, xb, x_gs == 0 ? 0 : (int64_t)B * pin, pin, wt, (int64_t)in * pv, pv, bias, bias_gs, yb,
-                                   pv, db, (int64_t)B * pv, pv, out_opt, dpre_gs, ldd, acc2, G, g0, B, in, V, grad_scale, 1));
+                                   ldbits, db, (int64_t)B * pv, pv, out_opt, dpre_gs, ldd, acc2, G, g0, B, in, V, grad_scale, 1));
     dim3 grid((unsigned)std::min<int64_t>(pg_cdiv((int64_t)B * V, 1024), 2048), (unsigned)G);
     bf16_to_f32_kernel<<<grid, 256, 0, st>>>(db, (long long)B * pv, pv, dpre, dpre_gs, ldd, B, V);
     PG_LAUNCHED(ctx);

@@ -200,6 +200,7 @@ struct pgmvae_model {
     // operand of the forward GEMMs), written by the Adam kernel together with the fp32 master weights.
     bool bf16 = false, shadow_dirty = true;
     __nv_bfloat16* yb = nullptr;            // [max_batch][Vp]
+    uint32_t* ybits = nullptr; int ldbits = 0;   // the same data bit-packed (targets of the fused MSE stage), [max_batch][ldbits]
     __nv_bfloat16* Hb[10] = {};             // activations (layer 4 = the latent stays fp32 in H[4])
     __nv_bfloat16* Gb[10] = {};             // d(loss)/d(pre-activation)
     __nv_bfloat16* stb = nullptr;           // straight-through output of the VQ layer
@@ -355,7 +356,10 @@ int upload_batch(pgmvae_model* m, const uint8_t* y, int on_device, int B, const 
         PG_CUDA(cudaMemcpyAsync(m->y_u8, y, (size_t)B * m->V, cudaMemcpyHostToDevice, st));
         *y_dev = m->y_u8;
     }
-    if (m->bf16) return pg_y_to_bf16(m->ctx, st, *y_dev, m->V, m->yb, m->Vp, B, m->V);
+    if (m->bf16) {
+        PG_TRY(pg_y_to_bits(m->ctx, st, *y_dev, m->V, m->ybits, m->ldbits, B, m->V));
+        return pg_y_to_bf16(m->ctx, st, *y_dev, m->V, m->yb, m->Vp, B, m->V);
+    }
     return pgmvae_y_to_f32(m->ctx, st, *y_dev, m->V, m->yf, m->Vp, B, m->V);
 }
 
@@ -599,6 +603,8 @@ int pgmvae_model_create(pgmvae_ctx* ctx, const int* units4, int nvar, int dim, i
     A((void**)&m->y_u8, (size_t)max_batch * nvar);
     if (m->bf16) {
         A((void**)&m->yb, (size_t)max_batch * m->Vp * 2);
+        m->ldbits = m->Vp / 32 + 2;
+        A((void**)&m->ybits, (size_t)max_batch * m->ldbits * 4);
         for (int l = 0; l < 10; ++l) {
             if (l < 9 && l != 4) A((void**)&m->Hb[l], vg * max_batch * m->L[l].pout * 2);
             A((void**)&m->Gb[l], vg * max_batch * m->L[l].pout * 2);
@@ -1037,7 +1043,7 @@ int run_step(pgmvae_model* m, const uint8_t* y, int y_on_device, int B, int glob
             const Layer& L = m->L[9];
             PG_TRY(pg_bf16_fwd_sigmoid_mse(ctx, st, m->Hb[8], MB * m->L[8].pout, m->L[8].pout,
                                            m->wb + L.w_off + (size_t)g0 * L.pin * L.pout, (int64_t)L.pin * L.pout, L.pout,
-                                           m->params + L.b_off + (size_t)g0 * L.pout, L.pout, m->yb, m->Vp, m->Gb[9], MB * L.pout,
+                                           m->params + L.b_off + (size_t)g0 * L.pout, L.pout, m->ybits, m->ldbits, m->Gb[9], MB * L.pout,
                                            L.pout, out_dev ? out_dev + (size_t)g0 * MB * L.pout : nullptr, MB * L.pout, L.pout,
                                            m->acc, Gn, g0, B, L.in, V, gscale, 1));
         }

@@ -111,7 +111,7 @@ int pg_bf16_fwd(pgmvae_ctx* ctx, cudaStream_t st, const __nv_bfloat16* x, int64_
                 float* outf, int64_t outf_gs, int ldof, int G, int B, int in, int out_dim, int act, int w_mn = 0);
 int pg_bf16_fwd_sigmoid_mse(pgmvae_ctx* ctx, cudaStream_t st, const __nv_bfloat16* x, int64_t x_gs, int ldx,
                             const __nv_bfloat16* wt, int64_t wt_gs, int ldwt, const float* bias, int64_t bias_gs,
-                            const __nv_bfloat16* yb, int ldyb, __nv_bfloat16* dpre, int64_t dpre_gs, int ldd, float* out_opt,
+                            const uint32_t* ybits, int ldbits, __nv_bfloat16* dpre, int64_t dpre_gs, int ldd, float* out_opt,
                             int64_t out_gs, int ldo, double* acc2, int G, int g0, int B, int in, int V, float grad_scale, int w_mn = 0);
 int pg_bf16_dgrad(pgmvae_ctx* ctx, cudaStream_t st, const __nv_bfloat16* dy, int64_t dy_gs, int lddy, const __nv_bfloat16* w,
                   int64_t w_gs, int ldw, const __nv_bfloat16* hb, int64_t hb_gs, int ldhb, const float* hf, int64_t hf_gs,
@@ -145,4 +145,6 @@ int pg_bf16_shadow(pgmvae_ctx* ctx, cudaStream_t st, const float* w, int64_t w_g
 int pg_flat_to_bf16(pgmvae_ctx* ctx, cudaStream_t st, const float* src, __nv_bfloat16* dst, int64_t n);
 int pg_adam_step_shadow(pgmvae_ctx* ctx, cudaStream_t stream, float* p, const float* g, float* m, float* v, int64_t n,
                         float alpha, double b1, double b2, double eps, __nv_bfloat16* wb, int64_t nwb);
+int pg_y_to_bits(pgmvae_ctx* ctx, cudaStream_t st, const uint8_t* y, int ldy, uint32_t* bits, int ldbits, int B, int V);
+int pg_f32_to_bits(pgmvae_ctx* ctx, cudaStream_t st, const float* y, int ldy, uint32_t* bits, int ldbits, int B, int V);
 int pg_y_to_bf16(pgmvae_ctx* ctx, cudaStream_t st, const uint8_t* y, int ldy, __nv_bfloat16* out, int ld, int B, int V);
