@@ -62,6 +62,7 @@ struct Bf16P {
     unsigned a_bytes, b_bytes;
     int vec;                                              // rows allow 16-byte vector access
     int tma_out, tma_in, in_shared;                       // bf16 output / epilogue operand move through staged TMA tiles
+    int out_db;                                           // dgrad: two output staging tiles next to the two operand tiles
     __nv_bfloat16* cb; long long cb_gs; int ldcb;         // bf16 output rows (may be null)
     float* cf; long long cf_gs; int ldcf;                 // fp32 output rows (may be null)
     const float* bias; long long bias_gs; int act;
@@ -159,6 +160,7 @@ struct EpiMaps {
 };
 constexpr int STG_TILE = TM * 64;      // one staged chunk: 128 rows x 32 bf16 (64 B, 64-byte swizzle) = 8 KB
 constexpr int STG_WG = 3 * STG_TILE;   // per epilogue warpgroup: out | in[0] | in[1]
+constexpr int STG_WG4 = 4 * STG_TILE;  // ... out[0] | out[1] | in[0] | in[1] (dgrad of the short-K layers: p.out_db)
 
 // (variable, M tile, N tile) of pair-tile `pt` for the CTA of rank `crank` in its cluster.  N fastest, then M, then
 // the variable; the two CTAs of a pair take neighbouring M tiles of one N tile (pair == 1: they share the B tile) or
@@ -205,8 +207,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     uint8_t* sA = smem;                                           // [stages][16 KB]
     uint8_t* sB = sA + (size_t)p.stages * A_BYTES;                // [stages][b_bytes]
     uint8_t* sStage = sB + (size_t)p.stages * p.b_bytes;          // [2 warpgroups][STG_WG] (only with tma_out / tma_in)
-    uint8_t* sOnes = sStage + ((p.tma_out || p.tma_in || EPI == EPI_SIGMOID_MSE) ? 2 * STG_WG : 0);      // (only with p.ones)
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sOnes + (p.ones ? ONES_BYTES : 0));
+    uint8_t* sOnes = sStage + ((p.tma_out || p.tma_in || EPI == EPI_SIGMOID_MSE) ? 2 * (p.out_db ? STG_WG4 : STG_WG) : 0);      // (only with p.ones)
+    float* sBias = reinterpret_cast<float*>(sOnes + (p.ones ? ONES_BYTES : 0));      // [2 warpgroups][256] bias of the tile
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + 2 * ACC_COLS);
     uint64_t* full = bars;                        // [MAX_STAGES]   TMA -> MMA
     uint64_t* empty = bars + MAX_STAGES;          // [MAX_STAGES]   MMA -> TMA
     uint64_t* tmem_full = bars + 2 * MAX_STAGES;  // [2]            MMA -> epilogue warpgroup
@@ -418,12 +421,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         // staged chunk [128 rows][64 B], 64-byte swizzle: the 16-byte piece j of row r sits at piece j ^ ((r >> 1) & 3)
         // per warpgroup: out | in[0] | in[1]; the MSE stage needs no operand tiles (its targets are bits) and uses the
         // room for a second output tile and its target words: out[0] | out[1] | words
-        uint8_t* sOut = sStage + (size_t)wg * STG_WG;
-        uint8_t* sIn = sOut + STG_TILE;
+        uint8_t* sOut = sStage + (size_t)wg * (p.out_db ? STG_WG4 : STG_WG);
+        uint8_t* sIn = sOut + (p.out_db ? 2 : 1) * STG_TILE;
         uint32_t* sY = reinterpret_cast<uint32_t*>(sOut + 2 * STG_TILE) + rt * 9;       // 9 target words of this thread's row
         const uint32_t swz = (uint32_t)((rt >> 1) & 3);
         uint64_t* my_in_full = in_full + wg * 2;
         uint32_t in_uses[2] = {0u, 0u};
+        uint32_t out_cnt = 0;
         const bool tin = p.tma_in != 0, tout = p.tma_out != 0;
         double dsq = 0.0, dab = 0.0;
         // hand an accumulator buffer back to the MMA issuer: under cta_group::2 that is the leader CTA's warp 1 for both CTAs
@@ -452,6 +456,19 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             }
             const int gin = p.in_shared ? 0 : g;
             float sq = 0.f, ab = 0.f;
+            // the tile's bias through shared memory: two predicated loads per thread and tile instead of 32 bounds-checked
+            // ones per chunk (which were 40 % of the instructions of a chunk).  The MSE stage keeps -log2(e) * bias: its
+            // sigmoid is 1 / (1 + 2^(-log2(e) * (acc + bias))).  The warpgroup's reads of the previous tile's bias
+            // precede the barriers of that tile's last write_out.
+            const bool sbias = tout && p.bias && (EPI == EPI_FWD || EPI == EPI_SIGMOID_MSE);
+            float* myBias = sBias + wg * ACC_COLS;
+            if (sbias) {
+                const float* bp = p.bias + (long long)g * p.bias_gs + n0;
+                const float sc = EPI == EPI_SIGMOID_MSE ? -LOG2E : 1.0f;
+                myBias[rt] = rt < ncols ? sc * __ldg(bp + rt) : 0.f;
+                myBias[rt + TM] = rt + TM < ncols ? sc * __ldg(bp + rt + TM) : 0.f;
+                tc::named_bar_sync(1 + wg, 128);
+            }
 
             // epilogue operand (targets / activation below) of chunk c -> staging buffer c & 1
             auto fetch_in = [&](int c) {
@@ -475,9 +492,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             };
             // the thread's 32 bf16 results of chunk c -> staging tile -> one TMA store per warpgroup
             auto write_out = [&](int c, const float (&v)[32]) {
-                uint8_t* tile = sOut + ((EPI == EPI_SIGMOID_MSE) ? (size_t)(c & 1) * STG_TILE : 0);
+                // (forward stages have no operand tiles: the room holds a second output tile)
+                const bool two_out = EPI == EPI_SIGMOID_MSE || EPI == EPI_FWD || p.out_db;
+                uint8_t* tile = sOut + (two_out ? (size_t)(out_cnt++ & 1u) * STG_TILE : 0);     // alternates ACROSS tiles as well
                 if (leader) {                                       // the store that last used this staging tile has read it
-                    if (EPI == EPI_SIGMOID_MSE) tc::bulk_wait_read1();
+                    if (two_out) tc::bulk_wait_read1();
                     else tc::bulk_wait_read();
                 }
                 tc::named_bar_sync(1 + wg, 128);
@@ -499,7 +518,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                 const int nb = n0 + c * 32;
                 const int nv = min(32, ncols - c * 32);            // valid columns of this chunk (tile and tensor bounds)
                 if (EPI == EPI_FWD) {
-                    if (p.bias) {
+                    if (sbias) {
+                        const float4* b4 = reinterpret_cast<const float4*>(myBias + c * 32);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float4 b = b4[j];
+                            v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+                        }
+                    } else if (p.bias) {
                         float bv[32];
                         load_f32_row(p.bias + (long long)g * p.bias_gs + nb, bv, nv, p.vec);
 #pragma unroll
@@ -517,10 +543,23 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                     else if (p.cb && rvalid) store_bf16_row(p.cb + (long long)g * p.cb_gs + (long long)row * p.ldcb + nb, v, nv, p.vec);
                 } else if (EPI == EPI_SIGMOID_MSE) {
                     float t[32];
-                    if (p.bias) {
-                        load_f32_row(p.bias + (long long)g * p.bias_gs + nb, t, nv, p.vec);
+                    // v <- -log2(e) * (acc + bias)
+                    if (sbias) {
+                        const float4* b4 = reinterpret_cast<const float4*>(myBias + c * 32);
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] += t[j];
+                        for (int j = 0; j < 8; ++j) {
+                            const float4 b = b4[j];
+                            v[4 * j] = fmaf(v[4 * j], -LOG2E, b.x); v[4 * j + 1] = fmaf(v[4 * j + 1], -LOG2E, b.y);
+                            v[4 * j + 2] = fmaf(v[4 * j + 2], -LOG2E, b.z); v[4 * j + 3] = fmaf(v[4 * j + 3], -LOG2E, b.w);
+                        }
+                    } else {
+                        if (p.bias) {
+                            load_f32_row(p.bias + (long long)g * p.bias_gs + nb, t, nv, p.vec);
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) v[j] += t[j];
+                        }
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] *= -LOG2E;
                     }
                     // targets (0 / 1): bit j of `bits` belongs to column nb + j
                     const uint32_t bits = (n0 & 31) ? __funnelshift_r(sY[c], sY[c + 1], n0 & 31) : sY[c];
@@ -532,7 +571,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                     if (nvr == 32 && (unsigned)self >= 32u) {                               // interior chunk: nothing to mask
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
-                            o[j] = sigmoid_fast(v[j]);
+                            o[j] = rcp_approx(1.0f + ex2_approx(v[j]));
                             const float d = o[j] - t[j];
                             sq = fmaf(d, d, sq);
                             ab += fabsf(d);
@@ -542,7 +581,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                     } else {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
-                            o[j] = sigmoid_fast(v[j]);
+                            o[j] = rcp_approx(1.0f + ex2_approx(v[j]));
                             float d = o[j] - t[j];
                             if (j >= nvr || j == self) d = 0.f;
                             sq = fmaf(d, d, sq);
@@ -863,9 +902,13 @@ int launch(pgmvae_ctx* ctx, cudaStream_t st, Bf16P& p, const Operand& A, const O
     }
     const size_t stage = (size_t)A_BYTES + p.b_bytes;
     const bool staged = p.tma_out || EPI == EPI_SIGMOID_MSE;       // (the MSE stage keeps its target words there)
-    const size_t fixed = 1024 + 256 + (staged ? 2 * (size_t)STG_WG : 0) + (p.ones ? ONES_BYTES : 0);
+    // short-K dgrad layers are bound by their epilogue, not by the depth of the operand ring: a second output tile
+    p.out_db = EPI == EPI_DGRAD && p.tma_in && p.kblocks <= 8;
+    const size_t fixed = 1024 + 256 + (staged ? 2 * (size_t)(p.out_db ? STG_WG4 : STG_WG) : 0) + (p.ones ? ONES_BYTES : 0) +
+                         2 * ACC_COLS * sizeof(float);
     int stages = (int)((ctx->smem_optin - fixed) / stage);
     if (stages > MAX_STAGES) stages = MAX_STAGES;
+    if (const char* ev = getenv("PGMVAE_BF16_STAGES")) stages = std::max(2, std::min(stages, atoi(ev)));   // (experiments)
     if (stages < 2) {
         pgmvae_set_error("%s: shared memory too small", name);
         return PGMVAE_EINVAL;
