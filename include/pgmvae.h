@@ -266,14 +266,25 @@ int pgmvae_model_get_tensor(pgmvae_model* m, const char* name, float* host, int6
 int pgmvae_model_set_ema_steps(pgmvae_model* m, int step_c, int step_w);
 int pgmvae_model_set_adam_step(pgmvae_model* m, int64_t t);
 
-/* Peer-to-peer gradient exchange (single node, data parallel; new work like pgmvae_comm_*): instead of NCCL
- * all-reduces followed by Adam, ONE kernel per rank reads the gradient buffers of all ranks over NVLink, sums
- * them in rank order and applies the Adam update (the replicas stay bit-identical).
- * export: writes 2 x 64 bytes (CUDA IPC handles of this rank's gradient buffer and flag block); the host
- * exchanges them (any side channel) and passes all of them, in rank order, to import.  Optional: without it
- * pgmvae_model_train_step reduces the gradients through the communicator.                                  */
-int pgmvae_model_p2p_export(pgmvae_model* m, void* handles_out128);
+/* Peer-to-peer gradient exchange (single node, data parallel; new work like pgmvae_comm_*; the reference is
+ * single-device, run.py:27-31).  Every rank maps the gradient / parameter / bf16-mirror / Adam-moment buffers and the
+ * flag block of every other rank (CUDA IPC).  Two kernels use the mapping instead of NCCL all-reduces + Adam:
+ *   narrow models (one variable group, chain kernels): ONE kernel per rank reads the gradient buffers of all ranks
+ *     over NVLink, sums them in rank order and applies the Adam update (two ranks by default; PGMVAE_P2P=1 forces it);
+ *   wide models (per-group path): per variable group, reduce-scatter + Adam + all-gather as ONE kernel -- a rank sums
+ *     ITS shard of the group's gradients from all peers, updates it and writes the new parameters (fp32 + bf16
+ *     mirror) into every rank's buffers; the CTAs are small enough to run next to the GEMMs of the following group
+ *     (any rank count up to 8; PGMVAE_P2P_SHARD=0 keeps NCCL).  The replicas stay bit-identical either way.
+ * export: writes 6 x 64 bytes (CUDA IPC handles: gradients, flag block, parameters, bf16 mirror, Adam m, Adam v);
+ * the host exchanges them (any side channel) and passes all of them, in rank order, to import.  Optional: without
+ * it pgmvae_model_train_step reduces the gradients through the communicator.                                  */
+int pgmvae_model_p2p_export(pgmvae_model* m, void* handles_out384);
 int pgmvae_model_p2p_import(pgmvae_model* m, int rank, int nranks, const void* all_handles);
+/* After steps of the sharded exchange the Adam moments are complete only on the rank that owns a shard
+ * (moments_sharded() == 1); sync_moments() -- COLLECTIVE over the ranks of the mapping -- completes them everywhere
+ * (before get_tensor("adam_m.*") / a checkpoint). */
+int pgmvae_model_p2p_moments_sharded(pgmvae_model* m);
+int pgmvae_model_p2p_sync_moments(pgmvae_model* m);
 /* turn the peer-to-peer exchange off again (a rank failed to map its peers): NCCL is used instead */
 int pgmvae_model_p2p_disable(pgmvae_model* m);
 /* cudaDeviceCanAccessPeer(device, peer): whether the CUDA-IPC mapping behind pgmvae_model_p2p_import can work */

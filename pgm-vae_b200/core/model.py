@@ -114,19 +114,20 @@ class VqVAE:
     def _setup_p2p(self):
         """Data parallel on one node: map every rank's gradient buffer into every other rank (CUDA IPC) so that the
         library can fuse the gradient exchange with Adam (pgmvae_model_p2p_*).  Collective: every rank creates its
-        model at the same point.  torch.distributed (gloo) only carries the 128 handle bytes."""
+        model at the same point.  torch.distributed (gloo) only carries the 384 handle bytes."""
         comm = self.comm
         if comm is None or getattr(comm, "h", None) is None or comm.nranks < 2 or comm.nranks > 8:
             return
-        # measured (cfg2 step): 2 GPUs 0.686 ms peer-to-peer vs 0.702 ms NCCL; 8 GPUs 0.80 vs 0.77 ms (every rank
-        # reads all eight buffers; NCCL reduces in the switch) -> default on for two ranks only, PGMVAE_P2P=0/1 overrides
-        want = os.environ.get("PGMVAE_P2P")
-        if want == "0" or (want != "1" and comm.nranks != 2):
+        # Which exchanges use the mapping is the library's decision (pgmvae_model_p2p_import): narrow models (chain kernels)
+        # sum the whole gradient buffer peer-to-peer at two ranks only (measured, cfg2 step: 0.686 vs 0.702 ms NCCL at 2
+        # GPUs, 0.80 vs 0.77 ms at 8, where every rank reads all eight buffers); wide models (per-group path) run the
+        # SHARDED exchange fused with Adam at any rank count.  PGMVAE_P2P=0: no mapping, NCCL everywhere.
+        if os.environ.get("PGMVAE_P2P") == "0":
             return
         import socket
         import torch.distributed as dist
         lib = _ffi.lib()
-        nbytes = 128
+        nbytes = 384
         # every rank must sit on the same host with peer access between all devices; otherwise (two nodes, GPUs
         # without NVLink / PCIe peer access) the NCCL path is the one that works.  The decision is collective.
         infos = [None] * comm.nranks
@@ -205,6 +206,12 @@ class VqVAE:
         _ffi.check(_ffi.lib().pgmvae_model_set_tensor(self._h, name.encode(), v.ctypes.data, v.size))
 
     def state_dict(self) -> Dict[str, np.ndarray]:
+        """Every tensor in the reference layouts + the Adam moments.  After data-parallel steps with the sharded
+        peer-to-peer exchange the moments live with the rank that owns a shard: the gather that completes them is
+        COLLECTIVE, so there state_dict() / save_weights() must be called on every rank."""
+        lib = _ffi.lib()
+        if lib.pgmvae_model_p2p_moments_sharded(self._h):
+            _ffi.check(lib.pgmvae_model_p2p_sync_moments(self._h))
         sd = {n: self._get_tensor(n) for n in self.tensor_names()}
         train = [f"fd{i}.{s}" for i in range(10) for s in ("kernel", "bias")] + ([] if self.ema else ["vq.embeddings"])
         for n in train:

@@ -1,5 +1,6 @@
 // Context, memory and error plumbing of the C-ABI (include/pgmvae.h).
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -45,6 +46,21 @@ int pgmvae_ctx_profile_end(pgmvae_ctx* ctx, char* json_out, size_t cap) {
     PG_CUDA(cudaDeviceSynchronize());
     struct Agg { std::string name; long n; double ms, bytes, flops; };
     std::vector<Agg> agg;
+    // PGMVAE_PROF_TIMELINE=<prefix> (file <prefix>.dev<device>.csv): every launch with its stream and its start / end relative to the first one (the
+    // overlap of the communication stream with the compute stream is read from this)
+    if (const char* path = getenv("PGMVAE_PROF_TIMELINE")) {
+        const std::string file = std::string(path) + ".dev" + std::to_string(ctx->device) + ".csv";
+        if (FILE* f = ctx->prof.empty() ? nullptr : fopen(file.c_str(), "a")) {
+            fprintf(f, "name,stream,start_ms,end_ms\n");
+            for (pg_prof_rec& r : ctx->prof) {
+                float t0 = 0.f, t1 = 0.f;
+                cudaEventElapsedTime(&t0, ctx->prof[0].e0, r.e0);
+                cudaEventElapsedTime(&t1, ctx->prof[0].e0, r.e1);
+                fprintf(f, "%s,%p,%.4f,%.4f\n", r.name, (void*)r.st, t0, t1);
+            }
+            fclose(f);
+        }
+    }
     for (pg_prof_rec& r : ctx->prof) {
         float ms = 0.f;
         cudaEventElapsedTime(&ms, r.e0, r.e1);

@@ -198,8 +198,10 @@ __device__ __forceinline__ void decode_tile(const Bf16P& p, int pt, int crank, i
 
 // CTA2: the instantiation that contains the cta_group::2 instructions (pair == 3).  It is a separate kernel because a
 // kernel holding such instructions can only be launched as clusters of CTA pairs ("cluster misconfiguration" otherwise).
+// 144 registers x 384 threads and 3 KB of shared memory less than the maximum leave room on every SM for one CTA of
+// the data-parallel exchange kernel (model.cu: p2p_shard_adam_kernel, 128 threads x 80 registers) NEXT TO this one.
 template <int EPI, bool CTA2>
-__global__ void __launch_bounds__(THREADS, 1)
+__global__ void __maxnreg__(144)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                  const __grid_constant__ EpiMaps em, const __grid_constant__ Bf16P p) {
     extern __shared__ uint8_t smem_raw[];
@@ -906,7 +908,8 @@ int launch(pgmvae_ctx* ctx, cudaStream_t st, Bf16P& p, const Operand& A, const O
     p.out_db = EPI == EPI_DGRAD && p.tma_in && p.kblocks <= 8;
     const size_t fixed = 1024 + 256 + (staged ? 2 * (size_t)(p.out_db ? STG_WG4 : STG_WG) : 0) + (p.ones ? ONES_BYTES : 0) +
                          2 * ACC_COLS * sizeof(float);
-    int stages = (int)((ctx->smem_optin - fixed) / stage);
+    const size_t smem_cap = ctx->smem_optin - 3072;                 // (room for a co-resident exchange CTA, see the kernel)
+    int stages = (int)((smem_cap - fixed) / stage);
     if (stages > MAX_STAGES) stages = MAX_STAGES;
     if (const char* ev = getenv("PGMVAE_BF16_STAGES")) stages = std::max(2, std::min(stages, atoi(ev)));   // (experiments)
     if (stages < 2) {

@@ -142,6 +142,212 @@ __global__ void p2p_wait_done_kernel(const int* my_flags, int R, int step, int* 
     }
 }
 
+// ---- sharded peer-to-peer exchange fused with Adam (wide models: one launch per variable group) ----------------------
+// The reduce-scatter + optimiser + all-gather of a data-parallel step as ONE kernel over peer memory (NVLink /
+// NVSwitch): rank r OWNS the variables [v_lo, v_hi) of the group.  For its shard of every gradient slice (20 dense
+// slices per group, + the codebook gradient without EMA) it reads the R partial gradients straight from the peers'
+// HBM, sums them in rank order, applies the Keras-form Adam update to ITS fp32 master weights and moments, and writes
+// what the other ranks compute with into the buffers of ALL ranks: the bf16 mirror of a kernel slice (bf16 mode; the
+// fp32 master of a kernel stays with its owner until pgmvae_model_p2p_sync_state), the fp32 values of everything else
+// (biases, fp32 / tf32 models, the codebook).  Per kernel parameter a rank moves 4 (R-1)/R bytes in and 2 (R-1)/R
+// bytes out over NVLink (an all-reduce moves 8 (R-1)/R each way) and runs 1/R of the optimiser's HBM traffic.
+// The CTAs are small (128 threads, 80 registers, no dynamic shared memory) so that one of them fits on every SM NEXT
+// TO the resident CTA of the persistent GEMM / VQ kernels of the following group: the exchange takes issue slots and
+// memory bandwidth, not SMs, from the compute it overlaps.
+// Flag words (ints of the 256-byte block): [0,16) the whole-buffer exchange above; [16,24) ready2[q]: rank q's
+// gradients of exchange `seq` are complete; [24,32) done2[q]: rank q has read this rank's gradients and written its
+// shard of the parameters for exchange `seq`; [32,40) the barrier of the on-demand gather of the sharded state.
+enum { SHARD_F32_ALL = 0, SHARD_BF16_ALL = 1, SHARD_BOTH_ALL = 2 };
+struct ShardSlice { long long off, per_var; int mode; };
+struct P2pShardArgs {
+    float* const* peer_grads; float* const* peer_params; __nv_bfloat16* const* peer_wb; int* const* peer_flags; int* my_flags;
+    float *m, *v;
+    int rank, R, seq, nslices;
+    long long v_lo, v_hi;
+    ShardSlice s[24];
+    float alpha, omb1, omb2, eps;
+    unsigned int* counter; int* err;
+};
+constexpr int P2P_SHARD_THREADS = 128;
+enum { P2P_READY2 = 16, P2P_DONE2 = 24, P2P_READY3 = 32 };
+
+// The exchange streams GBs per group through an L2 that the GEMMs it runs next to rely on for their operand re-reads:
+// every access carries an evict-first policy (and stays out of L1).
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ float4 ld_stream_f4(const float4* p, uint64_t pol) {
+    float4 v;
+    asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(pol) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_stream_f4(float4* p, const float4& v, uint64_t pol) {
+    asm volatile("st.global.L1::no_allocate.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;"
+                 :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void st_stream_u2(uint2* p, const uint2& v, uint64_t pol) {
+    asm volatile("st.global.L1::no_allocate.L2::cache_hint.v2.b32 [%0], {%1, %2}, %3;" :: "l"(p), "r"(v.x), "r"(v.y), "l"(pol) : "memory");
+}
+
+// RMAX >= R ranks, U elements of 16 bytes per thread in flight from every rank (RMAX * U = 8 loads: few ranks need the
+// deeper unroll to cover the NVLink latency with one small CTA per SM)
+template <int RMAX, int U>
+__global__ void __maxnreg__(80) p2p_shard_adam_kernel(const __grid_constant__ P2pShardArgs a) {
+    __shared__ float* sg[8];
+    __shared__ float* sp[8];
+    __shared__ __nv_bfloat16* sw[8];
+    __shared__ int ok;
+    const int tid = threadIdx.x;
+    if (tid < a.R) {
+        sg[tid] = a.peer_grads[tid];
+        sp[tid] = a.peer_params[tid];
+        sw[tid] = a.peer_wb ? a.peer_wb[tid] : nullptr;
+    }
+    if (blockIdx.x == 0 && tid < a.R) {
+        __threadfence_system();
+        *reinterpret_cast<volatile int*>(a.peer_flags[tid] + P2P_READY2 + a.rank) = a.seq;
+    }
+    if (tid == 0) {
+        int good = 1;
+        for (int q = 0; q < a.R && good; ++q) {
+            long long spins = 0;
+            while (ld_volatile_i32(a.my_flags + P2P_READY2 + q) < a.seq) {
+                if (++spins > 100000000ll) { good = 0; break; }
+                __nanosleep(200);
+            }
+        }
+        __threadfence_system();
+        ok = good;
+    }
+    __syncthreads();
+    if (!ok) {
+        if (tid == 0) *reinterpret_cast<volatile int*>(a.err) = 1;
+        return;
+    }
+    const long long nthreads = (long long)gridDim.x * blockDim.x;
+    const long long gt = (long long)blockIdx.x * blockDim.x + tid;
+    float* const pl = sp[a.rank];
+    const uint64_t pol = l2_evict_first_policy();
+    for (int si = 0; si < a.nslices; ++si) {
+        const long long base4 = (a.s[si].off + a.v_lo * a.s[si].per_var) >> 2;
+        const long long cnt4 = ((a.v_hi - a.v_lo) * a.s[si].per_var) >> 2;
+        const bool f32_all = a.s[si].mode != SHARD_BF16_ALL, bf16_all = a.s[si].mode != SHARD_F32_ALL;
+        for (long long i0 = gt; i0 < cnt4; i0 += nthreads * U) {
+            float4 t[U][RMAX];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const long long e = base4 + i0 + u * nthreads;
+                if (i0 + u * nthreads < cnt4) {
+#pragma unroll
+                    for (int q = 0; q < RMAX; ++q)
+                        if (q < a.R) t[u][q] = ld_stream_f4(reinterpret_cast<const float4*>(sg[q]) + e, pol);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const long long e = base4 + i0 + u * nthreads;
+                if (i0 + u * nthreads >= cnt4) break;
+                float4 pp = ld_stream_f4(reinterpret_cast<const float4*>(pl) + e, pol);
+                float4 mm = ld_stream_f4(reinterpret_cast<const float4*>(a.m) + e, pol);
+                float4 vv = ld_stream_f4(reinterpret_cast<const float4*>(a.v) + e, pol);
+                float4 gg = t[u][0];
+#pragma unroll
+                for (int q = 1; q < RMAX; ++q)
+                    if (q < a.R) { gg.x += t[u][q].x; gg.y += t[u][q].y; gg.z += t[u][q].z; gg.w += t[u][q].w; }
+#define PG_ADAM1(c)                                          \
+                mm.c += (gg.c - mm.c) * a.omb1;              \
+                vv.c += (gg.c * gg.c - vv.c) * a.omb2;       \
+                pp.c -= (mm.c * a.alpha) / (sqrtf(vv.c) + a.eps);
+                PG_ADAM1(x) PG_ADAM1(y) PG_ADAM1(z) PG_ADAM1(w)
+#undef PG_ADAM1
+                st_stream_f4(reinterpret_cast<float4*>(a.m) + e, mm, pol);
+                st_stream_f4(reinterpret_cast<float4*>(a.v) + e, vv, pol);
+                const __nv_bfloat162 lo = __floats2bfloat162_rn(pp.x, pp.y), hi = __floats2bfloat162_rn(pp.z, pp.w);
+                const uint2 pk = make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
+                if (!f32_all) st_stream_f4(reinterpret_cast<float4*>(pl) + e, pp, pol);      // the master stays with its owner
+#pragma unroll
+                for (int q = 0; q < RMAX; ++q)
+                    if (q < a.R) {
+                        if (f32_all) st_stream_f4(reinterpret_cast<float4*>(sp[q]) + e, pp, pol);
+                        if (bf16_all) st_stream_u2(reinterpret_cast<uint2*>(sw[q]) + e, pk, pol);
+                    }
+            }
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (tid == 0) {
+        if (atomicAdd(a.counter, 1u) == gridDim.x - 1) {           // last block: every read and write of the peers is done
+            *a.counter = 0u;
+            __threadfence_system();
+            for (int q = 0; q < a.R; ++q)
+                *reinterpret_cast<volatile int*>(a.peer_flags[q] + P2P_DONE2 + a.rank) = a.seq;
+        }
+    }
+}
+
+// wait until every rank has posted `seq` in the flag words flags[0..R)
+__global__ void p2p_wait_flags_kernel(const int* flags, int R, int seq, int* err) {
+    if ((int)threadIdx.x < R) {
+        long long spins = 0;
+        while (ld_volatile_i32(flags + threadIdx.x) < seq) {
+            if (++spins > 100000000ll) { *reinterpret_cast<volatile int*>(err) = 1; break; }
+            __nanosleep(200);
+        }
+        __threadfence_system();
+    }
+}
+
+// The moments (and, in bf16 mode, the fp32 master of the kernels) live with the owner of a shard; checkpoints and
+// the fp32 readers want them everywhere: every rank writes its shards into the buffers of all peers (on demand:
+// pgmvae_model_p2p_sync_state)
+struct P2pStateArgs {
+    float* const* peer_p; float* const* peer_m; float* const* peer_v;
+    int rank, R, nslices;
+    long long v_lo, v_hi;
+    ShardSlice s[24];
+};
+__global__ void __launch_bounds__(256) p2p_push_state_kernel(const __grid_constant__ P2pStateArgs a) {
+    const long long nthreads = (long long)gridDim.x * blockDim.x;
+    const long long gt = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const float* pl = a.peer_p[a.rank];
+    const float* ml = a.peer_m[a.rank];
+    const float* vl = a.peer_v[a.rank];
+    for (int si = 0; si < a.nslices; ++si) {
+        const long long base4 = (a.s[si].off + a.v_lo * a.s[si].per_var) >> 2;
+        const long long cnt4 = ((a.v_hi - a.v_lo) * a.s[si].per_var) >> 2;
+        const bool push_p = a.s[si].mode == SHARD_BF16_ALL;
+        for (long long i = gt; i < cnt4; i += nthreads) {
+            const float4 mm = reinterpret_cast<const float4*>(ml)[base4 + i];
+            const float4 vv = reinterpret_cast<const float4*>(vl)[base4 + i];
+            float4 pp = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (push_p) pp = reinterpret_cast<const float4*>(pl)[base4 + i];
+            for (int q = 0; q < a.R; ++q) {
+                if (q == a.rank) continue;
+                reinterpret_cast<float4*>(a.peer_m[q])[base4 + i] = mm;
+                reinterpret_cast<float4*>(a.peer_v[q])[base4 + i] = vv;
+                if (push_p) reinterpret_cast<float4*>(a.peer_p[q])[base4 + i] = pp;
+            }
+        }
+    }
+}
+// every earlier write of this stream to the peers is complete (kernel boundary): tell them, and wait for theirs
+__global__ void p2p_barrier_kernel(int* const* peer_flags, const int* my_flags, int word, int rank, int R, int seq, int* err) {
+    if ((int)threadIdx.x < R) {
+        __threadfence_system();
+        *reinterpret_cast<volatile int*>(peer_flags[threadIdx.x] + word + rank) = seq;
+        long long spins = 0;
+        while (ld_volatile_i32(my_flags + word + threadIdx.x) < seq) {
+            if (++spins > 100000000ll) { *reinterpret_cast<volatile int*>(err) = 1; break; }
+            __nanosleep(200);
+        }
+        __threadfence_system();
+    }
+}
+
 }  // namespace
 
 struct pgmvae_model {
@@ -185,6 +391,11 @@ struct pgmvae_model {
     unsigned int* p2p_counter = nullptr;
     int* p2p_err = nullptr;            // pinned host word: a peer barrier timed out
     std::vector<void*> ipc_opened;
+    // sharded exchange (wide models): the peers' parameter / mirror / moment buffers as well
+    bool p2p_chain = false, p2p_shard = false, state_sharded = false;
+    int p2p_seq = 0, p2p_seq3 = 0;
+    float **peer_params = nullptr, **peer_m = nullptr, **peer_v = nullptr;
+    __nv_bfloat16** peer_wb = nullptr;
     // stage 2 (count) walks the data in slabs larger than the training batch: nothing but codes and counts
     // leaves the SM, so the slab only needs its own copy of the data (uint8 + fp32)
     uint8_t* cnt_y8 = nullptr; float* cnt_yf = nullptr; int cnt_rows = 0;
@@ -400,6 +611,21 @@ int p2p_check(const pgmvae_model* m) {
         return PGMVAE_ENCCL;
     }
     return PGMVAE_OK;
+}
+
+// the parameter slices a variable group exchanges: per layer the kernel [V][pin][pout] and the bias [V][pout] (bf16
+// mirror at the same offsets in bf16 mode), and the codebook gradient when the codebook is trained by Adam.  Every
+// rank computes with the bf16 mirror of a kernel but with the fp32 values of a bias (and of everything in fp32 / tf32
+// mode): that decides what the owner of a shard hands to the other ranks.
+int shard_slices(const pgmvae_model* m, ShardSlice* s) {
+    int n = 0;
+    for (int l = 0; l < 10; ++l) {
+        const Layer& L = m->L[l];
+        s[n++] = ShardSlice{(long long)L.w_off, (long long)L.pin * L.pout, m->bf16 ? SHARD_BF16_ALL : SHARD_F32_ALL};
+        s[n++] = ShardSlice{(long long)L.b_off, (long long)L.pout, m->bf16 ? SHARD_BOTH_ALL : SHARD_F32_ALL};
+    }
+    if (!m->ema) s[n++] = ShardSlice{(long long)m->e_off, (long long)m->K * m->Dp, SHARD_F32_ALL};
+    return n;
 }
 
 bool use_chain(const pgmvae_model* m) {
@@ -748,7 +974,8 @@ int pgmvae_model_get_tensor(pgmvae_model* m, const char* name, float* host, int6
     return PGMVAE_OK;
 }
 
-/* handles_out: 2 x 64 bytes (cudaIpcMemHandle_t of the gradient buffer and of this rank's flag block) */
+/* handles_out: 6 x 64 bytes (cudaIpcMemHandle_t of the gradient buffer, this rank's flag block, the parameters, their
+ * bf16 mirror (zeros without one), and the two Adam moment buffers) */
 int pgmvae_model_p2p_export(pgmvae_model* m, void* handles_out) {
     PG_CHECK_ARG(m && handles_out);
     PG_CUDA(cudaSetDevice(m->ctx->device));
@@ -759,42 +986,93 @@ int pgmvae_model_p2p_export(pgmvae_model* m, void* handles_out) {
         *m->p2p_err = 0;
         PG_CUDA(cudaStreamSynchronize(m->ctx->stream));
     }
-    cudaIpcMemHandle_t h[2];
+    cudaIpcMemHandle_t h[6];
+    memset(h, 0, sizeof(h));
     PG_CUDA(cudaIpcGetMemHandle(&h[0], m->grads));
     PG_CUDA(cudaIpcGetMemHandle(&h[1], m->p2p_flags));
+    PG_CUDA(cudaIpcGetMemHandle(&h[2], m->params));
+    if (m->wb) PG_CUDA(cudaIpcGetMemHandle(&h[3], m->wb));
+    PG_CUDA(cudaIpcGetMemHandle(&h[4], m->adam_m));
+    PG_CUDA(cudaIpcGetMemHandle(&h[5], m->adam_v));
     memcpy(handles_out, h, sizeof(h));
     return PGMVAE_OK;
 }
 
-/* all_handles: nranks x 128 bytes in rank order (what every rank exported); at most 8 ranks on one node */
+/* all_handles: nranks x 384 bytes in rank order (what every rank exported); at most 8 ranks on one node */
 int pgmvae_model_p2p_import(pgmvae_model* m, int rank, int nranks, const void* all_handles) {
     PG_CHECK_ARG(m && all_handles && nranks >= 2 && nranks <= 8 && rank >= 0 && rank < nranks && m->p2p_flags);
     PG_CUDA(cudaSetDevice(m->ctx->device));
-    float* g[8]; int* f[8];
+    void* ptr[6][8];
+    void* own[6] = {m->grads, m->p2p_flags, m->params, m->wb, m->adam_m, m->adam_v};
     for (int q = 0; q < nranks; ++q) {
-        if (q == rank) { g[q] = m->grads; f[q] = m->p2p_flags; continue; }
-        cudaIpcMemHandle_t h[2];
+        if (q == rank) {
+            for (int k = 0; k < 6; ++k) ptr[k][q] = own[k];
+            continue;
+        }
+        cudaIpcMemHandle_t h[6];
         memcpy(h, (const char*)all_handles + (size_t)q * sizeof(h), sizeof(h));
-        void *pg = nullptr, *pf = nullptr;
-        PG_CUDA(cudaIpcOpenMemHandle(&pg, h[0], cudaIpcMemLazyEnablePeerAccess));
-        m->ipc_opened.push_back(pg);
-        PG_CUDA(cudaIpcOpenMemHandle(&pf, h[1], cudaIpcMemLazyEnablePeerAccess));
-        m->ipc_opened.push_back(pf);
-        g[q] = (float*)pg; f[q] = (int*)pf;
+        for (int k = 0; k < 6; ++k) {
+            ptr[k][q] = nullptr;
+            if (k == 3 && !m->wb) continue;
+            PG_CUDA(cudaIpcOpenMemHandle(&ptr[k][q], h[k], cudaIpcMemLazyEnablePeerAccess));
+            m->ipc_opened.push_back(ptr[k][q]);
+        }
     }
-    PG_TRY(dev_alloc(m, (void**)&m->peer_grads, 8 * sizeof(float*)));
-    PG_TRY(dev_alloc(m, (void**)&m->peer_flags, 8 * sizeof(int*)));
-    PG_CUDA(cudaMemcpyAsync(m->peer_grads, g, nranks * sizeof(float*), cudaMemcpyHostToDevice, m->ctx->stream));
-    PG_CUDA(cudaMemcpyAsync(m->peer_flags, f, nranks * sizeof(int*), cudaMemcpyHostToDevice, m->ctx->stream));
+    void** dst[6] = {(void**)&m->peer_grads, (void**)&m->peer_flags, (void**)&m->peer_params, (void**)&m->peer_wb,
+                     (void**)&m->peer_m, (void**)&m->peer_v};
+    for (int k = 0; k < 6; ++k) {
+        PG_TRY(dev_alloc(m, dst[k], 8 * sizeof(void*)));
+        PG_CUDA(cudaMemcpyAsync(*dst[k], ptr[k], nranks * sizeof(void*), cudaMemcpyHostToDevice, m->ctx->stream));
+    }
     PG_CUDA(cudaStreamSynchronize(m->ctx->stream));
-    m->p2p_rank = rank; m->p2p_n = nranks; m->p2p_step = 0; m->p2p = true;
+    m->p2p_rank = rank; m->p2p_n = nranks; m->p2p_step = 0; m->p2p_seq = 0; m->p2p_seq3 = 0; m->p2p = true;
+    // which exchanges use the mapping.  Narrow models (chain kernels, a few MB of gradients): the whole-buffer sum +
+    // Adam kernel, measured faster than NCCL at two ranks only (every rank reads every buffer); PGMVAE_P2P=1 forces it.
+    // Wide models (per-group path): the sharded exchange at any rank count; PGMVAE_P2P_SHARD=0 keeps NCCL there.
+    const char* want = getenv("PGMVAE_P2P");
+    m->p2p_chain = want ? atoi(want) == 1 : nranks == 2;
+    const char* ws = getenv("PGMVAE_P2P_SHARD");
+    m->p2p_shard = !(ws && atoi(ws) == 0);
     return PGMVAE_OK;
 }
 
 /* give up the peer-to-peer exchange (a rank could not map its peers): the NCCL path is used instead */
 int pgmvae_model_p2p_disable(pgmvae_model* m) {
     PG_CHECK_ARG(m != nullptr);
-    m->p2p = false;
+    m->p2p = false; m->p2p_chain = false; m->p2p_shard = false;
+    return PGMVAE_OK;
+}
+
+/* 1 when steps of the sharded exchange have left the Adam moments (and, in bf16 mode, the fp32 master of the dense
+ * kernels) complete only on the rank that owns a shard: sync_state() below completes them everywhere */
+int pgmvae_model_p2p_state_sharded(pgmvae_model* m) { return m && m->p2p && m->state_sharded ? 1 : 0; }
+
+/* COLLECTIVE over the ranks of the mapping: every rank writes its shards of the Adam moments (and fp32 master
+ * kernels) into the buffers of all peers; afterwards every tensor reads (get_tensor) complete on every rank */
+int pgmvae_model_p2p_sync_state(pgmvae_model* m) {
+    PG_CHECK_ARG(m != nullptr);
+    if (!m->p2p || !m->state_sharded) return PGMVAE_OK;
+    PG_TRY(p2p_check(m));
+    pgmvae_ctx* ctx = m->ctx;
+    cudaStream_t st = ctx->stream;
+    PG_CUDA(cudaSetDevice(ctx->device));
+    for (int g0 = 0; g0 < m->V; g0 += m->Vg) {
+        const int Gn = std::min(m->Vg, m->V - g0);
+        P2pStateArgs a{};
+        a.peer_p = m->peer_params; a.peer_m = m->peer_m; a.peer_v = m->peer_v; a.rank = m->p2p_rank; a.R = m->p2p_n;
+        a.v_lo = g0 + (long long)m->p2p_rank * Gn / m->p2p_n;
+        a.v_hi = g0 + (long long)(m->p2p_rank + 1) * Gn / m->p2p_n;
+        a.nslices = shard_slices(m, a.s);
+        if (a.v_hi <= a.v_lo) continue;
+        PG_KERNEL(ctx, st, "p2p_push_state", 0.0, 0.0);
+        p2p_push_state_kernel<<<ctx->sm_total * 2, 256, 0, st>>>(a);
+        PG_LAUNCHED(ctx);
+    }
+    p2p_barrier_kernel<<<1, 32, 0, st>>>(m->peer_flags, m->p2p_flags, P2P_READY3, m->p2p_rank, m->p2p_n, ++m->p2p_seq3, m->p2p_err);
+    PG_LAUNCHED(ctx);
+    PG_CUDA(cudaStreamSynchronize(st));
+    PG_TRY(p2p_check(m));
+    m->state_sharded = false;
     return PGMVAE_OK;
 }
 
@@ -850,6 +1128,18 @@ int run_step(pgmvae_model* m, const uint8_t* y, int y_on_device, int B, int glob
 
     const bool chain = use_chain(m) && out_dev == nullptr;
     bool overlapped = false, use_p2p = false, ema_done = false, ema_side = false;
+    const bool do_update = !(flags & (STEP_NO_UPDATE | STEP_FWD_ONLY));
+    const double b1 = 0.9, b2 = 0.999;
+    float alpha = 0.f;
+    if (do_update) {
+        m->adam_t += 1;
+        alpha = (float)((double)lr * sqrt(1.0 - pow(b2, (double)m->adam_t)) / (1.0 - pow(b1, (double)m->adam_t)));
+    }
+    // wide models under data parallelism on one node: per variable group, reduce-scatter + Adam + all-gather as one
+    // kernel over peer memory (p2p_shard_adam_kernel) instead of NCCL all-reduces followed by a replicated Adam
+    const bool use_shard = comm != nullptr && !chain && m->p2p && m->p2p_shard && do_update;
+    ShardSlice shard_s[24];
+    const int shard_n = use_shard ? shard_slices(m, shard_s) : 0;
     auto ema_update = [&](cudaStream_t es) -> int {
         if (ema_done || (flags & (STEP_NO_UPDATE | STEP_FWD_ONLY)) || !m->ema || (flags & STEP_NO_EMA)) return PGMVAE_OK;
         ema_done = true;
@@ -883,7 +1173,7 @@ int run_step(pgmvae_model* m, const uint8_t* y, int y_on_device, int B, int glob
         // single variable group under data parallelism: every exchange is issued as soon as its operand is
         // final and runs on the communication stream under the kernels that follow
         const bool overlap = comm != nullptr && Gn == V;
-        use_p2p = overlap && m->p2p && !(flags & (STEP_NO_UPDATE | STEP_FWD_ONLY));
+        use_p2p = overlap && m->p2p && m->p2p_chain && !(flags & (STEP_NO_UPDATE | STEP_FWD_ONLY));
         if (overlap) {      // EMA statistics + loss accumulators: one fused NCCL launch
             PG_TRY(pg_comm_group_begin(comm));
             PG_TRY(overlapped_allreduce(m, comm, m->acc, 4, 1));
@@ -1004,7 +1294,7 @@ int run_step(pgmvae_model* m, const uint8_t* y, int y_on_device, int B, int glob
         PG_CUDA(cudaEventRecord(m->ev_compute, st));
         PG_CUDA(cudaStreamWaitEvent(m->comm_stream, m->ev_compute, 0));
         PG_TRY(pg_comm_group_begin(comm));
-        if (!(flags & STEP_FWD_ONLY)) {
+        if (!(flags & STEP_FWD_ONLY) && !use_shard) {
             for (int l = 0; l < 10; ++l) {
                 const Layer& L = m->L[l];
                 PG_TRY(pg_comm_allreduce(comm, m->grads + L.w_off + (size_t)g0 * L.pin * L.pout, (int64_t)Gn * L.pin * L.pout, 0,
@@ -1020,6 +1310,46 @@ int run_step(pgmvae_model* m, const uint8_t* y, int y_on_device, int B, int glob
         }
         if (g0 + Gn >= V) PG_TRY(pg_comm_allreduce(comm, m->acc, 4, 1, m->comm_stream));      // loss accumulators: after the last group
         PG_TRY(pg_comm_group_end(comm));
+        // (measured at two GPUs: issuing the exchange BEFORE the NCCL launch -- so that it starts right at the group
+        // boundary -- is slower, 113 vs 109 ms per cfg3 step)
+        if (use_shard) {
+            P2pShardArgs a{};
+            a.peer_grads = m->peer_grads; a.peer_params = m->peer_params; a.peer_wb = m->bf16 ? m->peer_wb : nullptr;
+            a.peer_flags = m->peer_flags; a.my_flags = m->p2p_flags;
+            a.m = m->adam_m; a.v = m->adam_v;
+            a.rank = m->p2p_rank; a.R = m->p2p_n; a.seq = ++m->p2p_seq; a.nslices = shard_n;
+            a.v_lo = g0 + (long long)m->p2p_rank * Gn / m->p2p_n;
+            a.v_hi = g0 + (long long)(m->p2p_rank + 1) * Gn / m->p2p_n;
+            for (int i = 0; i < shard_n; ++i) a.s[i] = shard_s[i];
+            a.alpha = alpha; a.omb1 = (float)(1.0 - b1); a.omb2 = (float)(1.0 - b2); a.eps = 1e-7f;
+            a.counter = m->p2p_counter; a.err = m->p2p_err;
+            // algorithmic bytes per owned parameter: R gradient reads, p / m / v read and written locally, then 4 bytes
+            // (fp32) or 2 bytes (bf16 mirror of a kernel) to each of the other ranks
+            double bytes = 0.0, own = 0.0;
+            for (int i = 0; i < shard_n; ++i) {
+                const double n = (double)(a.v_hi - a.v_lo) * (double)shard_s[i].per_var;
+                const double out = shard_s[i].mode == SHARD_BF16_ALL ? 2.0 : (shard_s[i].mode == SHARD_BOTH_ALL ? 6.0 : 4.0);
+                bytes += n * (4.0 * m->p2p_n + 24.0 + out * m->p2p_n);
+                own += n;
+            }
+            PG_KERNEL(ctx, m->comm_stream, "p2p_shard_adam", bytes, (10.0 + m->p2p_n) * own);
+            // An SM holds ONE shared-memory configuration at a time: without this hint an exchange CTA that reaches an idle SM
+            // first leaves it at a small carve-out, and the GEMM CTA (224 KB) has to wait for it to finish.
+            static bool carve[16] = {};
+            if (!carve[ctx->device & 15]) {
+                PG_CUDA(cudaFuncSetAttribute(p2p_shard_adam_kernel<2, 4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+                PG_CUDA(cudaFuncSetAttribute(p2p_shard_adam_kernel<4, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+                PG_CUDA(cudaFuncSetAttribute(p2p_shard_adam_kernel<8, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+                carve[ctx->device & 15] = true;
+            }
+            int xg = ctx->sm_total;
+            if (const char* ev = getenv("PGMVAE_P2P_CTAS")) xg = std::max(1, atoi(ev));        // (tuning: CTAs of the exchange kernel)
+            if (m->p2p_n <= 2) p2p_shard_adam_kernel<2, 4><<<xg, P2P_SHARD_THREADS, 0, m->comm_stream>>>(a);
+            else if (m->p2p_n <= 4) p2p_shard_adam_kernel<4, 2><<<xg, P2P_SHARD_THREADS, 0, m->comm_stream>>>(a);
+            else p2p_shard_adam_kernel<8, 1><<<xg, P2P_SHARD_THREADS, 0, m->comm_stream>>>(a);
+            PG_LAUNCHED(ctx);
+            m->state_sharded = true;
+        }
         group_overlap = true;
         return PGMVAE_OK;
     };
@@ -1136,6 +1466,12 @@ int run_step(pgmvae_model* m, const uint8_t* y, int y_on_device, int B, int glob
         // every group's exchange has been issued; the optimiser and the codebook update wait for the last one
         PG_CUDA(cudaEventRecord(m->ev_comm, m->comm_stream));
         PG_CUDA(cudaStreamWaitEvent(st, m->ev_comm, 0));
+        if (use_shard) {
+            // ... and, sharded exchange: until every peer has written its shards of the new parameters into this rank's
+            // buffers and has read this rank's gradients (they are overwritten by the next step)
+            p2p_wait_flags_kernel<<<1, 32, 0, st>>>(m->p2p_flags + P2P_DONE2, m->p2p_n, m->p2p_seq, m->p2p_err);
+            PG_LAUNCHED(ctx);
+        }
     } else if (comm) {
         if (!(flags & STEP_FWD_ONLY)) PG_TRY(pg_comm_allreduce(comm, m->grads, (int64_t)trainable, 0, st));
         if (m->ema && !(flags & STEP_NO_EMA)) {
@@ -1145,10 +1481,7 @@ int run_step(pgmvae_model* m, const uint8_t* y, int y_on_device, int B, int glob
         PG_TRY(pg_comm_allreduce(comm, m->acc, 4, 1, st));
     }
 
-    if (!(flags & (STEP_NO_UPDATE | STEP_FWD_ONLY))) {
-        m->adam_t += 1;
-        const double b1 = 0.9, b2 = 0.999;
-        const float alpha = (float)((double)lr * sqrt(1.0 - pow(b2, (double)m->adam_t)) / (1.0 - pow(b1, (double)m->adam_t)));
+    if (do_update && !use_shard) {
         if (use_p2p) {
             P2pArgs a{};
             a.peer_grads = m->peer_grads; a.peer_flags = m->peer_flags; a.my_flags = m->p2p_flags;

@@ -214,8 +214,10 @@ __device__ __forceinline__ float quantize_row(const Vq16P& p, int g, int row, co
     return part;
 }
 
+// (16 warps x 104 registers: one CTA of the data-parallel exchange kernel -- model.cu: p2p_shard_adam_kernel, 4 warps x
+// 80 registers -- fits on the SM next to this one)
 template <int SUB>
-__global__ void __launch_bounds__(Cfg<SUB>::THREADS, 1)
+__global__ void __maxnreg__(SUB == 3 ? 104 : 128)
 vq_assign_f16_kernel(const __grid_constant__ CUtensorMap mapE, const Vq16P p) {
     using C = Cfg<SUB>;
     extern __shared__ uint8_t smem_raw[];

@@ -3,7 +3,7 @@
         pgm-vae_b200/tools/dp_check.py
 Every rank trains on its share of each global batch through the data-parallel path of libpgmvae.so (NCCL all-reduce
 of gradients, EMA statistics and loss accumulators, overlapped with compute; peer-to-peer exchange fused with Adam
-at two ranks); rank 0 then replays the same global batches on ONE GPU and the two runs must agree: losses, weights,
+at two ranks; per-group sharded peer-to-peer exchange fused with Adam for wide models); rank 0 then replays the same global batches on ONE GPU and the two runs must agree: losses, weights,
 codebook, PLL counts (``dp_parity``).  ``main`` walks every schedule the library has: precision fp32 / tf32 (chain
 kernels, comm-stream overlap) / bf16 (layer-by-layer tensor-core path, several variable groups),
 PGMVAE_P2P in {0, 1}, PGMVAE_DP_BUCKETS in {0, 1}.  bench.py calls ``dp_parity`` on the benchmarked configuration
@@ -49,8 +49,23 @@ def dp_parity(ctx, comm, rank, world, units, V, D, K, per_rank_batch, precision,
         m.dist = (n1 + 0.8) / (n1 + n0 + 1.6)
         pll_s = m.pseudo_log_likelihood(ye[lo:hi], total=len(ye))
         pll_v = m.pseudo_log_likelihood(ye, shard="variables")      # variable-sharded: one scalar crosses ranks
-        got = {n: m._get_tensor(n) for n in tensors} if rank == 0 else None
+        # (sharded peer-to-peer exchange: the Adam moments live with the owner of a shard until this collective gather)
+        lib = _ffi.lib()
+        sharded = bool(lib.pgmvae_model_p2p_moments_sharded(m._h))
+        if sharded:
+            _ffi.check(lib.pgmvae_model_p2p_sync_moments(m._h))
+        moments = ("adam_m.fd1.kernel", "adam_v.fd9.bias")
+        mine = {n: m._get_tensor(n) for n in tuple(tensors) + moments}
+        got = mine if rank == 0 else None
         emb = m._get_tensor("vq.embeddings") if rank == 0 else None
+        # the replicas must be bit-identical: compare a digest of every rank's tensors
+        import hashlib
+        digest = hashlib.sha1(b"".join(np.ascontiguousarray(mine[n]).tobytes() for n in sorted(mine))).hexdigest()
+        digests = [None] * world
+        if world > 1:
+            tdist.all_gather_object(digests, digest)
+        else:
+            digests = [digest]
         arith = int(_ffi.lib().pgmvae_model_arithmetic(m._h))
         groups = -(-V // m.group_size())
         del m
@@ -72,7 +87,9 @@ def dp_parity(ctx, comm, rank, world, units, V, D, K, per_rank_batch, precision,
                 "p2p": os.environ.get("PGMVAE_P2P", "default"), "buckets": os.environ.get("PGMVAE_DP_BUCKETS", "0"),
                 "loss_rel": float(np.abs(L[:, :3] - R[:, :3]).max() / np.abs(R[:, :3]).max()),
                 "vq_loss_rel": float((np.abs(L[:, 3] - R[:, 3]) / np.maximum(np.abs(R[:, 3]), 1e-30)).max()),
+                "sharded_exchange": sharded, "replicas_identical": len(set(digests)) == 1,
                 "weight_rel": max(_rel(got[n], ref._get_tensor(n)) for n in tensors),
+                "moment_rel": max(_rel(got[n], ref._get_tensor(n)) for n in moments),
                 "codebook_rel": _rel(emb, ref._get_tensor("vq.embeddings")),
                 "count_l1": float(np.abs(n1 - r1).sum() / max(r1.sum(), 1.0)),
                 "count_total_ok": bool((n1 + n0).sum() == len(ye) * V),
@@ -89,8 +106,10 @@ def dp_parity(ctx, comm, rank, world, units, V, D, K, per_rank_batch, precision,
 
 
 def check(res, tol=1e-3):
-    bad = [k for k in ("loss_rel", "weight_rel", "count_l1", "pll_rel_sample_sharded", "pll_rel_variable_sharded")
+    bad = [k for k in ("loss_rel", "weight_rel", "moment_rel", "count_l1", "pll_rel_sample_sharded", "pll_rel_variable_sharded")
            if not res[k] <= tol]
+    if not res["replicas_identical"]:
+        bad.append("replicas_identical")
     # a latent that sits within reduction-order rounding of a decision boundary may take the other code on one side,
     # which moves one code vector by ~(1 - decay) / (its size): a looser bar for the codebook maximum
     if not res["codebook_rel"] <= 10 * tol:
@@ -114,11 +133,20 @@ def main():
     cases.append((cfg2, "tf32", False, "0", "0", None))
     cases.append((cfg2, "bf16", False, "0", "0", None))
     for prec in ("tf32", "bf16"):
-        cases.append((wide, prec, True, "0", "0", "7"))      # several variable groups: per-group overlapped exchange
+        cases.append((wide, prec, True, "0", "0", "7"))      # several variable groups: per-group overlapped NCCL exchange
     cases.append((wide, "bf16", False, "0", "0", "5"))
+    if world <= 8:
+        # the same through the sharded peer-to-peer exchange fused with Adam (the default where the ranks can map
+        # each other): "d" = environment untouched
+        for prec in ("tf32", "bf16"):
+            cases.append((wide, prec, True, "d", "0", "7"))
+        cases.append((wide, "bf16", False, "d", "0", "5"))
     failed = 0
     for (units, V, D, K, prb), prec, ema, p2p, buckets, gv in cases:
-        os.environ["PGMVAE_P2P"] = p2p
+        if p2p == "d":
+            os.environ.pop("PGMVAE_P2P", None)
+        else:
+            os.environ["PGMVAE_P2P"] = p2p
         if buckets == "1":
             os.environ["PGMVAE_DP_BUCKETS"] = "1"
         else:
