@@ -272,19 +272,20 @@ int pgmvae_model_set_adam_step(pgmvae_model* m, int64_t t);
  *   narrow models (one variable group, chain kernels): ONE kernel per rank reads the gradient buffers of all ranks
  *     over NVLink, sums them in rank order and applies the Adam update (two ranks by default; PGMVAE_P2P=1 forces it);
  *   wide models (per-group path): per variable group, reduce-scatter + Adam + all-gather as ONE kernel -- a rank sums
- *     ITS shard of the group's gradients from all peers, updates it and writes the new parameters (fp32 + bf16
- *     mirror) into every rank's buffers; the CTAs are small enough to run next to the GEMMs of the following group
+ *     ITS shard of the group's gradients from all peers, updates it and writes what the other ranks compute with
+ *     (the bf16 mirror of a kernel; fp32 biases / fp32-mode parameters) into every rank's buffers; the CTAs are small enough to run next to the GEMMs of the following group
  *     (any rank count up to 8; PGMVAE_P2P_SHARD=0 keeps NCCL).  The replicas stay bit-identical either way.
  * export: writes 6 x 64 bytes (CUDA IPC handles: gradients, flag block, parameters, bf16 mirror, Adam m, Adam v);
  * the host exchanges them (any side channel) and passes all of them, in rank order, to import.  Optional: without
  * it pgmvae_model_train_step reduces the gradients through the communicator.                                  */
 int pgmvae_model_p2p_export(pgmvae_model* m, void* handles_out384);
 int pgmvae_model_p2p_import(pgmvae_model* m, int rank, int nranks, const void* all_handles);
-/* After steps of the sharded exchange the Adam moments are complete only on the rank that owns a shard
- * (moments_sharded() == 1); sync_moments() -- COLLECTIVE over the ranks of the mapping -- completes them everywhere
- * (before get_tensor("adam_m.*") / a checkpoint). */
-int pgmvae_model_p2p_moments_sharded(pgmvae_model* m);
-int pgmvae_model_p2p_sync_moments(pgmvae_model* m);
+/* After steps of the sharded exchange the Adam moments -- and, in bf16 mode, the fp32 master copy of the dense
+ * kernels (every rank computes with their bf16 mirror, which IS exchanged) -- are complete only on the rank that owns
+ * a shard (state_sharded() == 1); sync_state() -- COLLECTIVE over the ranks of the mapping -- completes them
+ * everywhere (before get_tensor / a checkpoint / the fp32 readers such as the Gibbs sampler; fit() ends with it). */
+int pgmvae_model_p2p_state_sharded(pgmvae_model* m);
+int pgmvae_model_p2p_sync_state(pgmvae_model* m);
 /* turn the peer-to-peer exchange off again (a rank failed to map its peers): NCCL is used instead */
 int pgmvae_model_p2p_disable(pgmvae_model* m);
 /* cudaDeviceCanAccessPeer(device, peer): whether the CUDA-IPC mapping behind pgmvae_model_p2p_import can work */

@@ -206,12 +206,11 @@ class VqVAE:
         _ffi.check(_ffi.lib().pgmvae_model_set_tensor(self._h, name.encode(), v.ctypes.data, v.size))
 
     def state_dict(self) -> Dict[str, np.ndarray]:
-        """Every tensor in the reference layouts + the Adam moments.  After data-parallel steps with the sharded
-        peer-to-peer exchange the moments live with the rank that owns a shard: the gather that completes them is
-        COLLECTIVE, so there state_dict() / save_weights() must be called on every rank."""
-        lib = _ffi.lib()
-        if lib.pgmvae_model_p2p_moments_sharded(self._h):
-            _ffi.check(lib.pgmvae_model_p2p_sync_moments(self._h))
+        """Every tensor in the reference layouts + the Adam moments.  After data-parallel train_on_batch() steps with the
+        sharded peer-to-peer exchange the moments and the fp32 master kernels live with the rank that owns a shard: the
+        gather that completes them (sync_state) is COLLECTIVE, so there state_dict() / save_weights() must be called on
+        every rank.  fit() ends with that gather."""
+        self.sync_state()
         sd = {n: self._get_tensor(n) for n in self.tensor_names()}
         train = [f"fd{i}.{s}" for i in range(10) for s in ("kernel", "bias")] + ([] if self.ema else ["vq.embeddings"])
         for n in train:
@@ -220,6 +219,13 @@ class VqVAE:
         sd["_adam_t"] = np.int64(self._adam_t)
         sd["_ema_steps"] = np.int64(self._ema_steps)
         return sd
+
+    def sync_state(self):
+        """COLLECTIVE under data parallelism with the sharded exchange (no-op otherwise): complete the optimiser state
+        and the fp32 master weights on every rank (pgmvae_model_p2p_sync_state)."""
+        lib = _ffi.lib()
+        if lib.pgmvae_model_p2p_state_sharded(self._h):
+            _ffi.check(lib.pgmvae_model_p2p_sync_state(self._h))
 
     def load_state_dict(self, sd: Dict[str, np.ndarray]):
         for n, v in sd.items():
@@ -385,6 +391,7 @@ class VqVAE:
             for cb in (callbacks or []):
                 if hasattr(cb, "on_epoch_end"):
                     cb.on_epoch_end(ep, {"loss": sums[0] / seen, "mae": sums[1] / seen})
+        self.sync_state()      # (data parallel, sharded exchange: every rank leaves fit() with the complete model)
         return hist
 
     # ---- stage 2 ---------------------------------------------------------------------

@@ -93,8 +93,8 @@ SIGNATURES = {
     "pgmvae_model_p2p_export": (_i, [_vp, _vp]),
     "pgmvae_model_p2p_import": (_i, [_vp, _i, _i, _vp]),
     "pgmvae_model_p2p_disable": (_i, [_vp]),
-    "pgmvae_model_p2p_moments_sharded": (_i, [_vp]),
-    "pgmvae_model_p2p_sync_moments": (_i, [_vp]),
+    "pgmvae_model_p2p_state_sharded": (_i, [_vp]),
+    "pgmvae_model_p2p_sync_state": (_i, [_vp]),
     "pgmvae_ctx_reserve_sms": (_i, [_vp, _i]),
     "pgmvae_device_can_access_peer": (_i, [_i, _i, _vp]),
     "pgmvae_model_train_step": (_i, [_vp, _vp, _i, _i, _i, _f, _vp, _i, _vp]),

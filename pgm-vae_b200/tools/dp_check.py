@@ -49,11 +49,12 @@ def dp_parity(ctx, comm, rank, world, units, V, D, K, per_rank_batch, precision,
         m.dist = (n1 + 0.8) / (n1 + n0 + 1.6)
         pll_s = m.pseudo_log_likelihood(ye[lo:hi], total=len(ye))
         pll_v = m.pseudo_log_likelihood(ye, shard="variables")      # variable-sharded: one scalar crosses ranks
-        # (sharded peer-to-peer exchange: the Adam moments live with the owner of a shard until this collective gather)
+        # (sharded peer-to-peer exchange: the Adam moments and fp32 master kernels live with the owner of a shard until this
+        # collective gather)
         lib = _ffi.lib()
-        sharded = bool(lib.pgmvae_model_p2p_moments_sharded(m._h))
+        sharded = bool(lib.pgmvae_model_p2p_state_sharded(m._h))
         if sharded:
-            _ffi.check(lib.pgmvae_model_p2p_sync_moments(m._h))
+            _ffi.check(lib.pgmvae_model_p2p_sync_state(m._h))
         moments = ("adam_m.fd1.kernel", "adam_v.fd9.bias")
         mine = {n: m._get_tensor(n) for n in tuple(tensors) + moments}
         got = mine if rank == 0 else None
