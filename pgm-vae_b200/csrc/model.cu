@@ -192,8 +192,8 @@ __device__ __forceinline__ void st_stream_u2(uint2* p, const uint2& v, uint64_t 
     asm volatile("st.global.L1::no_allocate.L2::cache_hint.v2.b32 [%0], {%1, %2}, %3;" :: "l"(p), "r"(v.x), "r"(v.y), "l"(pol) : "memory");
 }
 
-// RMAX >= R ranks, U elements of 16 bytes per thread in flight from every rank (RMAX * U = 8 loads: few ranks need the
-// deeper unroll to cover the NVLink latency with one small CTA per SM)
+// RMAX >= R ranks, U elements of 16 bytes per thread and source in flight ((RMAX + 3) * U loads of 16 bytes: gradients of
+// every rank, parameter, two moments; two ranks take the deeper unroll)
 template <int RMAX, int U>
 __global__ void __maxnreg__(80) p2p_shard_adam_kernel(const __grid_constant__ P2pShardArgs a) {
     __shared__ float* sg[8];
@@ -236,7 +236,8 @@ __global__ void __maxnreg__(80) p2p_shard_adam_kernel(const __grid_constant__ P2
         const long long cnt4 = ((a.v_hi - a.v_lo) * a.s[si].per_var) >> 2;
         const bool f32_all = a.s[si].mode != SHARD_BF16_ALL, bf16_all = a.s[si].mode != SHARD_F32_ALL;
         for (long long i0 = gt; i0 < cnt4; i0 += nthreads * U) {
-            float4 t[U][RMAX];
+            // every load of the U elements goes out before the first use: one round trip per iteration, not one per source
+            float4 t[U][RMAX], pp[U], mm[U], vv[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const long long e = base4 + i0 + u * nthreads;
@@ -244,34 +245,34 @@ __global__ void __maxnreg__(80) p2p_shard_adam_kernel(const __grid_constant__ P2
 #pragma unroll
                     for (int q = 0; q < RMAX; ++q)
                         if (q < a.R) t[u][q] = ld_stream_f4(reinterpret_cast<const float4*>(sg[q]) + e, pol);
+                    pp[u] = ld_stream_f4(reinterpret_cast<const float4*>(pl) + e, pol);
+                    mm[u] = ld_stream_f4(reinterpret_cast<const float4*>(a.m) + e, pol);
+                    vv[u] = ld_stream_f4(reinterpret_cast<const float4*>(a.v) + e, pol);
                 }
             }
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const long long e = base4 + i0 + u * nthreads;
                 if (i0 + u * nthreads >= cnt4) break;
-                float4 pp = ld_stream_f4(reinterpret_cast<const float4*>(pl) + e, pol);
-                float4 mm = ld_stream_f4(reinterpret_cast<const float4*>(a.m) + e, pol);
-                float4 vv = ld_stream_f4(reinterpret_cast<const float4*>(a.v) + e, pol);
                 float4 gg = t[u][0];
 #pragma unroll
                 for (int q = 1; q < RMAX; ++q)
                     if (q < a.R) { gg.x += t[u][q].x; gg.y += t[u][q].y; gg.z += t[u][q].z; gg.w += t[u][q].w; }
-#define PG_ADAM1(c)                                          \
-                mm.c += (gg.c - mm.c) * a.omb1;              \
-                vv.c += (gg.c * gg.c - vv.c) * a.omb2;       \
-                pp.c -= (mm.c * a.alpha) / (sqrtf(vv.c) + a.eps);
+#define PG_ADAM1(c)                                                \
+                mm[u].c += (gg.c - mm[u].c) * a.omb1;              \
+                vv[u].c += (gg.c * gg.c - vv[u].c) * a.omb2;       \
+                pp[u].c -= (mm[u].c * a.alpha) / (sqrtf(vv[u].c) + a.eps);
                 PG_ADAM1(x) PG_ADAM1(y) PG_ADAM1(z) PG_ADAM1(w)
 #undef PG_ADAM1
-                st_stream_f4(reinterpret_cast<float4*>(a.m) + e, mm, pol);
-                st_stream_f4(reinterpret_cast<float4*>(a.v) + e, vv, pol);
-                const __nv_bfloat162 lo = __floats2bfloat162_rn(pp.x, pp.y), hi = __floats2bfloat162_rn(pp.z, pp.w);
+                st_stream_f4(reinterpret_cast<float4*>(a.m) + e, mm[u], pol);
+                st_stream_f4(reinterpret_cast<float4*>(a.v) + e, vv[u], pol);
+                const __nv_bfloat162 lo = __floats2bfloat162_rn(pp[u].x, pp[u].y), hi = __floats2bfloat162_rn(pp[u].z, pp[u].w);
                 const uint2 pk = make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
-                if (!f32_all) st_stream_f4(reinterpret_cast<float4*>(pl) + e, pp, pol);      // the master stays with its owner
+                if (!f32_all) st_stream_f4(reinterpret_cast<float4*>(pl) + e, pp[u], pol);      // the master stays with its owner
 #pragma unroll
                 for (int q = 0; q < RMAX; ++q)
                     if (q < a.R) {
-                        if (f32_all) st_stream_f4(reinterpret_cast<float4*>(sp[q]) + e, pp, pol);
+                        if (f32_all) st_stream_f4(reinterpret_cast<float4*>(sp[q]) + e, pp[u], pol);
                         if (bf16_all) st_stream_u2(reinterpret_cast<uint2*>(sw[q]) + e, pk, pol);
                     }
             }
@@ -1337,15 +1338,15 @@ int run_step(pgmvae_model* m, const uint8_t* y, int y_on_device, int B, int glob
             // first leaves it at a small carve-out, and the GEMM CTA (224 KB) has to wait for it to finish.
             static bool carve[16] = {};
             if (!carve[ctx->device & 15]) {
-                PG_CUDA(cudaFuncSetAttribute(p2p_shard_adam_kernel<2, 4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-                PG_CUDA(cudaFuncSetAttribute(p2p_shard_adam_kernel<4, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+                PG_CUDA(cudaFuncSetAttribute(p2p_shard_adam_kernel<2, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+                PG_CUDA(cudaFuncSetAttribute(p2p_shard_adam_kernel<4, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
                 PG_CUDA(cudaFuncSetAttribute(p2p_shard_adam_kernel<8, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
                 carve[ctx->device & 15] = true;
             }
             int xg = ctx->sm_total;
             if (const char* ev = getenv("PGMVAE_P2P_CTAS")) xg = std::max(1, atoi(ev));        // (tuning: CTAs of the exchange kernel)
-            if (m->p2p_n <= 2) p2p_shard_adam_kernel<2, 4><<<xg, P2P_SHARD_THREADS, 0, m->comm_stream>>>(a);
-            else if (m->p2p_n <= 4) p2p_shard_adam_kernel<4, 2><<<xg, P2P_SHARD_THREADS, 0, m->comm_stream>>>(a);
+            if (m->p2p_n <= 2) p2p_shard_adam_kernel<2, 2><<<xg, P2P_SHARD_THREADS, 0, m->comm_stream>>>(a);
+            else if (m->p2p_n <= 4) p2p_shard_adam_kernel<4, 1><<<xg, P2P_SHARD_THREADS, 0, m->comm_stream>>>(a);
             else p2p_shard_adam_kernel<8, 1><<<xg, P2P_SHARD_THREADS, 0, m->comm_stream>>>(a);
             PG_LAUNCHED(ctx);
             m->state_sharded = true;
