@@ -63,6 +63,8 @@ struct Bf16P {
     int vec;                                              // rows allow 16-byte vector access
     int tma_out, tma_in, in_shared;                       // bf16 output / epilogue operand move through staged TMA tiles
     int out_db;                                           // dgrad: two output staging tiles next to the two operand tiles
+    int stage_f32;                                        // forward: fp32 rows leave through a transposing 16 KB staging tile
+    int zq_stage;                                         // dgrad at the VQ boundary: z / q rows arrive through one
     __nv_bfloat16* cb; long long cb_gs; int ldcb;         // bf16 output rows (may be null)
     float* cf; long long cf_gs; int ldcf;                 // fp32 output rows (may be null)
     const float* bias; long long bias_gs; int act;
@@ -209,7 +211,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     uint8_t* sA = smem;                                           // [stages][16 KB]
     uint8_t* sB = sA + (size_t)p.stages * A_BYTES;                // [stages][b_bytes]
     uint8_t* sStage = sB + (size_t)p.stages * p.b_bytes;          // [2 warpgroups][STG_WG] (only with tma_out / tma_in)
-    uint8_t* sOnes = sStage + ((p.tma_out || p.tma_in || EPI == EPI_SIGMOID_MSE) ? 2 * (p.out_db ? STG_WG4 : STG_WG) : 0);      // (only with p.ones)
+    uint8_t* sOnes = sStage + ((p.tma_out || p.tma_in || p.stage_f32 || p.zq_stage || EPI == EPI_SIGMOID_MSE) ? 2 * (p.out_db ? STG_WG4 : STG_WG) : 0);      // (only with p.ones)
     float* sBias = reinterpret_cast<float*>(sOnes + (p.ones ? ONES_BYTES : 0));      // [2 warpgroups][256] bias of the tile
     uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + 2 * ACC_COLS);
     uint64_t* full = bars;                        // [MAX_STAGES]   TMA -> MMA
@@ -462,7 +464,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             // ones per chunk (which were 40 % of the instructions of a chunk).  The MSE stage keeps -log2(e) * bias: its
             // sigmoid is 1 / (1 + 2^(-log2(e) * (acc + bias))).  The warpgroup's reads of the previous tile's bias
             // precede the barriers of that tile's last write_out.
-            const bool sbias = tout && p.bias && (EPI == EPI_FWD || EPI == EPI_SIGMOID_MSE);
+            const bool sf32 = EPI == EPI_FWD && p.stage_f32 != 0;
+            const bool sbias = (tout || sf32) && p.bias && (EPI == EPI_FWD || EPI == EPI_SIGMOID_MSE);
             float* myBias = sBias + wg * ACC_COLS;
             if (sbias) {
                 const float* bp = p.bias + (long long)g * p.bias_gs + n0;
@@ -516,6 +519,56 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                 }
             };
 
+            // fp32 rows [128][32 floats] through a staging tile of 16 KB (16-byte piece j of row r at j ^ (r & 7)): a thread
+            // owns a row, so direct 16-byte accesses touch 32 lines per warp instruction; through the tile a warp moves four
+            // whole 128-byte rows per instruction.  `tile16k` must not hold anything else of this warpgroup.
+            auto f32_rows_out = [&](uint8_t* tile16k, float* dst, int ld, int c, const float (&v)[32]) {
+                const int nv = min(32, ncols - c * 32);
+                tc::named_bar_sync(1 + wg, 128);                    // the tile's previous contents have been read
+                float4* rowp = reinterpret_cast<float4*>(tile16k + rt * 128);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) rowp[j ^ (rt & 7)] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                tc::named_bar_sync(1 + wg, 128);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const int i = rt + 128 * k, r = i >> 3, pc = i & 7;
+                    if (m0 + r >= p.M) continue;
+                    const float4 val = reinterpret_cast<const float4*>(tile16k + r * 128)[pc ^ (r & 7)];
+                    float* d = dst + (long long)(m0 + r) * ld + n0 + c * 32 + pc * 4;
+                    if (pc * 4 + 4 <= nv) *reinterpret_cast<float4*>(d) = val;
+                    else {
+                        const float e[4] = {val.x, val.y, val.z, val.w};
+                        for (int q4 = 0; q4 < 4; ++q4) if (pc * 4 + q4 < nv) d[q4] = e[q4];
+                    }
+                }
+            };
+            auto f32_rows_in = [&](uint8_t* tile16k, const float* src, int ld, int c, float (&t)[32]) {
+                const int nv = min(32, ncols - c * 32);
+                tc::named_bar_sync(1 + wg, 128);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const int i = rt + 128 * k, r = i >> 3, pc = i & 7;
+                    float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (m0 + r < p.M) {
+                        const float* a = src + (long long)(m0 + r) * ld + n0 + c * 32 + pc * 4;
+                        if (pc * 4 + 4 <= nv) val = *reinterpret_cast<const float4*>(a);
+                        else {
+                            float e[4] = {0.f, 0.f, 0.f, 0.f};
+                            for (int q4 = 0; q4 < 4; ++q4) if (pc * 4 + q4 < nv) e[q4] = a[q4];
+                            val = make_float4(e[0], e[1], e[2], e[3]);
+                        }
+                    }
+                    reinterpret_cast<float4*>(tile16k + r * 128)[pc ^ (r & 7)] = val;
+                }
+                tc::named_bar_sync(1 + wg, 128);
+                const float4* rowp = reinterpret_cast<const float4*>(tile16k + rt * 128);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float4 u = rowp[j ^ (rt & 7)];
+                    t[4 * j] = u.x; t[4 * j + 1] = u.y; t[4 * j + 2] = u.z; t[4 * j + 3] = u.w;
+                }
+            };
+
             auto process = [&](float (&v)[32], int c) {
                 const int nb = n0 + c * 32;
                 const int nv = min(32, ncols - c * 32);            // valid columns of this chunk (tile and tensor bounds)
@@ -540,7 +593,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 #pragma unroll
                         for (int j = 0; j < 32; ++j) v[j] = sigmoid_fast(v[j]);
                     }
-                    if (p.cf && rvalid) store_f32_row(p.cf + (long long)g * p.cf_gs + (long long)row * p.ldcf + nb, v, nv, p.vec);
+                    if (sf32) f32_rows_out(sOut, p.cf + (long long)g * p.cf_gs, p.ldcf, c, v);      // (out | in[0]: no operand tiles here)
+                    else if (p.cf && rvalid) store_f32_row(p.cf + (long long)g * p.cf_gs + (long long)row * p.ldcf + nb, v, nv, p.vec);
                     if (tout) write_out(c, v);
                     else if (p.cb && rvalid) store_bf16_row(p.cb + (long long)g * p.cb_gs + (long long)row * p.ldcb + nb, v, nv, p.vec);
                 } else if (EPI == EPI_SIGMOID_MSE) {
@@ -597,7 +651,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                     else if (p.cb && rvalid) store_bf16_row(p.cb + (long long)g * p.cb_gs + (long long)row * p.ldcb + nb, v, nv, p.vec);
                 } else if (EPI == EPI_DGRAD) {
                     float t[32];
-                    if (p.z && rvalid) {
+                    if (p.zq_stage) {
+                        // VQ boundary: commitment gradient cscale * (z - q) and selu'(z); the fp32 rows of z and q come
+                        // through the staging tile (in[0] | in[1]: the bf16 operand tiles are not in use here)
+                        float zv[32];
+                        f32_rows_in(sIn, p.z + (long long)g * p.zq_gs, p.ldzq, c, zv);
+                        f32_rows_in(sIn, p.q + (long long)g * p.zq_gs, p.ldzq, c, t);
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = fmaf(p.cscale, zv[j] - t[j], v[j]) * pg_dselu_from_out(zv[j]);
+                    } else if (p.z && rvalid) {
                         const long long zo = (long long)g * p.zq_gs + (long long)row * p.ldzq + nb;
                         float qv[32];
                         load_f32_row(p.z + zo, t, nv, p.vec);
@@ -605,7 +667,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 #pragma unroll
                         for (int j = 0; j < 32; ++j) v[j] = fmaf(p.cscale, t[j] - qv[j], v[j]);
                     }
-                    if (p.hb || p.hf) {
+                    if (!p.zq_stage && (p.hb || p.hf)) {
                         if (tin) read_in(c, t);
                         else if (p.hb) load_bf16_row(p.hb + (long long)g * p.hb_gs + (long long)(rvalid ? row : 0) * p.ldhb + nb, t, nv, p.vec);
                         else load_f32_row(p.hf + (long long)g * p.hf_gs + (long long)(rvalid ? row : 0) * p.ldhf + nb, t, nv, p.vec);
@@ -902,8 +964,11 @@ int launch(pgmvae_ctx* ctx, cudaStream_t st, Bf16P& p, const Operand& A, const O
             PG_TRY(tc::make_map(&em.in[nt], inp + n0, 2, (uint64_t)ncols, (uint64_t)p.M, (uint64_t)(p.in_shared ? 1 : p.G),
                                 (uint64_t)ld_in, (uint64_t)gs_in, 32, TM, false, true));
     }
+    p.stage_f32 = EPI == EPI_FWD && p.cf && !p.tma_out && p.vec && getenv("PGMVAE_BF16_DIRECT_EPI") == nullptr;
+    p.zq_stage = EPI == EPI_DGRAD && p.z && p.q && p.vec && !p.hb && p.hf == p.z && p.hf_gs == p.zq_gs && p.ldhf == p.ldzq &&
+                 p.act == PGMVAE_ACT_SELU && !p.tma_in && getenv("PGMVAE_BF16_DIRECT_EPI") == nullptr;
     const size_t stage = (size_t)A_BYTES + p.b_bytes;
-    const bool staged = p.tma_out || EPI == EPI_SIGMOID_MSE;       // (the MSE stage keeps its target words there)
+    const bool staged = p.tma_out || p.stage_f32 || p.zq_stage || EPI == EPI_SIGMOID_MSE;       // (the MSE stage keeps its target words there)
     // short-K dgrad layers are bound by their epilogue, not by the depth of the operand ring: a second output tile
     p.out_db = EPI == EPI_DGRAD && p.tma_in && p.kblocks <= 8;
     const size_t fixed = 1024 + 256 + (staged ? 2 * (size_t)(p.out_db ? STG_WG4 : STG_WG) : 0) + (p.ones ? ONES_BYTES : 0) +
