@@ -24,6 +24,7 @@ struct pgmvae_ctx {
     int sm_count = 148;           // SMs the library's persistent kernels may fill (device SMs minus the reserved ones)
     int sm_total = 148;
     int precision = PGMVAE_PREC_FP32;
+    bool coresident = false;      // the persistent GEMMs leave room for a co-resident exchange CTA (dense_bf16.cu: SLIM)
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int64_t launches = 0;

@@ -51,7 +51,9 @@ constexpr int ACC_COLS = 256;               // TMEM columns per accumulator buff
 constexpr int ONES_COL = 240;               // column of the bias-gradient accumulator (WGRAD_T, BN <= 240)
 constexpr int ONES_BYTES = 2048;            // [16 n][64 k] bf16 tile of 1.0 (K-major)
 
-enum { EPI_FWD = 0, EPI_SIGMOID_MSE = 1, EPI_DGRAD = 2, EPI_WGRAD_D = 3, EPI_WGRAD_T = 4 };
+enum { EPI_FWD = 0, EPI_SIGMOID_MSE = 1, EPI_DGRAD = 2, EPI_WGRAD_D = 3, EPI_WGRAD_T = 4,
+       EPI_DGRAD_VQ = 5 };   // dgrad at the VQ boundary (commitment gradient, fp32 z / q rows): its own instantiation, so that
+                             // its staging code does not cost the other dgrad launches registers
 
 struct Bf16P {
     int G, M, N, K, BN, tiles_m, tiles_n, kblocks, stages, total_tiles;
@@ -200,10 +202,12 @@ __device__ __forceinline__ void decode_tile(const Bf16P& p, int pt, int crank, i
 
 // CTA2: the instantiation that contains the cta_group::2 instructions (pair == 3).  It is a separate kernel because a
 // kernel holding such instructions can only be launched as clusters of CTA pairs ("cluster misconfiguration" otherwise).
-// 144 registers x 384 threads and 3 KB of shared memory less than the maximum leave room on every SM for one CTA of
-// the data-parallel exchange kernel (model.cu: p2p_shard_adam_kernel, 128 threads x 80 registers) NEXT TO this one.
-template <int EPI, bool CTA2>
-__global__ void __maxnreg__(144)
+// SLIM: 144 registers x 384 threads and 3 KB of shared memory less than the maximum leave room on every SM for one CTA
+// of the data-parallel exchange kernel (model.cu: p2p_shard_adam_kernel, 128 threads x 80 registers) NEXT TO this one
+// (ctx->coresident, set by the training step while that exchange is in use).  The cap costs the epilogues a few spills
+// (the MSE stage ~25 %), so everything else runs the full-register instantiation.
+template <int EPI, bool CTA2, bool SLIM>
+__global__ void __maxnreg__(SLIM ? 144 : 168)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                  const __grid_constant__ EpiMaps em, const __grid_constant__ Bf16P p) {
     extern __shared__ uint8_t smem_raw[];
@@ -649,16 +653,18 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                     if (p.cf && rvalid) store_f32_row(p.cf + (long long)g * p.cf_gs + (long long)row * p.ldcf + nb, o, nv, p.vec);
                     if (tout) write_out(c, v);
                     else if (p.cb && rvalid) store_bf16_row(p.cb + (long long)g * p.cb_gs + (long long)row * p.ldcb + nb, v, nv, p.vec);
-                } else if (EPI == EPI_DGRAD) {
+                } else if (EPI == EPI_DGRAD || EPI == EPI_DGRAD_VQ) {
                     float t[32];
-                    if (p.zq_stage) {
+                    if (EPI == EPI_DGRAD_VQ) {
                         // VQ boundary: commitment gradient cscale * (z - q) and selu'(z); the fp32 rows of z and q come
                         // through the staging tile (in[0] | in[1]: the bf16 operand tiles are not in use here)
-                        float zv[32];
-                        f32_rows_in(sIn, p.z + (long long)g * p.zq_gs, p.ldzq, c, zv);
+                        // (q first, then z, so that only one of the two rows is live: v - cscale q + cscale z)
                         f32_rows_in(sIn, p.q + (long long)g * p.zq_gs, p.ldzq, c, t);
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = fmaf(p.cscale, zv[j] - t[j], v[j]) * pg_dselu_from_out(zv[j]);
+                        for (int j = 0; j < 32; ++j) v[j] = fmaf(-p.cscale, t[j], v[j]);
+                        f32_rows_in(sIn, p.z + (long long)g * p.zq_gs, p.ldzq, c, t);
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = fmaf(p.cscale, t[j], v[j]) * pg_dselu_from_out(t[j]);
                     } else if (p.z && rvalid) {
                         const long long zo = (long long)g * p.zq_gs + (long long)row * p.ldzq + nb;
                         float qv[32];
@@ -667,7 +673,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 #pragma unroll
                         for (int j = 0; j < 32; ++j) v[j] = fmaf(p.cscale, t[j] - qv[j], v[j]);
                     }
-                    if (!p.zq_stage && (p.hb || p.hf)) {
+                    if (EPI != EPI_DGRAD_VQ && (p.hb || p.hf)) {
                         if (tin) read_in(c, t);
                         else if (p.hb) load_bf16_row(p.hb + (long long)g * p.hb_gs + (long long)(rvalid ? row : 0) * p.ldhb + nb, t, nv, p.vec);
                         else load_f32_row(p.hf + (long long)g * p.hf_gs + (long long)(rvalid ? row : 0) * p.ldhf + nb, t, nv, p.vec);
@@ -951,7 +957,7 @@ int launch(pgmvae_ctx* ctx, cudaStream_t st, Bf16P& p, const Operand& A, const O
     const __nv_bfloat16* inp = EPI == EPI_DGRAD ? p.hb : nullptr;
     const int ld_in = p.ldhb;
     const int64_t gs_in = p.hb_gs;
-    const bool epi_rows = EPI == EPI_FWD || EPI == EPI_SIGMOID_MSE || EPI == EPI_DGRAD;
+    const bool epi_rows = EPI == EPI_FWD || EPI == EPI_SIGMOID_MSE || EPI == EPI_DGRAD || EPI == EPI_DGRAD_VQ;
     p.in_shared = 0;
     p.tma_out = epi_rows && p.cb && p.tiles_n <= MAX_NT_MAPS && al16(p.cb) && p.ldcb % 8 == 0 && p.cb_gs % 8 == 0 &&
                 getenv("PGMVAE_BF16_DIRECT_EPI") == nullptr;
@@ -965,15 +971,15 @@ int launch(pgmvae_ctx* ctx, cudaStream_t st, Bf16P& p, const Operand& A, const O
                                 (uint64_t)ld_in, (uint64_t)gs_in, 32, TM, false, true));
     }
     p.stage_f32 = EPI == EPI_FWD && p.cf && !p.tma_out && p.vec && getenv("PGMVAE_BF16_DIRECT_EPI") == nullptr;
-    p.zq_stage = EPI == EPI_DGRAD && p.z && p.q && p.vec && !p.hb && p.hf == p.z && p.hf_gs == p.zq_gs && p.ldhf == p.ldzq &&
-                 p.act == PGMVAE_ACT_SELU && !p.tma_in && getenv("PGMVAE_BF16_DIRECT_EPI") == nullptr;
+    p.zq_stage = EPI == EPI_DGRAD_VQ;
     const size_t stage = (size_t)A_BYTES + p.b_bytes;
     const bool staged = p.tma_out || p.stage_f32 || p.zq_stage || EPI == EPI_SIGMOID_MSE;       // (the MSE stage keeps its target words there)
     // short-K dgrad layers are bound by their epilogue, not by the depth of the operand ring: a second output tile
     p.out_db = EPI == EPI_DGRAD && p.tma_in && p.kblocks <= 8;
     const size_t fixed = 1024 + 256 + (staged ? 2 * (size_t)(p.out_db ? STG_WG4 : STG_WG) : 0) + (p.ones ? ONES_BYTES : 0) +
                          2 * ACC_COLS * sizeof(float);
-    const size_t smem_cap = ctx->smem_optin - 3072;                 // (room for a co-resident exchange CTA, see the kernel)
+    const bool slim = ctx->coresident;
+    const size_t smem_cap = ctx->smem_optin - (slim ? 3072 : 0);    // (room for a co-resident exchange CTA, see the kernel)
     int stages = (int)((smem_cap - fixed) / stage);
     if (stages > MAX_STAGES) stages = MAX_STAGES;
     if (const char* ev = getenv("PGMVAE_BF16_STAGES")) stages = std::max(2, std::min(stages, atoi(ev)));   // (experiments)
@@ -993,12 +999,14 @@ int launch(pgmvae_ctx* ctx, cudaStream_t st, Bf16P& p, const Operand& A, const O
     else PG_TRY(tc::make_map(&mA, A.p, 2, (uint64_t)p.M, (uint64_t)p.K, (uint64_t)p.G, (uint64_t)A.ld, (uint64_t)A.gs, 64, BK));
     if (!p.b_mn) PG_TRY(tc::make_map(&mB, B.p, 2, (uint64_t)p.K, (uint64_t)p.N, (uint64_t)p.G, (uint64_t)B.ld, (uint64_t)B.gs, BK, b_box_rows));
     else PG_TRY(tc::make_map(&mB, B.p, 2, (uint64_t)p.N, (uint64_t)p.K, (uint64_t)p.G, (uint64_t)B.ld, (uint64_t)B.gs, 64, BK));
-    static size_t configured[16][2] = {};
+    static size_t configured[16][2][2] = {};
     const int dev = ctx->device & 15, two = p.pair == 3 ? 1 : 0;
-    if (smem > configured[dev][two]) {
-        if (two) PG_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<EPI, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        else PG_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<EPI, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured[dev][two] = smem;
+    using Kern = void (*)(const CUtensorMap, const CUtensorMap, const EpiMaps, const Bf16P);
+    const Kern kern = two ? (slim ? (Kern)gemm_bf16_kernel<EPI, true, true> : (Kern)gemm_bf16_kernel<EPI, true, false>)
+                          : (slim ? (Kern)gemm_bf16_kernel<EPI, false, true> : (Kern)gemm_bf16_kernel<EPI, false, false>);
+    if (smem > configured[dev][two][slim]) {
+        PG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured[dev][two][slim] = smem;
     }
     const int csize = p.pair == 4 ? 4 : (p.pair ? 2 : 1);
     int nclusters = std::min(p.total_ptiles, ctx->sm_count / csize);
@@ -1017,20 +1025,18 @@ int launch(pgmvae_ctx* ctx, cudaStream_t st, Bf16P& p, const Operand& A, const O
     if (csize == 4) {
         // tiles are assigned statically: never launch more clusters than can be resident at once (clusters of four do
         // not tile every GPC)
-        static int max_quads[16][5] = {};
-        int& mq = max_quads[dev][EPI];
+        static int max_quads[16][6][2] = {};
+        int& mq = max_quads[dev][EPI][slim];
         if (mq == 0) {
             int n = 0;
-            cudaError_t e = two ? cudaOccupancyMaxActiveClusters(&n, gemm_bf16_kernel<EPI, true>, &cfg)
-                                : cudaOccupancyMaxActiveClusters(&n, gemm_bf16_kernel<EPI, false>, &cfg);
+            cudaError_t e = cudaOccupancyMaxActiveClusters(&n, kern, &cfg);
             mq = (e == cudaSuccess && n > 0) ? n : 30;
         }
         nclusters = std::min(nclusters, mq);
         cfg.gridDim = dim3((unsigned)(nclusters * csize));
     }
     PG_KERNEL(ctx, st, name, bytes, 2.0 * p.G * (double)p.M * p.N * p.K);
-    if (two) PG_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<EPI, true>, mA, mB, em, p));
-    else PG_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<EPI, false>, mA, mB, em, p));
+    PG_CUDA(cudaLaunchKernelEx(&cfg, kern, mA, mB, em, p));
     PG_LAUNCHED(ctx);
     return PGMVAE_OK;
 }
@@ -1082,6 +1088,12 @@ int pg_bf16_dgrad(pgmvae_ctx* ctx, cudaStream_t st, const __nv_bfloat16* dy, int
     p.vec = (!dxb || (al16(dxb) && lddxb % 8 == 0 && dxb_gs % 8 == 0)) && (!dxf || (al16(dxf) && lddxf % 4 == 0 && dxf_gs % 4 == 0)) &&
             (!hb || (al16(hb) && ldhb % 8 == 0 && hb_gs % 8 == 0)) && (!hf || (al16(hf) && ldhf % 4 == 0 && hf_gs % 4 == 0)) &&
             (!z || (al16(z) && al16(q) && ldzq % 4 == 0 && zq_gs % 4 == 0));
+    // the dgrad below the VQ layer: z is both the commitment-gradient operand and the activation below
+    const bool vq_boundary = z && q && p.vec && !hb && hf == z && hf_gs == zq_gs && ldhf == ldzq && act_below == PGMVAE_ACT_SELU &&
+                             getenv("PGMVAE_BF16_DIRECT_EPI") == nullptr;
+    if (vq_boundary)
+        return launch<EPI_DGRAD_VQ>(ctx, st, p, Operand{dy, dy_gs, lddy}, Operand{w, w_gs, ldw}, "dense_dgrad_bf16",
+                                    2.0 * ((double)G * B * out_dim + (double)G * in * out_dim + (double)G * B * in) + 8.0 * G * B * in);
     return launch<EPI_DGRAD>(ctx, st, p, Operand{dy, dy_gs, lddy}, Operand{w, w_gs, ldw}, "dense_dgrad_bf16",
                              2.0 * ((double)G * B * out_dim + (double)G * in * out_dim + (double)G * B * in * 2.0) +
                                  (z ? 8.0 * G * B * in : 0.0));

@@ -1141,6 +1141,7 @@ int run_step(pgmvae_model* m, const uint8_t* y, int y_on_device, int B, int glob
     const bool use_shard = comm != nullptr && !chain && m->p2p && m->p2p_shard && do_update;
     ShardSlice shard_s[24];
     const int shard_n = use_shard ? shard_slices(m, shard_s) : 0;
+    ctx->coresident = use_shard;
     auto ema_update = [&](cudaStream_t es) -> int {
         if (ema_done || (flags & (STEP_NO_UPDATE | STEP_FWD_ONLY)) || !m->ema || (flags & STEP_NO_EMA)) return PGMVAE_OK;
         ema_done = true;
