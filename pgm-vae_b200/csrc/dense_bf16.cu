@@ -51,9 +51,7 @@ constexpr int ACC_COLS = 256;               // TMEM columns per accumulator buff
 constexpr int ONES_COL = 240;               // column of the bias-gradient accumulator (WGRAD_T, BN <= 240)
 constexpr int ONES_BYTES = 2048;            // [16 n][64 k] bf16 tile of 1.0 (K-major)
 
-enum { EPI_FWD = 0, EPI_SIGMOID_MSE = 1, EPI_DGRAD = 2, EPI_WGRAD_D = 3, EPI_WGRAD_T = 4,
-       EPI_DGRAD_VQ = 5 };   // dgrad at the VQ boundary (commitment gradient, fp32 z / q rows): its own instantiation, so that
-                             // its staging code does not cost the other dgrad launches registers
+enum { EPI_FWD = 0, EPI_SIGMOID_MSE = 1, EPI_DGRAD = 2, EPI_WGRAD_D = 3, EPI_WGRAD_T = 4 };
 
 struct Bf16P {
     int G, M, N, K, BN, tiles_m, tiles_n, kblocks, stages, total_tiles;
@@ -66,7 +64,6 @@ struct Bf16P {
     int tma_out, tma_in, in_shared;                       // bf16 output / epilogue operand move through staged TMA tiles
     int out_db;                                           // dgrad: two output staging tiles next to the two operand tiles
     int stage_f32;                                        // forward: fp32 rows leave through a transposing 16 KB staging tile
-    int zq_stage;                                         // dgrad at the VQ boundary: z / q rows arrive through one
     __nv_bfloat16* cb; long long cb_gs; int ldcb;         // bf16 output rows (may be null)
     float* cf; long long cf_gs; int ldcf;                 // fp32 output rows (may be null)
     const float* bias; long long bias_gs; int act;
@@ -215,7 +212,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     uint8_t* sA = smem;                                           // [stages][16 KB]
     uint8_t* sB = sA + (size_t)p.stages * A_BYTES;                // [stages][b_bytes]
     uint8_t* sStage = sB + (size_t)p.stages * p.b_bytes;          // [2 warpgroups][STG_WG] (only with tma_out / tma_in)
-    uint8_t* sOnes = sStage + ((p.tma_out || p.tma_in || p.stage_f32 || p.zq_stage || EPI == EPI_SIGMOID_MSE) ? 2 * (p.out_db ? STG_WG4 : STG_WG) : 0);      // (only with p.ones)
+    uint8_t* sOnes = sStage + ((p.tma_out || p.tma_in || p.stage_f32 || EPI == EPI_SIGMOID_MSE) ? 2 * (p.out_db ? STG_WG4 : STG_WG) : 0);      // (only with p.ones)
     float* sBias = reinterpret_cast<float*>(sOnes + (p.ones ? ONES_BYTES : 0));      // [2 warpgroups][256] bias of the tile
     uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + 2 * ACC_COLS);
     uint64_t* full = bars;                        // [MAX_STAGES]   TMA -> MMA
@@ -525,7 +522,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 
             // fp32 rows [128][32 floats] through a staging tile of 16 KB (16-byte piece j of row r at j ^ (r & 7)): a thread
             // owns a row, so direct 16-byte accesses touch 32 lines per warp instruction; through the tile a warp moves four
-            // whole 128-byte rows per instruction.  `tile16k` must not hold anything else of this warpgroup.
+            // whole 128-byte rows per instruction (fd4's latent: 0.118 -> 0.076 ms per group at cfg3).  `tile16k` must not
+            // hold anything else of this warpgroup.  (The same for the fp32 z / q rows READ by the dgrad at the VQ boundary
+            // was measured slower -- 0.34 vs 0.22 ms, four more barriers per chunk in a latency-bound tile loop -- and removed.)
             auto f32_rows_out = [&](uint8_t* tile16k, float* dst, int ld, int c, const float (&v)[32]) {
                 const int nv = min(32, ncols - c * 32);
                 tc::named_bar_sync(1 + wg, 128);                    // the tile's previous contents have been read
@@ -546,33 +545,6 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                     }
                 }
             };
-            auto f32_rows_in = [&](uint8_t* tile16k, const float* src, int ld, int c, float (&t)[32]) {
-                const int nv = min(32, ncols - c * 32);
-                tc::named_bar_sync(1 + wg, 128);
-#pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const int i = rt + 128 * k, r = i >> 3, pc = i & 7;
-                    float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (m0 + r < p.M) {
-                        const float* a = src + (long long)(m0 + r) * ld + n0 + c * 32 + pc * 4;
-                        if (pc * 4 + 4 <= nv) val = *reinterpret_cast<const float4*>(a);
-                        else {
-                            float e[4] = {0.f, 0.f, 0.f, 0.f};
-                            for (int q4 = 0; q4 < 4; ++q4) if (pc * 4 + q4 < nv) e[q4] = a[q4];
-                            val = make_float4(e[0], e[1], e[2], e[3]);
-                        }
-                    }
-                    reinterpret_cast<float4*>(tile16k + r * 128)[pc ^ (r & 7)] = val;
-                }
-                tc::named_bar_sync(1 + wg, 128);
-                const float4* rowp = reinterpret_cast<const float4*>(tile16k + rt * 128);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const float4 u = rowp[j ^ (rt & 7)];
-                    t[4 * j] = u.x; t[4 * j + 1] = u.y; t[4 * j + 2] = u.z; t[4 * j + 3] = u.w;
-                }
-            };
-
             auto process = [&](float (&v)[32], int c) {
                 const int nb = n0 + c * 32;
                 const int nv = min(32, ncols - c * 32);            // valid columns of this chunk (tile and tensor bounds)
@@ -653,19 +625,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                     if (p.cf && rvalid) store_f32_row(p.cf + (long long)g * p.cf_gs + (long long)row * p.ldcf + nb, o, nv, p.vec);
                     if (tout) write_out(c, v);
                     else if (p.cb && rvalid) store_bf16_row(p.cb + (long long)g * p.cb_gs + (long long)row * p.ldcb + nb, v, nv, p.vec);
-                } else if (EPI == EPI_DGRAD || EPI == EPI_DGRAD_VQ) {
+                } else if (EPI == EPI_DGRAD) {
                     float t[32];
-                    if (EPI == EPI_DGRAD_VQ) {
-                        // VQ boundary: commitment gradient cscale * (z - q) and selu'(z); the fp32 rows of z and q come
-                        // through the staging tile (in[0] | in[1]: the bf16 operand tiles are not in use here)
-                        // (q first, then z, so that only one of the two rows is live: v - cscale q + cscale z)
-                        f32_rows_in(sIn, p.q + (long long)g * p.zq_gs, p.ldzq, c, t);
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = fmaf(-p.cscale, t[j], v[j]);
-                        f32_rows_in(sIn, p.z + (long long)g * p.zq_gs, p.ldzq, c, t);
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = fmaf(p.cscale, t[j], v[j]) * pg_dselu_from_out(t[j]);
-                    } else if (p.z && rvalid) {
+                    if (p.z && rvalid) {
                         const long long zo = (long long)g * p.zq_gs + (long long)row * p.ldzq + nb;
                         float qv[32];
                         load_f32_row(p.z + zo, t, nv, p.vec);
@@ -673,7 +635,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 #pragma unroll
                         for (int j = 0; j < 32; ++j) v[j] = fmaf(p.cscale, t[j] - qv[j], v[j]);
                     }
-                    if (EPI != EPI_DGRAD_VQ && (p.hb || p.hf)) {
+                    if (p.hb || p.hf) {
                         if (tin) read_in(c, t);
                         else if (p.hb) load_bf16_row(p.hb + (long long)g * p.hb_gs + (long long)(rvalid ? row : 0) * p.ldhb + nb, t, nv, p.vec);
                         else load_f32_row(p.hf + (long long)g * p.hf_gs + (long long)(rvalid ? row : 0) * p.ldhf + nb, t, nv, p.vec);
@@ -957,7 +919,7 @@ int launch(pgmvae_ctx* ctx, cudaStream_t st, Bf16P& p, const Operand& A, const O
     const __nv_bfloat16* inp = EPI == EPI_DGRAD ? p.hb : nullptr;
     const int ld_in = p.ldhb;
     const int64_t gs_in = p.hb_gs;
-    const bool epi_rows = EPI == EPI_FWD || EPI == EPI_SIGMOID_MSE || EPI == EPI_DGRAD || EPI == EPI_DGRAD_VQ;
+    const bool epi_rows = EPI == EPI_FWD || EPI == EPI_SIGMOID_MSE || EPI == EPI_DGRAD;
     p.in_shared = 0;
     p.tma_out = epi_rows && p.cb && p.tiles_n <= MAX_NT_MAPS && al16(p.cb) && p.ldcb % 8 == 0 && p.cb_gs % 8 == 0 &&
                 getenv("PGMVAE_BF16_DIRECT_EPI") == nullptr;
@@ -970,10 +932,10 @@ int launch(pgmvae_ctx* ctx, cudaStream_t st, Bf16P& p, const Operand& A, const O
             PG_TRY(tc::make_map(&em.in[nt], inp + n0, 2, (uint64_t)ncols, (uint64_t)p.M, (uint64_t)(p.in_shared ? 1 : p.G),
                                 (uint64_t)ld_in, (uint64_t)gs_in, 32, TM, false, true));
     }
-    p.stage_f32 = EPI == EPI_FWD && p.cf && !p.tma_out && p.vec && getenv("PGMVAE_BF16_DIRECT_EPI") == nullptr;
-    p.zq_stage = EPI == EPI_DGRAD_VQ;
+    p.stage_f32 = EPI == EPI_FWD && p.cf && !p.tma_out && p.vec && getenv("PGMVAE_BF16_DIRECT_EPI") == nullptr &&
+                  getenv("PGMVAE_BF16_NO_F32_STAGE") == nullptr;
     const size_t stage = (size_t)A_BYTES + p.b_bytes;
-    const bool staged = p.tma_out || p.stage_f32 || p.zq_stage || EPI == EPI_SIGMOID_MSE;       // (the MSE stage keeps its target words there)
+    const bool staged = p.tma_out || p.stage_f32 || EPI == EPI_SIGMOID_MSE;       // (the MSE stage keeps its target words there)
     // short-K dgrad layers are bound by their epilogue, not by the depth of the operand ring: a second output tile
     p.out_db = EPI == EPI_DGRAD && p.tma_in && p.kblocks <= 8;
     const size_t fixed = 1024 + 256 + (staged ? 2 * (size_t)(p.out_db ? STG_WG4 : STG_WG) : 0) + (p.ones ? ONES_BYTES : 0) +
@@ -1025,7 +987,7 @@ int launch(pgmvae_ctx* ctx, cudaStream_t st, Bf16P& p, const Operand& A, const O
     if (csize == 4) {
         // tiles are assigned statically: never launch more clusters than can be resident at once (clusters of four do
         // not tile every GPC)
-        static int max_quads[16][6][2] = {};
+        static int max_quads[16][5][2] = {};
         int& mq = max_quads[dev][EPI][slim];
         if (mq == 0) {
             int n = 0;
@@ -1088,12 +1050,6 @@ int pg_bf16_dgrad(pgmvae_ctx* ctx, cudaStream_t st, const __nv_bfloat16* dy, int
     p.vec = (!dxb || (al16(dxb) && lddxb % 8 == 0 && dxb_gs % 8 == 0)) && (!dxf || (al16(dxf) && lddxf % 4 == 0 && dxf_gs % 4 == 0)) &&
             (!hb || (al16(hb) && ldhb % 8 == 0 && hb_gs % 8 == 0)) && (!hf || (al16(hf) && ldhf % 4 == 0 && hf_gs % 4 == 0)) &&
             (!z || (al16(z) && al16(q) && ldzq % 4 == 0 && zq_gs % 4 == 0));
-    // the dgrad below the VQ layer: z is both the commitment-gradient operand and the activation below
-    const bool vq_boundary = z && q && p.vec && !hb && hf == z && hf_gs == zq_gs && ldhf == ldzq && act_below == PGMVAE_ACT_SELU &&
-                             getenv("PGMVAE_BF16_DIRECT_EPI") == nullptr;
-    if (vq_boundary)
-        return launch<EPI_DGRAD_VQ>(ctx, st, p, Operand{dy, dy_gs, lddy}, Operand{w, w_gs, ldw}, "dense_dgrad_bf16",
-                                    2.0 * ((double)G * B * out_dim + (double)G * in * out_dim + (double)G * B * in) + 8.0 * G * B * in);
     return launch<EPI_DGRAD>(ctx, st, p, Operand{dy, dy_gs, lddy}, Operand{w, w_gs, ldw}, "dense_dgrad_bf16",
                              2.0 * ((double)G * B * out_dim + (double)G * in * out_dim + (double)G * B * in * 2.0) +
                                  (z ? 8.0 * G * B * in : 0.0));
