@@ -399,6 +399,7 @@ def run_ours(args, wl, wl_name):
         "frac": (tfs / tc_peak) if tensor_bound else (gbs / hbm_peak),
         "traffic": (traffic or {}).get(wl_name, {}).get(top["name"]) if traffic else None,
         "traffic_source": "ncu --set full capture committed as profiles/r2_dram_traffic.json (per launch)" if traffic else None,
+        "traffic_launch": (traffic or {}).get("_launch", {}).get(top["name"]) if traffic else None,
         "peak_source": peak_src + (" bf16 sustained" if arith != "tf32" else " bf16 sustained / 2 (tf32 operands)"),
         "avg_launch_ms": avg_ms, "launches_per_step": top["launches"] / psteps,
         "share_of_step": top["ms"] / tot_ms, "algorithmic_bytes_per_launch": top["bytes"] / top["launches"],
