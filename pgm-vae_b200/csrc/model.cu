@@ -745,6 +745,11 @@ struct PgModelView {
 int pg_model_view(pgmvae_model* m, PgModelView* v) {
     PG_CHECK_ARG(m && v);
     PG_TRY(p2p_check(m));
+    if (m->p2p && m->state_sharded && m->bf16) {
+        pgmvae_set_error("the sub-net path reads the fp32 master weights, which are sharded over the data-parallel ranks; call "
+                         "pgmvae_model_p2p_sync_state (VqVAE.sync_state) on EVERY rank first");
+        return PGMVAE_EINVAL;
+    }
     v->ctx = m->ctx; v->V = m->V; v->Vp = m->Vp; v->D = m->D; v->Dp = m->Dp; v->K = m->K;
     v->params = m->params; v->E = m->E();
     for (int l = 0; l < 5; ++l) {
@@ -943,6 +948,12 @@ int pgmvae_model_tensor_size(pgmvae_model* m, const char* name, int64_t* count) 
 
 int pgmvae_model_set_tensor(pgmvae_model* m, const char* name, const float* host, int64_t count) {
     PG_CHECK_ARG(m && name && host);
+    if (m->p2p && m->state_sharded) {
+        // (the bf16 mirror would be refreshed from fp32 master weights that are stale on the ranks that do not own them)
+        pgmvae_set_error("set_tensor '%s': the model's fp32 master weights are sharded over the data-parallel ranks; call "
+                         "pgmvae_model_p2p_sync_state (VqVAE.sync_state) on EVERY rank first", name);
+        return PGMVAE_EINVAL;
+    }
     TensorRef t;
     PG_TRY(resolve(m, name, &t));
     if (count != t.ref_count) {
@@ -961,6 +972,18 @@ int pgmvae_model_set_tensor(pgmvae_model* m, const char* name, const float* host
 int pgmvae_model_get_tensor(pgmvae_model* m, const char* name, float* host, int64_t count) {
     PG_CHECK_ARG(m && name && host);
     PG_TRY(p2p_check(m));
+    if (m->p2p && m->state_sharded) {
+        // after steps of the sharded exchange these tensors are complete only on the ranks that own their shards
+        const std::string s(name);
+        const bool moment = s.rfind("adam_m.", 0) == 0 || s.rfind("adam_v.", 0) == 0;
+        const bool master = m->bf16 && s.rfind("fd", 0) == 0 && s.size() > 7 && s.compare(s.size() - 7, 7, ".kernel") == 0;
+        if (moment || master) {
+            pgmvae_set_error("get_tensor '%s': after data-parallel steps with the sharded peer-to-peer exchange this tensor is "
+                             "complete only on the ranks that own its shards; call pgmvae_model_p2p_sync_state "
+                             "(VqVAE.sync_state) on EVERY rank first", name);
+            return PGMVAE_EINVAL;
+        }
+    }
     TensorRef t;
     PG_TRY(resolve(m, name, &t));
     if (count != t.ref_count) {
