@@ -285,6 +285,8 @@ int pgmvae_model_p2p_import(pgmvae_model* m, int rank, int nranks, const void* a
  * a shard (state_sharded() == 1); sync_state() -- COLLECTIVE over the ranks of the mapping -- completes them
  * everywhere (before get_tensor / a checkpoint / the fp32 readers such as the Gibbs sampler; fit() ends with it). */
 int pgmvae_model_p2p_state_sharded(pgmvae_model* m);
+/* which variables [*lo, *hi) of the variable group [g0, g0 + Gn) rank `rank` of `nranks` owns in the sharded exchange */
+int pgmvae_p2p_shard_bounds(int g0, int Gn, int rank, int nranks, int* lo, int* hi);
 int pgmvae_model_p2p_sync_state(pgmvae_model* m);
 /* turn the peer-to-peer exchange off again (a rank failed to map its peers): NCCL is used instead */
 int pgmvae_model_p2p_disable(pgmvae_model* m);

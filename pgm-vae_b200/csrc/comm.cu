@@ -111,12 +111,14 @@ int pgmvae_comm_unique_id(void* out128) {
 
 int pgmvae_comm_create(pgmvae_ctx* ctx, int rank, int nranks, const void* id128, pgmvae_comm** out) {
     PG_CHECK_ARG(ctx && out && nranks >= 1 && rank >= 0 && rank < nranks);
-    pgmvae_comm* c = new pgmvae_comm();
-    c->ctx = ctx; c->rank = rank; c->nranks = nranks;
+    PG_CHECK_ARG(nranks == 1 || id128 != nullptr);
     if (nranks > 1) {
-        PG_CHECK_ARG(id128 != nullptr);
         PG_TRY(load_nccl());
         PG_CUDA(cudaSetDevice(ctx->device));
+    }
+    pgmvae_comm* c = new pgmvae_comm();        // (nothing below returns without deleting it)
+    c->ctx = ctx; c->rank = rank; c->nranks = nranks;
+    if (nranks > 1) {
         ncclUniqueId id;
         memcpy(&id, id128, 128);
         const int rc = g_nccl.CommInitRank(&c->comm, nranks, id, rank);

@@ -1067,6 +1067,15 @@ int pgmvae_model_p2p_disable(pgmvae_model* m) {
     return PGMVAE_OK;
 }
 
+/* the variables [*lo, *hi) of the group [g0, g0 + Gn) that rank `rank` of `nranks` owns in the sharded exchange: the shards
+ * of a group are contiguous, disjoint, cover it, and differ by at most one variable (no CUDA call: testable on any host) */
+int pgmvae_p2p_shard_bounds(int g0, int Gn, int rank, int nranks, int* lo, int* hi) {
+    PG_CHECK_ARG(lo && hi && g0 >= 0 && Gn >= 0 && nranks >= 1 && rank >= 0 && rank < nranks);
+    *lo = g0 + (int)((long long)rank * Gn / nranks);
+    *hi = g0 + (int)((long long)(rank + 1) * Gn / nranks);
+    return PGMVAE_OK;
+}
+
 /* 1 when steps of the sharded exchange have left the Adam moments (and, in bf16 mode, the fp32 master of the dense
  * kernels) complete only on the rank that owns a shard: sync_state() below completes them everywhere */
 int pgmvae_model_p2p_state_sharded(pgmvae_model* m) { return m && m->p2p && m->state_sharded ? 1 : 0; }
@@ -1084,8 +1093,11 @@ int pgmvae_model_p2p_sync_state(pgmvae_model* m) {
         const int Gn = std::min(m->Vg, m->V - g0);
         P2pStateArgs a{};
         a.peer_p = m->peer_params; a.peer_m = m->peer_m; a.peer_v = m->peer_v; a.rank = m->p2p_rank; a.R = m->p2p_n;
-        a.v_lo = g0 + (long long)m->p2p_rank * Gn / m->p2p_n;
-        a.v_hi = g0 + (long long)(m->p2p_rank + 1) * Gn / m->p2p_n;
+        {
+            int lo = 0, hi = 0;
+            PG_TRY(pgmvae_p2p_shard_bounds(g0, Gn, m->p2p_rank, m->p2p_n, &lo, &hi));
+            a.v_lo = lo; a.v_hi = hi;
+        }
         a.nslices = shard_slices(m, a.s);
         if (a.v_hi <= a.v_lo) continue;
         PG_KERNEL(ctx, st, "p2p_push_state", 0.0, 0.0);
@@ -1343,8 +1355,11 @@ int run_step(pgmvae_model* m, const uint8_t* y, int y_on_device, int B, int glob
             a.peer_flags = m->peer_flags; a.my_flags = m->p2p_flags;
             a.m = m->adam_m; a.v = m->adam_v;
             a.rank = m->p2p_rank; a.R = m->p2p_n; a.seq = ++m->p2p_seq; a.nslices = shard_n;
-            a.v_lo = g0 + (long long)m->p2p_rank * Gn / m->p2p_n;
-            a.v_hi = g0 + (long long)(m->p2p_rank + 1) * Gn / m->p2p_n;
+            {
+                int lo = 0, hi = 0;
+                PG_TRY(pgmvae_p2p_shard_bounds(g0, Gn, m->p2p_rank, m->p2p_n, &lo, &hi));
+                a.v_lo = lo; a.v_hi = hi;
+            }
             for (int i = 0; i < shard_n; ++i) a.s[i] = shard_s[i];
             a.alpha = alpha; a.omb1 = (float)(1.0 - b1); a.omb2 = (float)(1.0 - b2); a.eps = 1e-7f;
             a.counter = m->p2p_counter; a.err = m->p2p_err;

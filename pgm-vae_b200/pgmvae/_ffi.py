@@ -94,6 +94,7 @@ SIGNATURES = {
     "pgmvae_model_p2p_import": (_i, [_vp, _i, _i, _vp]),
     "pgmvae_model_p2p_disable": (_i, [_vp]),
     "pgmvae_model_p2p_state_sharded": (_i, [_vp]),
+    "pgmvae_p2p_shard_bounds": (_i, [_i, _i, _i, _i, _vp, _vp]),
     "pgmvae_model_p2p_sync_state": (_i, [_vp]),
     "pgmvae_ctx_reserve_sms": (_i, [_vp, _i]),
     "pgmvae_device_can_access_peer": (_i, [_i, _i, _vp]),

@@ -78,3 +78,32 @@ def test_shard_bounds_partition():
             assert b[0][0] == 0 and b[-1][1] == n
             assert all(b[i][1] == b[i + 1][0] for i in range(w - 1))
             assert max(h - l for l, h in b) - min(h - l for l, h in b) <= 1
+
+
+def test_sharded_exchange_ownership_partition():
+    """The sharded peer-to-peer exchange (csrc/model.cu: p2p_shard_adam_kernel) gives every variable of every variable
+    group exactly one owner rank: the library's own ownership function, over the group walks the training step does
+    (cfg3: 1556 variables in groups of 148, last group 76; fewer variables than ranks; one group)."""
+    import ctypes as C
+    for p in (os.path.join(ROOT, "pgm-vae_b200"),):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    from pgmvae import _ffi
+    L = _ffi.load_library()
+    for V, Vg in ((1556, 148), (69, 20), (24, 7), (5, 5), (3, 148)):
+        for R in (2, 3, 4, 8):
+            owner = np.full(V, -1)
+            for g0 in range(0, V, Vg):
+                Gn = min(Vg, V - g0)
+                sizes = []
+                for r in range(R):
+                    lo, hi = C.c_int(-1), C.c_int(-1)
+                    assert L.pgmvae_p2p_shard_bounds(g0, Gn, r, R, C.byref(lo), C.byref(hi)) == 0
+                    assert g0 <= lo.value <= hi.value <= g0 + Gn
+                    assert (owner[lo.value:hi.value] == -1).all()
+                    owner[lo.value:hi.value] = r
+                    sizes.append(hi.value - lo.value)
+                assert max(sizes) - min(sizes) <= 1
+            assert (owner >= 0).all()
+    lo, hi = C.c_int(0), C.c_int(0)
+    assert L.pgmvae_p2p_shard_bounds(0, 4, 2, 2, C.byref(lo), C.byref(hi)) != 0       # rank out of range
