@@ -23,12 +23,16 @@
 // three variables, so weights and activations are shared through L2.
 //
 // Epilogues (thread = accumulator row, 32 columns per tcgen05.ld, the next chunk in flight while
-// the current one is processed):
+// the current one is processed; bf16 rows leave / arrive as staged TMA tiles, the tile's bias is
+// staged in shared memory once per tile, fp32 rows leave through a transposing tile):
 //   FWD          bias + selu / sigmoid / none -> bf16 row (next layer's operand) and/or fp32 row
 //   SIGMOID_MSE  fd9: bias + sigmoid + squared / absolute error sums + d(loss)/d(pre-activation) in
 //                bf16 (leave-one-out column masked), core/model.py:53 + run.py:61
 //   DGRAD        (+ commitment gradient at the VQ boundary) x act'(activation below) -> bf16 row
 //   WGRAD_D / WGRAD_T  fp32 weight gradient
+// Every instantiation exists twice: the full-register one, and a SLIM one (144 registers, 3 KB less
+// shared memory) that leaves room on the SM for a CTA of the data-parallel exchange kernel
+// (model.cu: p2p_shard_adam_kernel) next to it.
 #include <cuda_bf16.h>
 #include <stdlib.h>
 #include <string.h>

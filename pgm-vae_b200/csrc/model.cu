@@ -14,6 +14,12 @@
 //   activations       H_l [Vg][B][P(out_l)] for one group of Vg variables at a time; networks
 //     of different variables are independent, so a step walks the variables group by group
 //     and the workspace is sized for one group.
+//
+// Data parallelism (new work; the reference is single-device, run.py:27-31): NCCL all-reduces
+// of gradients / EMA statistics / loss sums (comm.cu), or -- ranks of one node that can map
+// each other's buffers -- the peer-to-peer kernels below: a whole-buffer sum + Adam for narrow
+// models, and for wide models a per-variable-group reduce-scatter + Adam + all-gather in one
+// kernel that runs next to the GEMMs of the following group.
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
