@@ -11,9 +11,11 @@ on; it fits one GPU: ~58 GB).  Prints ONE JSON line on rank 0.
   value       whole-job training samples/s, batches already resident in HBM (device pointers)
   e2e         the same through the public API (core.model.VqVAE.train_on_batch) with PINNED HOST batches: H2D copy
               of the batch and D2H read of the loss inside every step
-  roofline    the dominant kernel of the step, from a per-kernel CUDA-event pass over the same steps
-  dp_parity   N > 1 only, outside the timed region: three steps through the data-parallel path on every rank vs the
-              same global batches on one GPU (rank 0) -- losses, weights, codebook, PLL counts; the run FAILS above 1e-3
+  roofline    the dominant kernel of the step, from a per-kernel CUDA-event pass over the same steps (`traffic`: DRAM bytes
+              of the launch named in `traffic_launch`, from the committed ncu capture profiles/r2_dram_traffic.json)
+  dp_parity   N > 1 only, outside the timed region: three steps through the data-parallel path on every rank (wide
+              models: the sharded peer-to-peer exchange fused with Adam) vs the same global batches on one GPU (rank 0)
+              -- losses, weights, Adam moments, codebook, PLL counts, replicas bit-identical; the run FAILS above 1e-3
   cpu_baseline / --impl reference : the CPU restatement of the reference (oracle/, torch-CPU fp32; TensorFlow itself is
               not installable in this image) timed on the host cores on a bounded sample
   pll_eval    stage 2 (encoder + VQ assignment + histogram) samples/s: sample-sharded, variable-sharded, e2e
