@@ -70,3 +70,34 @@ def test_only_the_result_line_reaches_stdout(tmp_path):
     assert r.returncode == 0, r.stderr
     assert r.stdout == json.dumps({"metric": "x", "value": 1.0}) + "\n"
     assert "NCCL version" in r.stderr and "noise from a library" in r.stderr
+
+
+def test_round2_default_line_is_cfg3_with_the_contract_keys():
+    d = load("bench_r2_cfg3_n1.json")
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks",
+              "pll_eval", "vq_assign", "cfg2"):
+        assert k in d, k
+    assert d["config"]["workload"].startswith("cfg3") and d["dtype"] == "bf16" and d["n_gpus"] == 1
+    r = d["roofline"]
+    assert r["bound"] == "tensor" and r["kernel"].startswith("dense_") and 0.3 < r["frac"] < 1
+    assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+    assert 0 < d["e2e"]["value"] <= d["value"] * 1.02 and d["e2e"]["h2d_bytes_per_step"] > 0
+    assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+
+
+@pytest.mark.parametrize("n", [2, 4, 8])
+def test_round2_multi_gpu_lines_carry_parity_of_the_sharded_exchange(n):
+    """Every multi-GPU line of the sharded peer-to-peer exchange carries its own correctness evidence: the
+    data-parallel run agrees with one GPU on the same global batches and the replicas are bit-identical."""
+    d = load(f"bench_r2_cfg3_n{n}_sharded.json")
+    one = load("bench_r2_cfg3_n1.json")
+    assert d["n_gpus"] == n and d["scaling"] == "weak"
+    assert d["config"]["global_batch"] == n * one["config"]["global_batch"]
+    assert 0.85 * n * one["value"] < d["value"] <= n * one["value"] * 1.05
+    p = d["dp_parity"]
+    assert p["world"] == n and p["sharded_exchange"] is True and p["replicas_identical"] is True and p["failed"] == []
+    for k in ("loss_rel", "weight_rel", "moment_rel", "count_l1", "pll_rel_sample_sharded", "pll_rel_variable_sharded"):
+        assert p[k] <= 1e-3, (k, p[k])
+    nccl = load(f"bench_r2_cfg3_n{n}.json")               # the NCCL exchange of the same round
+    assert d["value"] > nccl["value"]
