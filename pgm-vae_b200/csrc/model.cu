@@ -1171,15 +1171,22 @@ int run_step(pgmvae_model* m, const uint8_t* y, int y_on_device, int B, int glob
     const bool chain = use_chain(m) && out_dev == nullptr;
     bool overlapped = false, use_p2p = false, ema_done = false, ema_side = false;
     const bool do_update = !(flags & (STEP_NO_UPDATE | STEP_FWD_ONLY));
+    // wide models under data parallelism on one node: per variable group, reduce-scatter + Adam + all-gather as one
+    // kernel over peer memory (p2p_shard_adam_kernel) instead of NCCL all-reduces followed by a replicated Adam
+    const bool use_shard = comm != nullptr && !chain && m->p2p && m->p2p_shard && do_update;
+    if (do_update && !use_shard && m->p2p && m->state_sharded) {
+        // a replicated optimiser step would update fp32 master weights that are stale on the ranks that do not own them
+        pgmvae_set_error("train_step: the optimiser state of this model is sharded over the data-parallel ranks (sharded "
+                         "peer-to-peer exchange); call pgmvae_model_p2p_sync_state (VqVAE.sync_state) on EVERY rank before "
+                         "training it through another path");
+        return PGMVAE_EINVAL;
+    }
     const double b1 = 0.9, b2 = 0.999;
     float alpha = 0.f;
     if (do_update) {
         m->adam_t += 1;
         alpha = (float)((double)lr * sqrt(1.0 - pow(b2, (double)m->adam_t)) / (1.0 - pow(b1, (double)m->adam_t)));
     }
-    // wide models under data parallelism on one node: per variable group, reduce-scatter + Adam + all-gather as one
-    // kernel over peer memory (p2p_shard_adam_kernel) instead of NCCL all-reduces followed by a replicated Adam
-    const bool use_shard = comm != nullptr && !chain && m->p2p && m->p2p_shard && do_update;
     ShardSlice shard_s[24];
     const int shard_n = use_shard ? shard_slices(m, shard_s) : 0;
     ctx->coresident = use_shard;
