@@ -277,7 +277,8 @@ int pgmvae_model_set_adam_step(pgmvae_model* m, int64_t t);
  *     (any rank count up to 8; PGMVAE_P2P_SHARD=0 keeps NCCL).  The replicas stay bit-identical either way.
  * export: writes 6 x 64 bytes (CUDA IPC handles: gradients, flag block, parameters, bf16 mirror, Adam m, Adam v);
  * the host exchanges them (any side channel) and passes all of them, in rank order, to import.  Optional: without
- * it pgmvae_model_train_step reduces the gradients through the communicator.                                  */
+ * it pgmvae_model_train_step reduces the gradients through the communicator.  Every rank creates its model with the
+ * same shapes, max_batch and group-size settings (the ownership of the shards follows the variable groups).    */
 int pgmvae_model_p2p_export(pgmvae_model* m, void* handles_out384);
 int pgmvae_model_p2p_import(pgmvae_model* m, int rank, int nranks, const void* all_handles);
 /* After steps of the sharded exchange the Adam moments -- and, in bf16 mode, the fp32 master copy of the dense
