@@ -1,5 +1,6 @@
 """world_size-2 gloo tests (CPU) of the data-parallel host logic: batch sharding, global
-normalisation of the sharded gradients, EMA-statistic and PLL-count reductions.  Compute is
+normalisation of the sharded gradients, EMA-statistic and PLL-count reductions, and the sharded
+exchange (owner-computes reduce-scatter + Adam + all-gather, ownership from the library).  Compute is
 the oracle (this file is test code); the reductions go through pgmvae.dist.GlooComm, which
 has the interface of the NCCL communicator the product path uses."""
 import os
@@ -55,6 +56,105 @@ def _worker(rank, world, port, out):
         out.put("ok")
     dist.barrier()
     dist.destroy_process_group()
+
+
+def _adam_f32(p, m, v, g, t, lr=1e-3, b1=0.9, b2=0.999, eps=1e-7):
+    """Keras-form Adam in fp32, the expression of csrc/pll.cu: adam_kernel / csrc/model.cu: p2p_shard_adam_kernel"""
+    f = np.float32
+    alpha = f(lr * np.sqrt(1.0 - b2 ** t) / (1.0 - b1 ** t))
+    m = m + (g - m) * f(1.0 - b1)
+    v = v + (g * g - v) * f(1.0 - b2)
+    return p - (m * alpha) / (np.sqrt(v) + f(eps)), m, v
+
+
+def _worker_sharded(rank, world, port, out):
+    """The SHARDED exchange of csrc/model.cu (p2p_shard_adam_kernel) restated on CPU over gloo: per variable group the
+    owner of a variable (the library's own pgmvae_p2p_shard_bounds) sums the ranks' partial gradients in rank order,
+    applies Adam to its shard and hands the new values to everybody; moments stay with the owner until the gather.  Must
+    equal all-reduce + replicated Adam, leave the replicas bit-identical, and complete the moments after the gather."""
+    import ctypes as C
+    import hashlib
+    for p in (os.path.join(ROOT, "pgm-vae_b200"), os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
+        sys.path.insert(0, p)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(1)
+    import pgmvae_oracle as O
+    import np_expanded as NE
+    from pgmvae import _ffi
+    from pgmvae.dist import shard_bounds
+    L = _ffi.load_library()
+    units, V, D, K, B, Vg = [6, 5, 4, 3], 5, 2, 4, 22, 2           # variable groups {0,1} {2,3} {4}
+    params = {k: v.numpy().astype(np.float32) for k, v in O.init_params(units, V, D, K, seed=3).items()}
+    names = [n for n in params if n.startswith("fd")]              # the dense tensors ([V, ...]); EMA codebook: no Adam
+    mom_m = {n: np.zeros_like(params[n]) for n in names}
+    mom_v = {n: np.zeros_like(params[n]) for n in names}
+    ref_p = {n: params[n].copy() for n in names}
+    ref_m = {n: np.zeros_like(params[n]) for n in names}
+    ref_v = {n: np.zeros_like(params[n]) for n in names}
+    owner = np.full(V, -1)
+    for g0 in range(0, V, Vg):
+        for r in range(world):
+            lo, hi = C.c_int(), C.c_int()
+            assert L.pgmvae_p2p_shard_bounds(g0, min(Vg, V - g0), r, world, C.byref(lo), C.byref(hi)) == 0
+            owner[lo.value:hi.value] = r
+    assert (owner >= 0).all()
+    mine = owner == rank
+    for t in (1, 2):
+        y = O.synthetic_binary(B, V, seed=10 + t)
+        lo, hi = shard_bounds(B, rank, world)
+        full = dict(params)
+        _, g_local, _ = NE.step_grads(full, y[lo:hi], D, K, 0.25, True, global_B=B)
+        g32 = {n: g_local[n].astype(np.float32) for n in names}
+        gathered = [None] * world
+        dist.all_gather_object(gathered, g32)                       # "every rank maps every rank's gradient buffer"
+        for n in names:
+            g = gathered[0][n].copy()
+            for q in range(1, world):
+                g = g + gathered[q][n]                              # rank order, fp32
+            # replicated reference: every rank updates everything
+            ref_p[n], ref_m[n], ref_v[n] = _adam_f32(ref_p[n], ref_m[n], ref_v[n], g, t)
+            # sharded: only the owned variables
+            pn, mn, vn = _adam_f32(params[n][mine], mom_m[n][mine], mom_v[n][mine], g[mine], t)
+            params[n] = params[n].copy()
+            params[n][mine], mom_m[n][mine], mom_v[n][mine] = pn, mn, vn
+        handed = [None] * world
+        dist.all_gather_object(handed, {n: params[n][mine] for n in names})      # "writes into the buffers of all ranks"
+        for q in range(world):
+            for n in names:
+                params[n][owner == q] = handed[q][n]
+    for n in names:
+        np.testing.assert_array_equal(params[n], ref_p[n])          # same arithmetic, same order: bit-equal
+        assert not np.array_equal(mom_m[n], ref_m[n]) or mine.all()    # the moments are sharded ...
+    state = [None] * world
+    dist.all_gather_object(state, {n: (mom_m[n][mine], mom_v[n][mine]) for n in names})   # ... until the gather (sync_state)
+    for q in range(world):
+        for n in names:
+            mom_m[n][owner == q], mom_v[n][owner == q] = state[q][n]
+    for n in names:
+        np.testing.assert_array_equal(mom_m[n], ref_m[n])
+        np.testing.assert_array_equal(mom_v[n], ref_v[n])
+    digest = hashlib.sha1(b"".join(params[n].tobytes() for n in sorted(names))).hexdigest()
+    digests = [None] * world
+    dist.all_gather_object(digests, digest)
+    assert len(set(digests)) == 1
+    if rank == 0:
+        out.put("ok")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_exchange_equals_replicated_adam_gloo_world2():
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_worker_sharded, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(180)
+        assert p.exitcode == 0
+    assert out.get(timeout=5) == "ok"
 
 
 def test_data_parallel_reductions_gloo_world2():
